@@ -1,0 +1,770 @@
+// apm_capi.cu -- context, orchestration and the C ABI declared in include/apm_b200.h.
+//
+// One context = one data set on one GPU.  All bulk state lives in HBM:
+//   K, LB, Z        [max_chains][np][np]   prior covariance, chol(B) of the current Newton step, Z = (L_B^{-1} W^1/2 K)^T
+//   slot L_K, L_C   [n_slots][np][np]      the reference's cached_results (chol K, chol C), row-major lower
+//   slot mu         [n_slots][np]          f_post
+//   UT, F, Zf       [max_chains][Npad][np] transposed auxiliary normals, latent samples, L_K^{-1} f
+// np = n rounded up to 64; padded rows/cols carry the identity so every kernel works on whole tiles.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+
+#include "../../include/apm_b200.h"
+#include "tile_engine.cuh"
+#include "vec_kernels.cuh"
+
+using namespace apm;
+
+static thread_local std::string g_err;
+static void set_err(const std::string& s) { g_err = s; }
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            set_err(std::string(#expr) + ": " + cudaGetErrorString(e__));                             \
+            return (e__ == cudaErrorMemoryAllocation) ? APM_ERR_NOMEM : APM_ERR_CUDA;                 \
+        }                                                                                             \
+    } while (0)
+#define APM_TRY(expr)                 \
+    do {                              \
+        int r__ = (expr);             \
+        if (r__ != APM_OK) return r__; \
+    } while (0)
+
+enum { V_F = 0, V_W, V_WS, V_B, V_A, V_T, V_S, V_FNEW, V_COUNT };
+
+struct apm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int n = 0, D = 0, np = 0, nb = 0, P = 0, kind = 0;
+    double eps = 1e-8;
+    int maxB = 0, nslots = 0, maxN = 0, maxNpad = 0;
+    double tol = 1e-4;
+    int max_iters = 1000;
+    size_t mat = 0;  // np*np
+    double *dX = nullptr, *dy = nullptr;
+    double *dK = nullptr, *dLB = nullptr, *dZ = nullptr;
+    double *dSlotLK = nullptr, *dSlotLC = nullptr, *dSlotMu = nullptr, *dSlotLdK = nullptr, *dSlotLdC = nullptr;
+    double* dLdB = nullptr;
+    double* dVec[V_COUNT] = {nullptr};
+    double *dUT = nullptr, *dF = nullptr, *dZf = nullptr, *dUstage = nullptr;
+    double *dKp = nullptr, *dOut = nullptr, *dLogw = nullptr;
+    int *dStatus = nullptr, *dActive = nullptr, *dIters = nullptr, *dNActive = nullptr, *dSlotsA = nullptr, *dSlotsB = nullptr;
+    // pinned host staging
+    double *hKp = nullptr, *hOut = nullptr;
+    int *hInts = nullptr, *hNActive = nullptr;
+    std::vector<char> slot_valid;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+};
+
+template <typename T>
+static int dev_alloc(apm_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+    if (e != cudaSuccess) {
+        set_err(std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) + " bytes: " + cudaGetErrorString(e));
+        return APM_ERR_NOMEM;
+    }
+    c->allocs.push_back(q);
+    *p = (T*)q;
+    return APM_OK;
+}
+
+static int check_launch(apm_ctx* c, const char* what) {
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_err(std::string("launch ") + what + ": " + cudaGetErrorString(e));
+        return APM_ERR_CUDA;
+    }
+    return APM_OK;
+}
+
+static int g_attr_done = 0;
+static int set_kernel_attrs() {
+    if (g_attr_done) return APM_OK;
+    CU_TRY(cudaFuncSetAttribute(k_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_gemm_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_build_K, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU_TRY(cudaFuncSetAttribute(k_trsv2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU_TRY(cudaFuncSetAttribute(k_is_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    g_attr_done = 1;
+    return APM_OK;
+}
+
+extern "C" const char* apm_version(void) { return "apm_b200 0.1.0 (sm_100a, fp64 DMMA tile engine)"; }
+extern "C" const char* apm_last_error(void) { return g_err.c_str(); }
+
+extern "C" int apm_create(const double* X, const double* y, int n, int D, int kernel_kind, double epsilon,
+                          int max_chains, int n_slots, int max_nimp, int device, apm_ctx** out) {
+    if (!X || !y || !out || n <= 0 || D <= 0 || max_chains <= 0 || n_slots <= 0 || max_nimp <= 0 ||
+        (kernel_kind != APM_KERNEL_ISO && kernel_kind != APM_KERNEL_ARD)) {
+        set_err("apm_create: invalid argument");
+        return APM_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_err("apm_create: no CUDA device visible (apm_b200 has no CPU fallback)");
+        return APM_ERR_NOGPU;
+    }
+    if (device < 0 || device >= ndev) {
+        set_err("apm_create: bad device ordinal");
+        return APM_ERR_INVALID;
+    }
+    CU_TRY(cudaSetDevice(device));
+    APM_TRY(set_kernel_attrs());
+    apm_ctx* c = new apm_ctx();
+    c->device = device;
+    c->n = n;
+    c->D = D;
+    c->np = (n + TB - 1) / TB * TB;
+    c->nb = c->np / TB;
+    c->kind = kernel_kind;
+    c->P = (kernel_kind == APM_KERNEL_ARD) ? D + 1 : 2;
+    c->eps = epsilon;
+    c->maxB = max_chains;
+    c->nslots = n_slots;
+    c->maxN = max_nimp;
+    c->maxNpad = (max_nimp + TB - 1) / TB * TB;
+    c->mat = (size_t)c->np * c->np;
+    c->slot_valid.assign(n_slots, 0);
+    const size_t B = max_chains, np = c->np;
+    int rc = APM_OK;
+    auto A = [&](int r) { if (rc == APM_OK) rc = r; };
+    A(dev_alloc(c, &c->dX, np * D));
+    A(dev_alloc(c, &c->dy, np));
+    A(dev_alloc(c, &c->dK, B * c->mat));
+    A(dev_alloc(c, &c->dLB, B * c->mat));
+    A(dev_alloc(c, &c->dZ, B * c->mat));
+    A(dev_alloc(c, &c->dSlotLK, (size_t)n_slots * c->mat));
+    A(dev_alloc(c, &c->dSlotLC, (size_t)n_slots * c->mat));
+    A(dev_alloc(c, &c->dSlotMu, (size_t)n_slots * np));
+    A(dev_alloc(c, &c->dSlotLdK, (size_t)n_slots * c->nb));
+    A(dev_alloc(c, &c->dSlotLdC, (size_t)n_slots * c->nb));
+    A(dev_alloc(c, &c->dLdB, B * c->nb));
+    for (int v = 0; v < V_COUNT; v++) A(dev_alloc(c, &c->dVec[v], B * np));
+    const size_t usz = B * (size_t)c->maxNpad * np;
+    A(dev_alloc(c, &c->dUT, usz));
+    A(dev_alloc(c, &c->dF, usz));
+    A(dev_alloc(c, &c->dZf, usz));
+    A(dev_alloc(c, &c->dUstage, B * (size_t)n * max_nimp));
+    A(dev_alloc(c, &c->dKp, B * (size_t)(D + 1)));
+    A(dev_alloc(c, &c->dOut, B * 2));
+    A(dev_alloc(c, &c->dLogw, B * (size_t)max_nimp));
+    A(dev_alloc(c, &c->dStatus, B));
+    A(dev_alloc(c, &c->dActive, B));
+    A(dev_alloc(c, &c->dIters, B));
+    A(dev_alloc(c, &c->dNActive, 4));
+    A(dev_alloc(c, &c->dSlotsA, B));
+    A(dev_alloc(c, &c->dSlotsB, B));
+    if (rc != APM_OK) {
+        apm_destroy(c);
+        return rc;
+    }
+    if (cudaMallocHost(&c->hKp, B * (D + 1) * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost(&c->hOut, B * 2 * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost(&c->hInts, B * 4 * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&c->hNActive, 4 * sizeof(int)) != cudaSuccess) {
+        set_err("apm_create: pinned host allocation failed");
+        apm_destroy(c);
+        return APM_ERR_NOMEM;
+    }
+    // data set: X padded with zero rows, y padded with +1
+    std::vector<double> Xp(np * D, 0.0), yp(np, 1.0);
+    memcpy(Xp.data(), X, sizeof(double) * (size_t)n * D);
+    memcpy(yp.data(), y, sizeof(double) * n);
+    for (int i = 0; i < n; i++) {
+        if (!(y[i] == 1.0 || y[i] == -1.0)) {
+            set_err("apm_create: targets y must be +1 / -1 (lpa.py:86 multiplies y*f)");
+            apm_destroy(c);
+            return APM_ERR_INVALID;
+        }
+    }
+    cudaError_t e = cudaMemcpy(c->dX, Xp.data(), sizeof(double) * np * D, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(c->dy, yp.data(), sizeof(double) * np, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(c->dStatus, 0, sizeof(int) * B);
+    if (e != cudaSuccess) {
+        set_err(std::string("apm_create: upload: ") + cudaGetErrorString(e));
+        apm_destroy(c);
+        return APM_ERR_CUDA;
+    }
+    *out = c;
+    return APM_OK;
+}
+
+extern "C" int apm_destroy(apm_ctx* c) {
+    if (!c) return APM_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->hKp) cudaFreeHost(c->hKp);
+    if (c->hOut) cudaFreeHost(c->hOut);
+    if (c->hInts) cudaFreeHost(c->hInts);
+    if (c->hNActive) cudaFreeHost(c->hNActive);
+    delete c;
+    return APM_OK;
+}
+
+extern "C" int apm_set_stream(apm_ctx* c, uint64_t s) {
+    if (!c) return APM_ERR_INVALID;
+    c->stream = (cudaStream_t)(uintptr_t)s;
+    return APM_OK;
+}
+extern "C" int apm_synchronize(apm_ctx* c) {
+    if (!c) return APM_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return APM_OK;
+}
+extern "C" int apm_set_newton(apm_ctx* c, double tol, int max_iters) {
+    if (!c || !(tol > 0) || max_iters <= 0) return APM_ERR_INVALID;
+    c->tol = tol;
+    c->max_iters = max_iters;
+    return APM_OK;
+}
+extern "C" int apm_get_info(apm_ctx* c, int* n, int* D, int* n_pad, int* n_theta, int* n_slots, int* max_chains,
+                            int* max_nimp) {
+    if (!c) return APM_ERR_INVALID;
+    if (n) *n = c->n;
+    if (D) *D = c->D;
+    if (n_pad) *n_pad = c->np;
+    if (n_theta) *n_theta = c->P;
+    if (n_slots) *n_slots = c->nslots;
+    if (max_chains) *max_chains = c->maxB;
+    if (max_nimp) *max_nimp = c->maxN;
+    return APM_OK;
+}
+extern "C" int64_t apm_launch_count(apm_ctx* c, int reset) {
+    if (!c) return 0;
+    int64_t v = c->launches;
+    if (reset) c->launches = 0;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// building blocks
+// ------------------------------------------------------------------------------------------------
+static int check_B(apm_ctx* c, int B) {
+    if (!c || B <= 0 || B > c->maxB) {
+        set_err("batch size B out of range for this context (1..max_chains)");
+        return APM_ERR_INVALID;
+    }
+    CU_TRY(cudaSetDevice(c->device));
+    return APM_OK;
+}
+
+static int reset_status(apm_ctx* c, int B) {
+    CU_TRY(cudaMemsetAsync(c->dStatus, 0, sizeof(int) * B, c->stream));
+    return APM_OK;
+}
+
+// sigma = exp(theta0); ARD: tau_k = exp(theta_k); ISO: 2 tau^2 -- host libm, as the reference's libc exp
+static int upload_kernel_params(apm_ctx* c, const double* theta, int B, int kind) {
+    const int P = (kind == APM_KERNEL_ARD) ? c->D + 1 : 2;
+    const int stride = c->D + 1;
+    for (int b = 0; b < B; b++) {
+        const double* th = theta + (size_t)b * P;
+        double* kp = c->hKp + (size_t)b * stride;
+        kp[0] = exp(th[0]);
+        if (kind == APM_KERNEL_ARD) {
+            for (int k = 0; k < c->D; k++) kp[1 + k] = exp(th[1 + k]);
+        } else {
+            const double tau = exp(th[1]);
+            kp[1] = 2. * (tau * tau);
+        }
+    }
+    CU_TRY(cudaMemcpyAsync(c->dKp, c->hKp, sizeof(double) * (size_t)B * stride, cudaMemcpyHostToDevice, c->stream));
+    return APM_OK;
+}
+
+static int build_K(apm_ctx* c, int B, int kind, double eps) {
+    KBuildParams p;
+    p.X = c->dX; p.n = c->n; p.D = c->D; p.np = c->np; p.nb = c->nb;
+    p.kp = c->dKp; p.kp_stride = c->D + 1;
+    p.ard = (kind == APM_KERNEL_ARD); p.eps = eps;
+    p.K = c->dK; p.k_bs = (long long)c->mat;
+    p.ntiles = c->nb * (c->nb + 1) / 2;
+    const size_t smem = (size_t)(2 * 64 * c->D + 64 * TSP + c->D + 1) * sizeof(double);
+    if (smem > 96 * 1024) {
+        set_err("build_K: feature dimension too large for the shared-memory staging of X");
+        return APM_ERR_INVALID;
+    }
+    k_build_K<<<B * p.ntiles, 256, smem, c->stream>>>(p);
+    return check_launch(c, "k_build_K");
+}
+
+static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, const int* src_idx, double* dst,
+                    long long dst_bs, const int* dst_idx, const double* scale, int add_identity, double* logdet_parts,
+                    const int* logdet_idx, int fail_code, const int* active) {
+    CholParams p;
+    p.src = src; p.src_bs = src_bs; p.lds = c->np; p.src_idx = src_idx;
+    p.dst = dst; p.dst_bs = dst_bs; p.ldd = c->np; p.dst_idx = dst_idx;
+    p.scale = scale; p.scale_bs = c->np;
+    p.add_identity = add_identity;
+    p.nb = c->nb;
+    p.logdet_parts = logdet_parts; p.logdet_stride = c->nb; p.logdet_idx = logdet_idx;
+    p.status = c->dStatus; p.fail_code = fail_code;
+    p.active = active;
+    p.nchains = B;
+    for (int k = -1; k <= c->nb - 2; k++) {
+        const int grid = (k < 0) ? B : B * (c->nb - k - 1);
+        k_chol_step<<<grid, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(p, k);
+        APM_TRY(check_launch(c, "k_chol_step"));
+    }
+    return APM_OK;
+}
+
+static NewtonVecs make_nv(apm_ctx* c) {
+    NewtonVecs nv;
+    nv.f = c->dVec[V_F]; nv.W = c->dVec[V_W]; nv.Ws = c->dVec[V_WS]; nv.bvec = c->dVec[V_B];
+    nv.a = c->dVec[V_A]; nv.t = c->dVec[V_T]; nv.s = c->dVec[V_S]; nv.fnew = c->dVec[V_FNEW];
+    nv.vs = c->np; nv.y = c->dy; nv.n = c->n; nv.np = c->np;
+    nv.active = c->dActive; nv.iters = c->dIters; nv.status = c->dStatus; nv.n_active = c->dNActive;
+    nv.tol = c->tol; nv.max_iters = c->max_iters;
+    return nv;
+}
+
+// Newton mode search (lpa.py:81-102) for chains 0..B-1 whose K sits in c->dK.  On exit f (V_F) is the
+// mode, LB / Ws / a are those of the last executed iteration of each chain, dIters the iteration counts.
+static int run_newton(apm_ctx* c, int B) {
+    NewtonVecs nv = make_nv(c);
+    CU_TRY(cudaMemsetAsync(nv.f, 0, sizeof(double) * (size_t)B * c->np, c->stream));
+    CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
+    k_fill_int<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dActive, 1, B);
+    APM_TRY(check_launch(c, "k_fill_int"));
+    k_fill_int<<<1, 32, 0, c->stream>>>(c->dNActive, B, 1);
+    APM_TRY(check_launch(c, "k_fill_int"));
+    const size_t trsv_smem = (size_t)(c->np + 64 * TSP + 64) * sizeof(double);
+    if (trsv_smem > 160 * 1024) {
+        set_err("run_newton: n too large for the single-CTA triangular solve");
+        return APM_ERR_INVALID;
+    }
+    const dim3 mv_grid(c->np / 32, B);
+    for (int it = 0; it < c->max_iters; it++) {
+        k_newton_prep<<<B, 256, 0, c->stream>>>(nv);
+        APM_TRY(check_launch(c, "k_newton_prep"));
+        // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b))
+        k_matvec<<<mv_grid, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, c->np, nv.bvec, nv.Ws, nv.t, c->np,
+                                                 c->dActive, c->dStatus);
+        APM_TRY(check_launch(c, "k_matvec"));
+        // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
+        APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
+                         nullptr, APM_CHAIN_CHOL_B, c->dActive));
+        // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
+        k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, nv);
+        APM_TRY(check_launch(c, "k_trsv2"));
+        // f_new = K a                                              (lpa.py:95)
+        k_matvec<<<mv_grid, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, c->np, nv.a, nullptr, nv.fnew, c->np,
+                                                 c->dActive, c->dStatus);
+        APM_TRY(check_launch(c, "k_matvec"));
+        k_newton_finish<<<B, 256, 0, c->stream>>>(nv);
+        APM_TRY(check_launch(c, "k_newton_finish"));
+        CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (c->hNActive[0] <= 0) break;
+    }
+    return APM_OK;
+}
+
+// C = K - Z Z^T with Z L_B^T = K W^1/2  (lpa.py:111-112), lower tiles into dst
+static int run_covariance(apm_ctx* c, int B, double* dst, long long dst_bs, const int* dst_idx) {
+    TrsmParams t;
+    t.R = c->dK; t.r_bs = (long long)c->mat; t.ldr = c->np; t.r_idx = nullptr;
+    t.cs = c->dVec[V_WS]; t.cs_bs = c->np;
+    t.X = c->dZ; t.x_bs = (long long)c->mat; t.ldx = c->np;
+    t.L = c->dLB; t.l_bs = (long long)c->mat; t.ldl = c->np; t.l_idx = nullptr;
+    t.nb = c->nb; t.row_blocks = c->nb;
+    t.status = c->dStatus; t.active = nullptr;
+    k_trsm_rows<<<B * c->nb, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
+    APM_TRY(check_launch(c, "k_trsm_rows"));
+    SyrkParams s;
+    s.S = c->dK; s.s_bs = (long long)c->mat; s.lds = c->np;
+    s.Z = c->dZ; s.z_bs = (long long)c->mat; s.ldz = c->np;
+    s.C = dst; s.c_bs = dst_bs; s.ldc = c->np; s.c_idx = dst_idx;
+    s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
+    s.status = c->dStatus;
+    k_syrk_sub<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
+    return check_launch(c, "k_syrk_sub");
+}
+
+// bring u (reference layout [B][n][N]) into UT [B][Npad][np]
+static int stage_u(apm_ctx* c, const double* u, int u_on_device, int N, int B) {
+    if (N <= 0 || N > c->maxN) {
+        set_err("N (importance samples) out of range for this context");
+        return APM_ERR_INVALID;
+    }
+    const double* du = u;
+    if (!u_on_device) {
+        CU_TRY(cudaMemcpyAsync(c->dUstage, u, sizeof(double) * (size_t)B * c->n * N, cudaMemcpyHostToDevice, c->stream));
+        du = c->dUstage;
+    }
+    const int Npad = (N + TB - 1) / TB * TB;
+    dim3 grid(c->np / 32, Npad / 32, B), block(32, 8);
+    k_transpose_u<<<grid, block, 0, c->stream>>>(du, (long long)c->n * N, c->n, N, c->dUT, (long long)Npad * c->np, c->np,
+                                                 Npad);
+    return check_launch(c, "k_transpose_u");
+}
+
+// the O(n^2 N) tail (estimators.py:221-241) for chains whose caches sit in slots dSlots[b]
+static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_logml, double* d_logw, int mode) {
+    const int Npad = (N + TB - 1) / TB * TB;
+    const int rblocks = Npad / TB;
+    const long long ubs = (long long)Npad * c->np;
+    GemmTriParams g;
+    g.UT = c->dUT; g.u_bs = ubs; g.ldu = c->np;
+    g.L = (mode == 0) ? c->dSlotLC : c->dSlotLK; g.l_bs = (long long)c->mat; g.ldl = c->np; g.l_idx = dSlots;
+    g.mu = (mode == 0) ? c->dSlotMu : nullptr; g.mu_bs = c->np; g.mu_idx = dSlots;
+    g.F = c->dF; g.f_bs = ubs; g.ldf = c->np;
+    g.nb = c->nb; g.row_blocks = rblocks;
+    g.status = c->dStatus;
+    k_gemm_tri<<<B * c->nb * rblocks, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(g);
+    APM_TRY(check_launch(c, "k_gemm_tri"));
+    if (mode == 0) {
+        TrsmParams t;
+        t.R = c->dF; t.r_bs = ubs; t.ldr = c->np; t.r_idx = nullptr;
+        t.cs = nullptr; t.cs_bs = 0;
+        t.X = c->dZf; t.x_bs = ubs; t.ldx = c->np;
+        t.L = c->dSlotLK; t.l_bs = (long long)c->mat; t.ldl = c->np; t.l_idx = dSlots;
+        t.nb = c->nb; t.row_blocks = rblocks;
+        t.status = c->dStatus; t.active = nullptr;
+        k_trsm_rows<<<B * rblocks, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
+        APM_TRY(check_launch(c, "k_trsm_rows"));
+    }
+    EpilogueParams e;
+    e.F = c->dF; e.Zf = c->dZf; e.UT = c->dUT; e.bs = ubs; e.ld = c->np;
+    e.y = c->dy; e.n = c->n; e.N = N;
+    e.logdetK = c->dSlotLdK; e.logdetC = c->dSlotLdC; e.ld_stride = c->nb; e.nb = c->nb; e.slot_idx = dSlots;
+    e.status = c->dStatus;
+    e.logml = d_logml; e.logw = d_logw;
+    e.mode = mode;
+    k_is_epilogue<<<B, 256, sizeof(double) * N, c->stream>>>(e);
+    return check_launch(c, "k_is_epilogue");
+}
+
+static int upload_slots(apm_ctx* c, const int* slots, int B, int* dSlots, bool require_valid) {
+    for (int b = 0; b < B; b++) {
+        if (slots[b] < 0 || slots[b] >= c->nslots) {
+            set_err("slot index out of range");
+            return APM_ERR_INVALID;
+        }
+        if (require_valid && !c->slot_valid[slots[b]]) {
+            set_err("slot " + std::to_string(slots[b]) + " holds no valid cache");
+            return APM_ERR_INVALID;
+        }
+        c->hInts[b] = slots[b];
+    }
+    CU_TRY(cudaMemcpyAsync(dSlots, c->hInts, sizeof(int) * B, cudaMemcpyHostToDevice, c->stream));
+    // hInts is re-used by the caller only after a stream sync
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return APM_OK;
+}
+
+static int fetch_results(apm_ctx* c, int B, double* out_d, int n_out, double* out_h, int* iters_h, int iters_add,
+                         int* status_h) {
+    if (out_h) CU_TRY(cudaMemcpyAsync(c->hOut, out_d, sizeof(double) * (size_t)B * n_out, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->hInts, c->dIters, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->hInts + B, c->dStatus, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (out_h) memcpy(out_h, c->hOut, sizeof(double) * (size_t)B * n_out);
+    for (int b = 0; b < B; b++) {
+        if (iters_h) iters_h[b] = c->hInts[b] + iters_add;
+        if (status_h) status_h[b] = c->hInts[B + b];
+    }
+    return APM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: kernels
+// ------------------------------------------------------------------------------------------------
+extern "C" int apm_kernel_build(apm_ctx* c, const double* theta, int B, int kernel_kind, double epsilon, double* K_out,
+                                int K_on_device) {
+    APM_TRY(check_B(c, B));
+    if (!theta || !K_out) return APM_ERR_INVALID;
+    const int kind = kernel_kind < 0 ? c->kind : kernel_kind;
+    const double eps = epsilon < 0 ? c->eps : epsilon;
+    APM_TRY(upload_kernel_params(c, theta, B, kind));
+    APM_TRY(build_K(c, B, kind, eps));
+    const size_t n = c->n;
+    for (int b = 0; b < B; b++) {
+        CU_TRY(cudaMemcpy2DAsync(K_out + (size_t)b * n * n, n * sizeof(double), c->dK + (size_t)b * c->mat,
+                                 (size_t)c->np * sizeof(double), n * sizeof(double), n,
+                                 K_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return APM_OK;
+}
+
+static int import_matrices(apm_ctx* c, const double* M, int on_device, int B, double* dst, long long dst_bs) {
+    const size_t n = c->n;
+    for (int b = 0; b < B; b++) {
+        CU_TRY(cudaMemcpy2DAsync(dst + (size_t)b * dst_bs, (size_t)c->np * sizeof(double), M + (size_t)b * n * n,
+                                 n * sizeof(double), n * sizeof(double), n,
+                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    }
+    if (c->np > c->n) {
+        dim3 grid(64, B);
+        k_pad_identity<<<grid, 256, 0, c->stream>>>(dst, dst_bs, c->n, c->np);
+        APM_TRY(check_launch(c, "k_pad_identity"));
+    }
+    return APM_OK;
+}
+
+extern "C" int apm_laplace(apm_ctx* c, const double* K, int K_on_device, int B, int calc_cov, int calc_lml, double* f_out,
+                           double* C_out, int C_on_device, double* lml_out, int* cubic_ops_out, int* chain_status) {
+    APM_TRY(check_B(c, B));
+    if (!K) return APM_ERR_INVALID;
+    APM_TRY(reset_status(c, B));
+    APM_TRY(import_matrices(c, K, K_on_device, B, c->dK, (long long)c->mat));
+    APM_TRY(run_newton(c, B));
+    NewtonVecs nv = make_nv(c);
+    if (calc_lml) {
+        k_laplace_lml<<<B, 256, 0, c->stream>>>(nv, c->dLdB, c->nb, c->nb, c->dOut);
+        APM_TRY(check_launch(c, "k_laplace_lml"));
+    }
+    if (calc_cov && C_out) {
+        // C (lower tiles) -> LB buffer (chol(B) is dead after the triangular solve), then a dense symmetric export
+        APM_TRY(run_covariance(c, B, c->dLB, (long long)c->mat, nullptr));
+        const size_t n = c->n;
+        for (int b = 0; b < B; b++) {
+            dim3 grid((c->n + 255) / 256, c->n);
+            k_export_lower<<<grid, 256, 0, c->stream>>>(c->dLB + (size_t)b * c->mat, c->np, c->n, c->dZ + (size_t)b * c->mat, 1);
+            APM_TRY(check_launch(c, "k_export_lower"));
+            CU_TRY(cudaMemcpyAsync(C_out + (size_t)b * n * n, c->dZ + (size_t)b * c->mat, sizeof(double) * n * n,
+                                   C_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    if (f_out) {
+        CU_TRY(cudaMemcpy2DAsync(f_out, (size_t)c->n * sizeof(double), nv.f, (size_t)c->np * sizeof(double),
+                                 (size_t)c->n * sizeof(double), B, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return fetch_results(c, B, c->dOut, 1, calc_lml ? lml_out : nullptr, cubic_ops_out, calc_cov ? 1 : 0, chain_status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: estimators
+// ------------------------------------------------------------------------------------------------
+static int full_front(apm_ctx* c, const double* theta, int B, const int* slots) {
+    APM_TRY(reset_status(c, B));
+    APM_TRY(upload_slots(c, slots, B, c->dSlotsA, false));
+    for (int b = 0; b < B; b++) c->slot_valid[slots[b]] = 0;
+    APM_TRY(upload_kernel_params(c, theta, B, c->kind));
+    APM_TRY(build_K(c, B, c->kind, c->eps));
+    // chol(K) -> slot L_K                                                         (estimators.py:206)
+    return run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dSlotLK, (long long)c->mat, c->dSlotsA, nullptr, 0,
+                    c->dSlotLdK, c->dSlotsA, APM_CHAIN_CHOL_K, nullptr);
+}
+
+extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
+                                 const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status) {
+    APM_TRY(check_B(c, B));
+    if (!theta || !u || !slots || !logml_out) return APM_ERR_INVALID;
+    APM_TRY(full_front(c, theta, B, slots));
+    APM_TRY(stage_u(c, u, u_on_device, N, B));
+    APM_TRY(run_newton(c, B));                                                  // estimators.py:207 -> lpa.py:81-102
+    APM_TRY(run_covariance(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA));    // lpa.py:111-112
+    // chol(C) in place in the slot                                                estimators.py:209
+    APM_TRY(run_chol(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA, c->dSlotLC, (long long)c->mat, c->dSlotsA, nullptr,
+                     0, c->dSlotLdC, c->dSlotsA, APM_CHAIN_CHOL_C, nullptr));
+    dim3 cg((c->np + 255) / 256, B);
+    k_copy_vec<<<cg, 256, 0, c->stream>>>(c->dVec[V_F], c->np, nullptr, c->dSlotMu, c->np, c->dSlotsA, c->np, c->dStatus);
+    APM_TRY(check_launch(c, "k_copy_vec"));
+    APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, nullptr, 0));
+    std::vector<int> st(B);
+    APM_TRY(fetch_results(c, B, c->dOut, 1, logml_out, cubic_ops_out, 3, st.data()));  // iters + 1 + 2 (est.py:217)
+    for (int b = 0; b < B; b++) {
+        c->slot_valid[slots[b]] = (st[b] == 0);
+        if (chain_status) chain_status[b] = st[b];
+    }
+    return APM_OK;
+}
+
+static int cached_common(apm_ctx* c, const int* slots, const double* u, int u_on_device, int N, int B, double* logml_out,
+                         double* logw_out, int* chain_status) {
+    APM_TRY(check_B(c, B));
+    if (!slots || !u) return APM_ERR_INVALID;
+    APM_TRY(reset_status(c, B));
+    APM_TRY(upload_slots(c, slots, B, c->dSlotsA, true));
+    APM_TRY(stage_u(c, u, u_on_device, N, B));
+    APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, logw_out ? c->dLogw : nullptr, 0));
+    if (logw_out) CU_TRY(cudaMemcpyAsync(logw_out, c->dLogw, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
+    return fetch_results(c, B, c->dOut, 1, logml_out, nullptr, 0, chain_status);
+}
+
+extern "C" int apm_estimate_cached(apm_ctx* c, const int* slots, const double* u, int u_on_device, int N, int B,
+                                   double* logml_out, int* chain_status) {
+    if (!logml_out) return APM_ERR_INVALID;
+    return cached_common(c, slots, u, u_on_device, N, B, logml_out, nullptr, chain_status);
+}
+
+extern "C" int apm_estimate_cached_weights(apm_ctx* c, const int* slots, const double* u, int u_on_device, int N, int B,
+                                           double* logw_out) {
+    if (!logw_out) return APM_ERR_INVALID;
+    return cached_common(c, slots, u, u_on_device, N, B, nullptr, logw_out, nullptr);
+}
+
+extern "C" int apm_laplace_lml(apm_ctx* c, const double* theta, int B, double* lml_out, int* cubic_ops_out,
+                               int* chain_status) {
+    APM_TRY(check_B(c, B));
+    if (!theta || !lml_out) return APM_ERR_INVALID;
+    APM_TRY(reset_status(c, B));
+    APM_TRY(upload_kernel_params(c, theta, B, c->kind));
+    APM_TRY(build_K(c, B, c->kind, c->eps));
+    APM_TRY(run_newton(c, B));
+    NewtonVecs nv = make_nv(c);
+    k_laplace_lml<<<B, 256, 0, c->stream>>>(nv, c->dLdB, c->nb, c->nb, c->dOut);
+    APM_TRY(check_launch(c, "k_laplace_lml"));
+    return fetch_results(c, B, c->dOut, 1, lml_out, cubic_ops_out, 0, chain_status);
+}
+
+extern "C" int apm_estimate_prior_mc(apm_ctx* c, const double* theta, const int* slots, const double* u, int u_on_device,
+                                     int N, int B, double* logml_out, int* chain_status) {
+    APM_TRY(check_B(c, B));
+    if (!slots || !u || !logml_out) return APM_ERR_INVALID;
+    if (theta) {
+        APM_TRY(full_front(c, theta, B, slots));
+    } else {
+        APM_TRY(reset_status(c, B));
+        APM_TRY(upload_slots(c, slots, B, c->dSlotsA, false));
+    }
+    APM_TRY(stage_u(c, u, u_on_device, N, B));
+    APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, nullptr, 1));
+    CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
+    return fetch_results(c, B, c->dOut, 1, logml_out, nullptr, 0, chain_status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: slots
+// ------------------------------------------------------------------------------------------------
+__global__ void k_logdet_parts(const double* L, int np, double* parts) {
+    const int k = blockIdx.x, r = k * 64 + threadIdx.x;  // 64 threads
+    double lg = log(L[(size_t)r * np + r]);
+    lg = warp_sum(lg);
+    __shared__ double red[2];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lg;
+    __syncthreads();
+    if (threadIdx.x == 0) parts[k] = red[0] + red[1];
+}
+
+extern "C" int apm_slot_export(apm_ctx* c, int slot, double* K_chol, double* C_chol, double* f_post, double* logdets2) {
+    if (!c || slot < 0 || slot >= c->nslots) return APM_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t n = c->n;
+    dim3 grid((c->n + 255) / 256, c->n);
+    double* stage = c->dZ;  // scratch (dense n x n)
+    if (K_chol) {
+        k_export_lower<<<grid, 256, 0, c->stream>>>(c->dSlotLK + (size_t)slot * c->mat, c->np, c->n, stage, 0);
+        APM_TRY(check_launch(c, "k_export_lower"));
+        CU_TRY(cudaMemcpyAsync(K_chol, stage, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if (C_chol) {
+        k_export_lower<<<grid, 256, 0, c->stream>>>(c->dSlotLC + (size_t)slot * c->mat, c->np, c->n, stage, 0);
+        APM_TRY(check_launch(c, "k_export_lower"));
+        CU_TRY(cudaMemcpyAsync(C_chol, stage, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if (f_post) CU_TRY(cudaMemcpyAsync(f_post, c->dSlotMu + (size_t)slot * c->np, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (logdets2) {
+        std::vector<double> a(c->nb), b(c->nb);
+        CU_TRY(cudaMemcpyAsync(a.data(), c->dSlotLdK + (size_t)slot * c->nb, sizeof(double) * c->nb, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(b.data(), c->dSlotLdC + (size_t)slot * c->nb, sizeof(double) * c->nb, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        logdets2[0] = logdets2[1] = 0.0;
+        for (int k = 0; k < c->nb; k++) {
+            logdets2[0] += a[k];
+            logdets2[1] += b[k];
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return APM_OK;
+}
+
+extern "C" int apm_slot_import(apm_ctx* c, int slot, const double* K_chol, const double* C_chol, const double* f_post) {
+    if (!c || slot < 0 || slot >= c->nslots || !K_chol) return APM_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->device));
+    APM_TRY(import_matrices(c, K_chol, 0, 1, c->dSlotLK + (size_t)slot * c->mat, (long long)c->mat));
+    k_logdet_parts<<<c->nb, 64, 0, c->stream>>>(c->dSlotLK + (size_t)slot * c->mat, c->np, c->dSlotLdK + (size_t)slot * c->nb);
+    APM_TRY(check_launch(c, "k_logdet_parts"));
+    if (C_chol) {
+        APM_TRY(import_matrices(c, C_chol, 0, 1, c->dSlotLC + (size_t)slot * c->mat, (long long)c->mat));
+        k_logdet_parts<<<c->nb, 64, 0, c->stream>>>(c->dSlotLC + (size_t)slot * c->mat, c->np, c->dSlotLdC + (size_t)slot * c->nb);
+        APM_TRY(check_launch(c, "k_logdet_parts"));
+    }
+    if (f_post) {
+        CU_TRY(cudaMemsetAsync(c->dSlotMu + (size_t)slot * c->np, 0, sizeof(double) * c->np, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->dSlotMu + (size_t)slot * c->np, f_post, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->slot_valid[slot] = 1;
+    return APM_OK;
+}
+
+extern "C" int apm_slot_copy(apm_ctx* c, const int* src, const int* dst, int B) {
+    if (!c || !src || !dst || B <= 0) return APM_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->device));
+    for (int b = 0; b < B; b++) {
+        if (src[b] < 0 || src[b] >= c->nslots || dst[b] < 0 || dst[b] >= c->nslots) return APM_ERR_INVALID;
+        if (src[b] == dst[b]) continue;
+        const size_t s = src[b], d = dst[b];
+        CU_TRY(cudaMemcpyAsync(c->dSlotLK + d * c->mat, c->dSlotLK + s * c->mat, sizeof(double) * c->mat, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->dSlotLC + d * c->mat, c->dSlotLC + s * c->mat, sizeof(double) * c->mat, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->dSlotMu + d * c->np, c->dSlotMu + s * c->np, sizeof(double) * c->np, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->dSlotLdK + d * c->nb, c->dSlotLdK + s * c->nb, sizeof(double) * c->nb, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->dSlotLdC + d * c->nb, c->dSlotLdC + s * c->nb, sizeof(double) * c->nb, cudaMemcpyDeviceToDevice, c->stream));
+        c->slot_valid[d] = c->slot_valid[s];
+    }
+    return APM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp64 peak probes
+// ------------------------------------------------------------------------------------------------
+extern "C" int apm_measure_fp64_peak(int device, int kind, double* tflops) {
+    if (!tflops) return APM_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_err("no CUDA device visible");
+        return APM_ERR_NOGPU;
+    }
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CU_TRY(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    const int iters = 20000, threads = 256, blocks = prop.multiProcessorCount * 4;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU_TRY(cudaEventRecord(e0));
+        if (kind == 0) k_peak_dmma<<<blocks, threads>>>(d, iters);
+        else k_peak_dfma<<<blocks, threads>>>(d, iters);
+        CU_TRY(cudaEventRecord(e1));
+        CU_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        // DMMA: 8 mma per iter per warp, 2*8*8*4 flop each; DFMA: 16 fma per iter per thread, 2 flop each
+        const double flop = (kind == 0) ? (double)blocks * (threads / 32) * iters * 8.0 * 512.0
+                                        : (double)blocks * threads * iters * 16.0 * 2.0;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return APM_OK;
+}

@@ -1,0 +1,460 @@
+// tile_engine.cuh -- blocked fp64 dense kernels on 64x64 tiles, batched over chains.
+//
+// Everything O(n^3) in the reference's hot path (LAPACK dpotrf/dpotrs and BLAS dgemm reached through
+// scipy: lpa.py:92, 111-112; estimators.py:206, 209, 223, 225) is expressed with four kernels that share
+// one DMMA micro-kernel (acc += A * B^T on a 64x64 tile, both operands row-major with k contiguous):
+//
+//   k_chol_step   left-looking blocked Cholesky, one launch per block column, with the next diagonal
+//                 block factorised by the CTA that produced the panel block above it (look-ahead)
+//   k_trsm_rows   X L^T = R for a 64-row panel of right-hand sides, one CTA walks all block columns
+//   k_syrk_sub    C = S - Z Z^T (lower tiles)
+//   k_gemm_tri    F = mu + U^T L^T (lower-triangular L, block column ranges clipped)
+//
+// The 64x64 diagonal factorisation and the triangular solve keep one matrix row per thread in registers
+// (thread-per-row substitution; column broadcast through shared memory).
+#pragma once
+#include "common.cuh"
+
+namespace apm {
+
+// ------------------------------------------------------------------------------------------------
+// DMMA micro-kernel: acc(64x64) += A(64 x kdepth) * B(64 x kdepth)^T.  128 threads = 2x2 warps, each
+// warp owns a 32x32 block = 4x4 m8n8 tiles.  A/B k-chunks are staged by a 4-deep cp.async pipeline.
+// ------------------------------------------------------------------------------------------------
+struct Acc {
+    double v[4][4][2];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[i][j][0] = v[i][j][1] = 0.0;
+    }
+};
+
+__device__ __forceinline__ void gemm_load_stage(double* smA, double* smB, const double* __restrict__ A, int lda,
+                                                const double* __restrict__ Bm, int ldb, int k0, int tid) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int seg = tid + q * TILE_THREADS;  // 512 16-byte segments per operand per stage
+        const int row = seg >> 3, cs = (seg & 7) * 2;
+        cp_async16(smA + row * KCP + cs, A + (size_t)row * lda + k0 + cs);
+        cp_async16(smB + row * KCP + cs, Bm + (size_t)row * ldb + k0 + cs);
+    }
+}
+
+__device__ __forceinline__ void gemm_nt_64x64(Acc& acc, const double* __restrict__ A, int lda,
+                                              const double* __restrict__ Bm, int ldb, int kdepth, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double* smA = smem;
+    double* smB = smem + STAGES * TB * KCP;
+    const int nchunks = kdepth / KC;
+    if (nchunks == 0) return;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nchunks) gemm_load_stage(smA + s * TB * KCP, smB + s * TB * KCP, A, lda, Bm, ldb, s * KC, tid);
+        cp_async_commit();
+    }
+    for (int kc = 0; kc < nchunks; kc++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nk = kc + STAGES - 1;
+            if (nk < nchunks) {
+                const int st = nk % STAGES;
+                gemm_load_stage(smA + st * TB * KCP, smB + st * TB * KCP, A, lda, Bm, ldb, nk * KC, tid);
+            }
+            cp_async_commit();
+        }
+        const int st = kc % STAGES;
+        const double* a_s = smA + st * TB * KCP + (wm * 32 + g) * KCP + t;
+        const double* b_s = smB + st * TB * KCP + (wn * 32 + g) * KCP + t;
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; kk++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = a_s[mi * 8 * KCP + kk * 4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) b[ni] = b_s[ni * 8 * KCP + kk * 4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc.v[mi][ni][0], acc.v[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // all warps done with the stage buffers: they may be re-used by the caller
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64x64 work tile in shared memory (row stride TSP) -- coalesced global I/O and fragment exchange
+// ------------------------------------------------------------------------------------------------
+// Ts = diag(rs) * S * diag(cs) (+ I on a diagonal tile).  rs / cs may be null.
+__device__ __forceinline__ void tile_load(double* Ts, const double* __restrict__ S, int ld, const double* rs,
+                                          const double* cs, bool add_identity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = lane * 2;
+    const double c0 = cs ? cs[c] : 1.0, c1 = cs ? cs[c + 1] : 1.0;
+#pragma unroll 4
+    for (int rr = 0; rr < 16; rr++) {
+        const int r = warp * 16 + rr;
+        double2 v = *reinterpret_cast<const double2*>(S + (size_t)r * ld + c);
+        if (rs || cs) {
+            const double rsv = rs ? rs[r] : 1.0;
+            v.x = rsv * v.x * c0;
+            v.y = rsv * v.y * c1;
+        }
+        if (add_identity) {
+            if (r == c) v.x += 1.0;
+            if (r == c + 1) v.y += 1.0;
+        }
+        Ts[r * TSP + c] = v.x;
+        Ts[r * TSP + c + 1] = v.y;
+    }
+}
+__device__ __forceinline__ void tile_fill_rowvec(double* Ts, const double* vec) {  // Ts[r][c] = vec[c]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double v0 = vec[lane * 2], v1 = vec[lane * 2 + 1];
+#pragma unroll 4
+    for (int rr = 0; rr < 16; rr++) {
+        const int r = warp * 16 + rr;
+        Ts[r * TSP + lane * 2] = v0;
+        Ts[r * TSP + lane * 2 + 1] = v1;
+    }
+}
+__device__ __forceinline__ void tile_store(const double* Ts, double* __restrict__ Dm, int ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 4
+    for (int rr = 0; rr < 16; rr++) {
+        const int r = warp * 16 + rr;
+        double2 v;
+        v.x = Ts[r * TSP + lane * 2];
+        v.y = Ts[r * TSP + lane * 2 + 1];
+        *reinterpret_cast<double2*>(Dm + (size_t)r * ld + lane * 2) = v;
+    }
+}
+// Ts += sign * acc (fragment layout of the DMMA accumulators)
+__device__ __forceinline__ void tile_add_acc(double* Ts, const Acc& acc, double sign) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            double* p = Ts + (wm * 32 + mi * 8 + g) * TSP + wn * 32 + ni * 8 + 2 * t;
+            p[0] += sign * acc.v[mi][ni][0];
+            p[1] += sign * acc.v[mi][ni][1];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64x64 Cholesky, one row per thread in registers (threads 0..63 = warps 0 and 1 take part, one
+// named barrier per column).  Right-looking: after column j is scaled every row subtracts its multiple
+// of the column, which it reads as a shared-memory broadcast.  The thread that owns row j+1 finishes
+// pivot j+1 early so the next column's reciprocal is published by the same barrier.
+// On exit Ts holds L (zeros above the diagonal).  Returns false through *sh_fail if a pivot is <= 0 / NaN.
+// ------------------------------------------------------------------------------------------------
+struct PotrfScratch {
+    double colbuf[2][TB];
+    double inv[TB];
+    int fail;
+};
+
+__device__ __forceinline__ void potrf64_rows(double* Ts, PotrfScratch* sc) {
+    const int r = threadIdx.x;  // < 64
+    double a[TB];
+#pragma unroll
+    for (int c = 0; c < TB; c++) a[c] = Ts[r * TSP + c];
+    if (r == 0) {
+        const double d = a[0];
+        if (!(d > 0.0)) sc->fail = 1;
+        const double s = sqrt(d);
+        a[0] = s;
+        sc->inv[0] = 1.0 / s;
+    }
+    named_bar_sync(1, 64);
+#pragma unroll
+    for (int j = 0; j < TB - 1; j++) {
+        double l = 0.0;
+        if (r > j) {
+            l = a[j] * sc->inv[j];
+            a[j] = l;
+            sc->colbuf[j & 1][r] = l;
+            if (r == j + 1) {
+                const double d = a[j + 1] - l * l;
+                if (!(d > 0.0)) sc->fail = 1;
+                const double s = sqrt(d);
+                a[j + 1] = s;
+                sc->inv[j + 1] = 1.0 / s;
+            }
+        }
+        named_bar_sync(1, 64);
+        if (r > j + 1) {
+            const double2* cb = reinterpret_cast<const double2*>(sc->colbuf[j & 1]);
+#pragma unroll
+            for (int cp = (j + 1) >> 1; cp < TB / 2; cp++) {
+                const double2 v = cb[cp];
+                if (2 * cp >= j + 1) a[2 * cp] = fma(-l, v.x, a[2 * cp]);
+                a[2 * cp + 1] = fma(-l, v.y, a[2 * cp + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < TB; c++) Ts[r * TSP + c] = (c <= r) ? a[c] : 0.0;
+}
+
+// X = T * L^{-T} for a 64x64 tile, one row of T per thread (threads 0..63).  LT[c*LTS + c'] = L[c'][c],
+// invd[c] = 1 / L[c][c].
+constexpr int LTS = 66;
+__device__ __forceinline__ void trsm64_rows(double* Ts, const double* LT, const double* invd) {
+    const int r = threadIdx.x;  // < 64
+    double x[TB];
+#pragma unroll
+    for (int c = 0; c < TB; c++) x[c] = Ts[r * TSP + c];
+#pragma unroll
+    for (int c = 0; c < TB; c++) {
+        x[c] *= invd[c];
+        const double xc = x[c];
+        const double2* lt = reinterpret_cast<const double2*>(LT + c * LTS);
+#pragma unroll
+        for (int cp = (c + 1) >> 1; cp < TB / 2; cp++) {
+            const double2 v = lt[cp];
+            if (2 * cp >= c + 1) x[2 * cp] = fma(-xc, v.x, x[2 * cp]);
+            x[2 * cp + 1] = fma(-xc, v.y, x[2 * cp + 1]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < TB; c++) Ts[r * TSP + c] = x[c];
+}
+
+// load the diagonal block L_kk (row-major, ld) transposed into LT, and its reciprocal diagonal
+__device__ __forceinline__ void load_diag_transposed(double* LT, double* invd, const double* __restrict__ Lkk, int ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 4
+    for (int rr = 0; rr < 16; rr++) {
+        const int r = warp * 16 + rr;
+        const double2 v = *reinterpret_cast<const double2*>(Lkk + (size_t)r * ld + lane * 2);
+        LT[(lane * 2) * LTS + r] = v.x;
+        LT[(lane * 2 + 1) * LTS + r] = v.y;
+        if (r == lane * 2) invd[r] = 1.0 / v.x;
+        if (r == lane * 2 + 1) invd[r] = 1.0 / v.y;
+    }
+}
+
+// carve the epilogue scratch out of the (finished) GEMM stage buffers
+struct TileScratch {
+    double* Ts;
+    double* LT;
+    double* invd;
+    PotrfScratch* potrf;
+};
+__device__ __forceinline__ TileScratch carve_scratch(double* smem) {
+    TileScratch s;
+    s.Ts = smem;                          // 64*65
+    s.LT = smem + TB * TSP;               // 4160 doubles = 33280 B, 16-byte aligned
+    s.invd = s.LT + TB * LTS;             // 4224 doubles
+    s.potrf = reinterpret_cast<PotrfScratch*>(s.invd + TB);
+    return s;
+}
+static_assert((TB * TSP + TB * LTS + TB) * 8 + sizeof(PotrfScratch) <= TILE_SMEM_BYTES, "tile scratch exceeds GEMM smem");
+
+// ------------------------------------------------------------------------------------------------
+// Blocked left-looking Cholesky, launch `k` of nb (k = -1 .. nb-2):
+//   CTAs (chain b, row block i = k+1 .. nb-1):
+//     if k >= 0 :  L_ik = (A_ik - sum_{j<k} L_ij L_kj^T) L_kk^{-T}
+//     if i==k+1 :  L_ii = chol(A_ii - sum_{j<=k} L_ij L_ij^T)          (look-ahead for the next launch)
+//   A = diag(scale) * src * diag(scale) (+ I)   -- so B = I + W^1/2 K W^1/2 (lpa.py:91) is never stored.
+// ------------------------------------------------------------------------------------------------
+struct CholParams {
+    const double* src; long long src_bs; int lds; const int* src_idx;
+    double* dst; long long dst_bs; int ldd; const int* dst_idx;
+    const double* scale; long long scale_bs;   // W^1/2 per chain (null: none)
+    int add_identity;
+    int nb;
+    double* logdet_parts; int logdet_stride; const int* logdet_idx;   // [chain or slot][nb] partial sums of log L_jj
+    int* status; int fail_code;                 // per-chain status (skip chain if non-zero)
+    const int* active;                          // optional Newton mask (skip chain if 0)
+    int nchains;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_chol_step(CholParams p, int k) {
+    extern __shared__ __align__(16) double smem[];
+    // heavy CTAs (the look-ahead diagonal) first in launch order
+    const int rows_per_chain = p.nb - k - 1;
+    int b, i;
+    if ((int)blockIdx.x < p.nchains) {
+        b = blockIdx.x;
+        i = k + 1;
+    } else {
+        const int r = blockIdx.x - p.nchains;
+        b = r / (rows_per_chain - 1);
+        i = k + 2 + r % (rows_per_chain - 1);
+    }
+    if (p.status[b] != 0) return;
+    if (p.active && !p.active[b]) return;
+    const double* src = p.src + chain_index(p.src_idx, b) * p.src_bs;
+    double* dst = p.dst + chain_index(p.dst_idx, b) * p.dst_bs;
+    const double* sc = p.scale ? p.scale + (long long)b * p.scale_bs : nullptr;
+    TileScratch s = carve_scratch(smem);
+    Acc acc;
+    if (k >= 0) {
+        acc.zero();
+        gemm_nt_64x64(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
+        tile_load(s.Ts, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
+                  sc ? sc + k * TB : nullptr, false);
+        load_diag_transposed(s.LT, s.invd, dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
+        __syncthreads();
+        tile_add_acc(s.Ts, acc, -1.0);
+        __syncthreads();
+        if (threadIdx.x < 64) trsm64_rows(s.Ts, s.LT, s.invd);
+        __syncthreads();
+        tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + k * TB, p.ldd);
+    }
+    if (i == k + 1) {
+        if (k >= 0) {
+            __threadfence();
+            __syncthreads();  // the panel block just written is an operand of the diagonal update
+        }
+        acc.zero();
+        gemm_nt_64x64(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)i * TB * p.ldd, p.ldd, i * TB, smem);
+        tile_load(s.Ts, src + (size_t)i * TB * p.lds + i * TB, p.lds, sc ? sc + i * TB : nullptr,
+                  sc ? sc + i * TB : nullptr, p.add_identity != 0);
+        if (threadIdx.x == 0) s.potrf->fail = 0;
+        __syncthreads();
+        tile_add_acc(s.Ts, acc, -1.0);
+        __syncthreads();
+        if (threadIdx.x < 64) potrf64_rows(s.Ts, s.potrf);
+        __syncthreads();
+        tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + i * TB, p.ldd);
+        if (threadIdx.x < 64) {
+            double lg = log(s.Ts[threadIdx.x * TSP + threadIdx.x]);
+            lg = warp_sum(lg);
+            if ((threadIdx.x & 31) == 0) s.invd[threadIdx.x >> 5] = lg;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (p.logdet_parts)
+                p.logdet_parts[(size_t)chain_index(p.logdet_idx, b) * p.logdet_stride + i] = s.invd[0] + s.invd[1];
+            if (s.potrf->fail) atomicMax(&p.status[b], p.fail_code);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// X L^T = R for 64-row panels: CTA (chain b, row block r) walks block columns k = 0..nb-1:
+//   X_rk = (R_rk - sum_{j<k} X_rj L_kj^T) L_kk^{-T}
+// R_rk = Rsrc tile scaled by column vector cs (R = K diag(W^1/2), lpa.py:90/111) or a plain tile.
+// ------------------------------------------------------------------------------------------------
+struct TrsmParams {
+    const double* R; long long r_bs; int ldr; const int* r_idx;
+    const double* cs; long long cs_bs;          // optional column scaling of R
+    double* X; long long x_bs; int ldx;
+    const double* L; long long l_bs; int ldl; const int* l_idx;
+    int nb;         // block columns (n_pad / 64)
+    int row_blocks; // row blocks of R / X per chain
+    const int* status; const int* active;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_trsm_rows(TrsmParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / p.row_blocks, rb = blockIdx.x % p.row_blocks;
+    if (p.status[b] != 0) return;
+    if (p.active && !p.active[b]) return;
+    const double* R = p.R + chain_index(p.r_idx, b) * p.r_bs + (size_t)rb * TB * p.ldr;
+    double* X = p.X + (long long)b * p.x_bs + (size_t)rb * TB * p.ldx;
+    const double* L = p.L + chain_index(p.l_idx, b) * p.l_bs;
+    const double* cs = p.cs ? p.cs + (long long)b * p.cs_bs : nullptr;
+    TileScratch s = carve_scratch(smem);
+    Acc acc;
+    for (int k = 0; k < p.nb; k++) {
+        acc.zero();
+        gemm_nt_64x64(acc, X, p.ldx, L + (size_t)k * TB * p.ldl, p.ldl, k * TB, smem);
+        tile_load(s.Ts, R + k * TB, p.ldr, nullptr, cs ? cs + k * TB : nullptr, false);
+        load_diag_transposed(s.LT, s.invd, L + (size_t)k * TB * p.ldl + k * TB, p.ldl);
+        __syncthreads();
+        tile_add_acc(s.Ts, acc, -1.0);
+        __syncthreads();
+        if (threadIdx.x < 64) trsm64_rows(s.Ts, s.LT, s.invd);
+        __syncthreads();
+        tile_store(s.Ts, X + k * TB, p.ldx);
+        __threadfence();
+        __syncthreads();  // X_rk is an operand of the following block columns
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C = S - Z Z^T, lower tiles (i >= j) only.  (lpa.py:112 with Z = (B^{-1/2} W^{1/2} K)^T)
+// ------------------------------------------------------------------------------------------------
+struct SyrkParams {
+    const double* S; long long s_bs; int lds;
+    const double* Z; long long z_bs; int ldz;
+    double* C; long long c_bs; int ldc; const int* c_idx;
+    int nb; int ntiles;  // nb*(nb+1)/2
+    const int* status;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_syrk_sub(SyrkParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / p.ntiles;
+    int tix = blockIdx.x % p.ntiles;
+    if (p.status[b] != 0) return;
+    // tix -> (i, j), j <= i : row i starts at i(i+1)/2
+    int i = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= tix) i++;
+    while (i * (i + 1) / 2 > tix) i--;
+    const int j = tix - i * (i + 1) / 2;
+    const double* S = p.S + (long long)b * p.s_bs;
+    const double* Z = p.Z + (long long)b * p.z_bs;
+    double* C = p.C + chain_index(p.c_idx, b) * p.c_bs;
+    TileScratch s = carve_scratch(smem);
+    Acc acc;
+    acc.zero();
+    gemm_nt_64x64(acc, Z + (size_t)i * TB * p.ldz, p.ldz, Z + (size_t)j * TB * p.ldz, p.ldz, p.nb * TB, smem);
+    tile_load(s.Ts, S + (size_t)i * TB * p.lds + j * TB, p.lds, nullptr, nullptr, false);
+    __syncthreads();
+    tile_add_acc(s.Ts, acc, -1.0);
+    __syncthreads();
+    tile_store(s.Ts, C + (size_t)i * TB * p.ldc + j * TB, p.ldc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// F[s][i] = mu[i] + sum_{j <= i} U^T[s][j] L[i][j]   (estimators.py:223, 323), tile (row block rb of
+// samples, block column k): depth clipped to the lower triangle ((k+1)*64 columns).
+// ------------------------------------------------------------------------------------------------
+struct GemmTriParams {
+    const double* UT; long long u_bs; int ldu;           // [chain][Npad][n_pad]
+    const double* L; long long l_bs; int ldl; const int* l_idx;
+    const double* mu; long long mu_bs; const int* mu_idx; // null -> 0 (prior MC)
+    double* F; long long f_bs; int ldf;
+    int nb; int row_blocks;
+    const int* status;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_gemm_tri(GemmTriParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int per_chain = p.nb * p.row_blocks;
+    const int b = blockIdx.x / per_chain;
+    const int r = blockIdx.x % per_chain;
+    const int rb = r / p.nb, k = p.nb - 1 - (r % p.nb);  // deepest tiles first
+    if (p.status && p.status[b] != 0) return;
+    const double* UT = p.UT + (long long)b * p.u_bs + (size_t)rb * TB * p.ldu;
+    const double* L = p.L + chain_index(p.l_idx, b) * p.l_bs + (size_t)k * TB * p.ldl;
+    double* F = p.F + (long long)b * p.f_bs + (size_t)rb * TB * p.ldf + k * TB;
+    TileScratch s = carve_scratch(smem);
+    Acc acc;
+    acc.zero();
+    gemm_nt_64x64(acc, UT, p.ldu, L, p.ldl, (k + 1) * TB, smem);
+    if (p.mu) {
+        tile_fill_rowvec(s.Ts, p.mu + chain_index(p.mu_idx, b) * p.mu_bs + k * TB);
+    } else {
+        for (int e = threadIdx.x; e < TB * TSP; e += TILE_THREADS) s.Ts[e] = 0.0;
+    }
+    __syncthreads();
+    tile_add_acc(s.Ts, acc, 1.0);
+    __syncthreads();
+    tile_store(s.Ts, F, p.ldf);
+}
+
+}  // namespace apm

@@ -1,0 +1,519 @@
+// vec_kernels.cuh -- the HBM-bound part of the path: K(theta) build, Newton vector updates, matvecs,
+// single right-hand-side triangular solves, the importance-sampling epilogue, layout helpers.
+#pragma once
+#include "common.cuh"
+
+namespace apm {
+
+constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+// ------------------------------------------------------------------------------------------------
+// K(theta): gpdemo/kernels.pyx:12-49 (isotropic) and :52-90 (ARD), batched over chains.
+// Arithmetic follows the scalar reference loop exactly (k ascending, division by the length-scale,
+// no FMA contraction); sigma = exp(theta0), tau_k = exp(theta_k) and 2*tau^2 are computed on the host
+// with libm and passed in kp[chain][*].  Lower tiles are computed and mirrored through shared memory.
+// Rows/cols >= n (padding up to a multiple of 64) are set to the identity.
+// ------------------------------------------------------------------------------------------------
+struct KBuildParams {
+    const double* X; int n, D, np, nb;          // X [np][D] (pad rows zero)
+    const double* kp; int kp_stride;            // per chain: ARD [sigma, tau_1..tau_D], ISO [sigma, 2 tau^2]
+    int ard; double eps;
+    double* K; long long k_bs;                  // [chain][np][np]
+    int ntiles;                                 // nb(nb+1)/2
+};
+
+__global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / p.ntiles;
+    const int tix = blockIdx.x % p.ntiles;
+    int ti = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= tix) ti++;
+    while (ti * (ti + 1) / 2 > tix) ti--;
+    const int tj = tix - ti * (ti + 1) / 2;
+    const int D = p.D;
+    double* Xi = smem;                    // [64][D]
+    double* XjT = Xi + 64 * D;            // [D][64]
+    double* Ts = XjT + 64 * D;            // [64][65] mirror staging
+    double* prm = Ts + 64 * TSP;          // [D+1]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 64 * D; e += 256) {
+        const int r = e / D, k = e % D;
+        Xi[e] = p.X[(size_t)(ti * 64 + r) * D + k];
+        XjT[k * 64 + r] = p.X[(size_t)(tj * 64 + r) * D + k];
+    }
+    const double* kp = p.kp + (size_t)b * p.kp_stride;
+    for (int e = tid; e < D + 1; e += 256) prm[e] = (p.ard || e < 2) ? kp[e] : 0.0;
+    __syncthreads();
+    const double sigma = prm[0];
+    const int tx = tid & 31, ty = tid >> 5;
+    double* Kb = p.K + (long long)b * p.k_bs;
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) {
+        const int r = ty * 8 + rr;
+        const int gi = ti * 64 + r;
+        double out[2];
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int c = tx * 2 + cc;
+            const int gj = tj * 64 + c;
+            double acc = 0.0;
+            if (p.ard) {
+                for (int k = 0; k < D; k++) {
+                    const double d = __ddiv_rn(__dsub_rn(Xi[r * D + k], XjT[k * 64 + c]), prm[k + 1]);
+                    acc = __dadd_rn(acc, __dmul_rn(d, d));
+                }
+                acc = __dmul_rn(sigma, exp(-acc * 0.5));
+            } else {
+                for (int k = 0; k < D; k++) {
+                    const double d = __dsub_rn(Xi[r * D + k], XjT[k * 64 + c]);
+                    acc = __dadd_rn(acc, __dmul_rn(d, d));
+                }
+                acc = __dmul_rn(sigma, exp(__ddiv_rn(-acc, prm[1])));
+            }
+            if (gi == gj) acc = sigma + p.eps;
+            if (gi >= p.n || gj >= p.n) acc = (gi == gj) ? 1.0 : 0.0;
+            out[cc] = acc;
+        }
+        *reinterpret_cast<double2*>(Kb + (size_t)gi * p.np + tj * 64 + tx * 2) = make_double2(out[0], out[1]);
+        Ts[r * TSP + tx * 2] = out[0];
+        Ts[r * TSP + tx * 2 + 1] = out[1];
+    }
+    if (ti != tj) {
+        __syncthreads();
+        // mirrored tile: K[tj*64 + c][ti*64 + r] = Ts[r][c]
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+            const int c = ty * 8 + cc;
+            double2 v;
+            v.x = Ts[(tx * 2) * TSP + c];
+            v.y = Ts[(tx * 2 + 1) * TSP + c];
+            *reinterpret_cast<double2*>(Kb + (size_t)(tj * 64 + c) * p.np + ti * 64 + tx * 2) = v;
+        }
+    }
+}
+
+// u [chain][n][N] (reference layout, estimators.py:155-160) -> uT [chain][Npad][np], zero padded
+__global__ void k_transpose_u(const double* __restrict__ u, long long u_bs, int n, int N, double* __restrict__ uT,
+                              long long ut_bs, int np, int Npad) {
+    __shared__ double tile[32][33];
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const double* ub = u + (long long)b * u_bs;
+    double* utb = uT + (long long)b * ut_bs;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, s = s0 + tx;
+        tile[r][tx] = (i < n && s < N) ? ub[(size_t)i * N + s] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int s = s0 + r, i = i0 + tx;
+        if (s < Npad && i < np) utb[(size_t)s * np + i] = tile[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Newton iteration pieces (lpa.py:85-99), one CTA per chain for the O(n) parts
+// ------------------------------------------------------------------------------------------------
+struct NewtonVecs {
+    double* f; double* W; double* Ws; double* bvec; double* a; double* t; double* s; double* fnew;
+    long long vs;   // stride between chains (= np)
+    const double* y;
+    int n, np;
+    int* active; int* iters; int* status; int* n_active;   // n_active: device counter of still-active chains
+    double tol; int max_iters;
+};
+
+// v = exp(-f^2/2 - log_ndtr(y f) - log(2 pi)/2); grad = v y; W = v^2 + grad f; Ws = sqrt(W); b = W f + grad
+__global__ void k_newton_prep(NewtonVecs nv) {
+    const int b = blockIdx.x;
+    if (!nv.active[b] || nv.status[b] != 0) return;
+    const long long o = (long long)b * nv.vs;
+    for (int i = threadIdx.x; i < nv.np; i += blockDim.x) {
+        double W = 0.0, Ws = 0.0, bv = 0.0;
+        if (i < nv.n) {
+            const double f = nv.f[o + i], y = nv.y[i];
+            const double v = exp(-0.5 * f * f - log_ndtr(y * f) - HALF_LOG_2PI);
+            const double g = v * y;
+            W = v * v + g * f;
+            Ws = sqrt(W);
+            bv = W * f + g;
+        }
+        nv.W[o + i] = W;
+        nv.Ws[o + i] = Ws;
+        nv.bvec[o + i] = bv;
+    }
+}
+
+// out[i] = rs[i] * sum_j M[i][j] x[j]; grid (np/32, chains), 256 threads (8 warps x 4 rows)
+__global__ void __launch_bounds__(256) k_matvec(const double* __restrict__ M, long long m_bs, int ld, int ncols,
+                                                const double* __restrict__ x, const double* __restrict__ rs,
+                                                double* __restrict__ out, long long vs, const int* active,
+                                                const int* status) {
+    const int b = blockIdx.y;
+    if ((active && !active[b]) || (status && status[b] != 0)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* Mb = M + (long long)b * m_bs;
+    const double* xb = x + (long long)b * vs;
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int r = blockIdx.x * 32 + warp * 4 + rr;
+        const double* row = Mb + (size_t)r * ld;
+        double acc = 0.0;
+        for (int j = lane * 2; j < ncols; j += 64) {
+            const double2 m = *reinterpret_cast<const double2*>(row + j);
+            const double2 xv = *reinterpret_cast<const double2*>(xb + j);
+            acc = fma(m.x, xv.x, acc);
+            acc = fma(m.y, xv.y, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[(long long)b * vs + r] = rs ? rs[(long long)b * vs + r] * acc : acc;
+    }
+}
+
+// s = L^{-T} L^{-1} t (lpa.py:94 cho_solve with one right-hand side), then a = b - Ws * s.
+// One CTA (256 threads) per chain; dynamic smem: w[np] + Ls[64][65] + misc.
+__global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, long long l_bs, int ld, int nb,
+                                               NewtonVecs nv) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x;
+    if (!nv.active[b] || nv.status[b] != 0) return;
+    const int np = nb * 64;
+    double* w = smem;                 // [np]
+    double* Ls = w + np;              // [64][65]
+    double* invd = Ls + 64 * TSP;     // [64]
+    const double* Lb = L + (long long)b * l_bs;
+    const long long o = (long long)b * nv.vs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < np; i += 256) w[i] = nv.t[o + i];
+    __syncthreads();
+    // ---- forward: L w = t
+    for (int kb = 0; kb < nb; kb++) {
+        // stage the diagonal block
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int r = e >> 5, c2 = (e & 31) * 2;
+            const double2 v = *reinterpret_cast<const double2*>(Lb + (size_t)(kb * 64 + r) * ld + kb * 64 + c2);
+            Ls[r * TSP + c2] = v.x;
+            Ls[r * TSP + c2 + 1] = v.y;
+            if (r == c2) invd[r] = 1.0 / v.x;
+            if (r == c2 + 1) invd[r] = 1.0 / v.y;
+        }
+        // rows of this block minus the already solved part
+        const int kcols = kb * 64;
+        for (int rr = 0; rr < 8; rr++) {
+            const int r = kb * 64 + warp * 8 + rr;
+            const double* row = Lb + (size_t)r * ld;
+            double acc = 0.0;
+            for (int j = lane * 2; j < kcols; j += 64) {
+                const double2 m = *reinterpret_cast<const double2*>(row + j);
+                acc = fma(m.x, w[j], acc);
+                acc = fma(m.y, w[j + 1], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) w[r] -= acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double r0 = w[kb * 64 + lane], r1 = w[kb * 64 + 32 + lane];
+#pragma unroll 8
+            for (int c = 0; c < 64; c++) {
+                const double mine = (c < 32) ? r0 : r1;
+                const double wc = __shfl_sync(0xffffffffu, mine, c & 31) * invd[c];
+                if (c < 32) {
+                    if (lane == c) r0 = wc;
+                    if (lane > c) r0 = fma(-Ls[lane * TSP + c], wc, r0);
+                    r1 = fma(-Ls[(32 + lane) * TSP + c], wc, r1);
+                } else {
+                    if (lane == c - 32) r1 = wc;
+                    if (lane > c - 32) r1 = fma(-Ls[(32 + lane) * TSP + c], wc, r1);
+                }
+            }
+            w[kb * 64 + lane] = r0;
+            w[kb * 64 + 32 + lane] = r1;
+        }
+        __syncthreads();
+    }
+    // ---- backward: L^T s = w
+    for (int kb = nb - 1; kb >= 0; kb--) {
+        for (int e = tid; e < 64 * 32; e += 256) {
+            const int r = e >> 5, c2 = (e & 31) * 2;
+            const double2 v = *reinterpret_cast<const double2*>(Lb + (size_t)(kb * 64 + r) * ld + kb * 64 + c2);
+            Ls[r * TSP + c2] = v.x;
+            Ls[r * TSP + c2 + 1] = v.y;
+            if (r == c2) invd[r] = 1.0 / v.x;
+            if (r == c2 + 1) invd[r] = 1.0 / v.y;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double r0 = w[kb * 64 + lane], r1 = w[kb * 64 + 32 + lane];
+#pragma unroll 8
+            for (int c = 63; c >= 0; c--) {
+                const double mine = (c < 32) ? r0 : r1;
+                const double sc = __shfl_sync(0xffffffffu, mine, c & 31) * invd[c];
+                // rhs_r -= L[c][r] * s_c for r < c
+                if (c >= 32) {
+                    if (lane == c - 32) r1 = sc;
+                    if (lane < c - 32) r1 = fma(-Ls[c * TSP + 32 + lane], sc, r1);
+                    r0 = fma(-Ls[c * TSP + lane], sc, r0);
+                } else {
+                    if (lane == c) r0 = sc;
+                    if (lane < c) r0 = fma(-Ls[c * TSP + lane], sc, r0);
+                }
+            }
+            w[kb * 64 + lane] = r0;
+            w[kb * 64 + 32 + lane] = r1;
+        }
+        __syncthreads();
+        // w[c] -= sum_r L[kb*64 + r][c] * s[kb*64 + r]   for c < kb*64  (thread per column, coalesced rows)
+        const int kcols = kb * 64;
+        for (int c = tid; c < kcols; c += 256) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < 64; r++) acc = fma(Lb[(size_t)(kb * 64 + r) * ld + c], w[kb * 64 + r], acc);
+            w[c] -= acc;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < np; i += 256) {
+        const double s = w[i];
+        nv.s[o + i] = s;
+        nv.a[o + i] = nv.bvec[o + i] - nv.Ws[o + i] * s;
+    }
+}
+
+// diff = mean((fnew - f)^2); f <- fnew; iteration bookkeeping (lpa.py:96-102)
+__global__ void __launch_bounds__(256) k_newton_finish(NewtonVecs nv) {
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    if (!nv.active[b]) return;
+    if (nv.status[b] != 0) {  // failed earlier (chol K / chol B): retire the chain
+        if (threadIdx.x == 0) {
+            nv.active[b] = 0;
+            atomicSub(nv.n_active, 1);
+        }
+        return;
+    }
+    const long long o = (long long)b * nv.vs;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nv.n; i += 256) {
+        const double fn = nv.fnew[o + i];
+        const double d = fn - nv.f[o + i];
+        acc = fma(d, d, acc);
+        nv.f[o + i] = fn;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; w++) tot += red[w];
+        const double diff = tot / (double)nv.n;
+        const int it = nv.iters[b] + 1;
+        nv.iters[b] = it;
+        bool still = true;
+        if (!(diff == diff) || isinf(diff)) {
+            nv.status[b] = 4;
+            still = false;
+        } else if (diff < nv.tol) {
+            still = false;
+        } else if (it >= nv.max_iters) {
+            nv.status[b] = 2;
+            still = false;
+        }
+        if (!still) {
+            nv.active[b] = 0;
+            atomicSub(nv.n_active, 1);
+        }
+    }
+}
+
+// approximate log marginal likelihood (lpa.py:105-106): -a.f/2 + sum log Phi(y f) - sum log diag L
+__global__ void __launch_bounds__(256) k_laplace_lml(NewtonVecs nv, const double* logdet_parts, int ld_stride, int nb,
+                                                     double* lml_out) {
+    __shared__ double red[2][8];
+    const int b = blockIdx.x;
+    if (nv.status[b] != 0) {
+        if (threadIdx.x == 0) lml_out[b] = nan("");
+        return;
+    }
+    const long long o = (long long)b * nv.vs;
+    double af = 0.0, ll = 0.0;
+    for (int i = threadIdx.x; i < nv.n; i += 256) {
+        const double f = nv.f[o + i];
+        af = fma(nv.a[o + i], f, af);
+        ll += log_ndtr(nv.y[i] * f);
+    }
+    af = warp_sum(af);
+    ll = warp_sum(ll);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = af;
+        red[1][threadIdx.x >> 5] = ll;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0, ld = 0.0;
+        for (int w = 0; w < 8; w++) {
+            s0 += red[0][w];
+            s1 += red[1][w];
+        }
+        for (int k = 0; k < nb; k++) ld += logdet_parts[(size_t)b * ld_stride + k];
+        lml_out[b] = -0.5 * s0 + s1 - ld;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Importance-sampling epilogue (estimators.py:225-240), one CTA per chain:
+//   lw_s = sum_i log Phi(y_i F_si) - q_K/2 - sum log diag L_K + q_u/2 + sum log diag L_C
+//   with q_K = |L_K^{-1} f_s|^2 (rows of Zf) and q_u = |u_s|^2 (== (f_s-mu)^T C^{-1} (f_s-mu), est.py:232-234)
+//   out = logsumexp_s lw_s - log N
+// mode 1 (prior MC, estimators.py:323-325): lw_s = sum_i log Phi(y_i F_si) only.
+// ------------------------------------------------------------------------------------------------
+struct EpilogueParams {
+    const double* F; const double* Zf; const double* UT; long long bs; int ld;   // [chain][Npad][np]
+    const double* y; int n, N;
+    const double* logdetK; const double* logdetC; int ld_stride; int nb; const int* slot_idx;   // per slot parts
+    const int* status;
+    double* logml; double* logw;   // logw optional [chain][N]
+    int mode;
+};
+
+__global__ void __launch_bounds__(256) k_is_epilogue(EpilogueParams p) {
+    extern __shared__ __align__(16) double lw[];   // [N]
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    if (p.status && p.status[b] != 0) {
+        if (threadIdx.x == 0) p.logml[b] = nan("");
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double ldK = 0.0, ldC = 0.0;
+    if (p.mode == 0) {
+        const long long sl = chain_index(p.slot_idx, b);
+        for (int k = 0; k < p.nb; k++) {
+            ldK += p.logdetK[(size_t)sl * p.ld_stride + k];
+            ldC += p.logdetC[(size_t)sl * p.ld_stride + k];
+        }
+    }
+    for (int s = warp; s < p.N; s += 8) {
+        const double* Fr = p.F + (long long)b * p.bs + (size_t)s * p.ld;
+        double ll = 0.0, qk = 0.0, qu = 0.0;
+        if (p.mode == 0) {
+            const double* Zr = p.Zf + (long long)b * p.bs + (size_t)s * p.ld;
+            const double* Ur = p.UT + (long long)b * p.bs + (size_t)s * p.ld;
+            for (int i = lane; i < p.n; i += 32) {
+                ll += log_ndtr(p.y[i] * Fr[i]);
+                const double z = Zr[i], u = Ur[i];
+                qk = fma(z, z, qk);
+                qu = fma(u, u, qu);
+            }
+        } else {
+            for (int i = lane; i < p.n; i += 32) ll += log_ndtr(p.y[i] * Fr[i]);
+        }
+        ll = warp_sum(ll);
+        qk = warp_sum(qk);
+        qu = warp_sum(qu);
+        if (lane == 0) {
+            const double v = (p.mode == 0) ? (ll + (-0.5 * qk - ldK) - (-0.5 * qu - ldC)) : ll;
+            lw[s] = v;
+            if (p.logw) p.logw[(size_t)b * p.N + s] = v;
+        }
+    }
+    __syncthreads();
+    double m = -INFINITY;
+    for (int s = threadIdx.x; s < p.N; s += 256) m = fmax(m, lw[s]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < 8; w++) m = fmax(m, red[w]);
+    __syncthreads();
+    double sum = 0.0;
+    for (int s = threadIdx.x; s < p.N; s += 256) sum += exp(lw[s] - m);
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; w++) tot += red[w];
+        p.logml[b] = (log(tot) + m) - log((double)p.N);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------------
+// pad region of a [np][np] matrix -> identity (after importing an n x n matrix)
+__global__ void k_pad_identity(double* M, long long bs, int n, int np) {
+    double* Mb = M + (long long)blockIdx.y * bs;
+    const int npad = np - n;
+    const long long total = (long long)np * npad * 2;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int r, c;
+        if (e < (long long)np * npad) {  // right strip: all rows, cols n..np
+            r = (int)(e / npad);
+            c = n + (int)(e % npad);
+        } else {  // bottom strip: rows n..np, all cols
+            const long long e2 = e - (long long)np * npad;
+            r = n + (int)(e2 / np);
+            c = (int)(e2 % np);
+        }
+        Mb[(size_t)r * np + c] = (r == c) ? 1.0 : 0.0;
+    }
+}
+// out[r][c] (n x n, dense) = r >= c ? M[r][c] : (mirror ? M[c][r] : 0)
+__global__ void k_export_lower(const double* __restrict__ M, int np, int n, double* __restrict__ out, int mirror) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= n) return;
+    double v;
+    if (r >= c) v = M[(size_t)r * np + c];
+    else v = mirror ? M[(size_t)c * np + r] : 0.0;
+    out[(size_t)r * n + c] = v;
+}
+__global__ void k_fill_int(int* p, int v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_double(double* p, double v, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// copy a [np] vector per chain with optional slot indirection on either side
+__global__ void k_copy_vec(const double* src, long long s_bs, const int* s_idx, double* dst, long long d_bs,
+                           const int* d_idx, int len, const int* status) {
+    const int b = blockIdx.y;
+    if (status && status[b] != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) dst[chain_index(d_idx, b) * d_bs + i] = src[chain_index(s_idx, b) * s_bs + i];
+}
+
+// fp64 peak probes (bench.py roofline denominators): dependent-free DMMA / DFMA streams
+__global__ void k_peak_dmma(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, bb = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma884(c[i][0], c[i][1], a, bb);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+__global__ void k_peak_dfma(double* out, int iters) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i] = threadIdx.x * 1e-3 + i;
+    const double a = 1.0000001, bb = 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) c[i] = fma(c[i], a, bb);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i];
+    if (s == 123.456) out[0] = s;
+}
+
+}  // namespace apm

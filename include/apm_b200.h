@@ -1,0 +1,172 @@
+/*
+ * apm_b200.h -- C ABI of the B200-native pseudo-marginal likelihood engine (GP probit, Laplace
+ * importance-sampling estimator).  This is the drop-in boundary for the hot path of
+ * matt-graham/auxiliary-pm-mcmc: everything gpdemo.kernels / gpdemo.latent_posterior_approximations
+ * / gpdemo.estimators compute, batched over independent chains, in fp64 on one GPU.
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types.  All functions return an apm_status (0 = ok) and never abort the
+ *    process; apm_last_error() gives a message for the calling thread's last failure.
+ *  - "host" pointers are ordinary CPU memory (pinned or pageable).  Bulk inputs that may already be
+ *    resident in HBM (the auxiliary normals u) carry an explicit *_on_device flag; a device pointer is
+ *    what torch.Tensor.data_ptr() returns for a CUDA tensor.
+ *  - all matrices are row-major (numpy C order), fp64.  Targets y are +1/-1.
+ *  - a "chain" is one independent Markov chain; B chains are processed in lock-step by one call.
+ *  - a "slot" is a device-resident cache of (chol K, chol C, f_post, log-dets) for one theta, i.e. the
+ *    reference's `cached_results` tuple (gpdemo/estimators.py:171-186).  Samplers keep <= 2 per chain.
+ *  - per-chain status codes (chain_status[]) mirror the reference's exceptions:
+ *      0 ok
+ *      1 chol(K) failed            -> numpy.linalg.LinAlgError          (gpdemo/estimators.py:206)
+ *      2 Newton > max_iters        -> MaximumIterationsExceededError    (lpa.py:100-102)
+ *      3 chol(C) failed            -> InvalidCovarianceMatrixError      (gpdemo/estimators.py:208-215)
+ *      4 non-finite input/result   -> ValueError (scipy check_finite)
+ *      5 chol(B) failed            -> numpy.linalg.LinAlgError          (lpa.py:92)
+ */
+#ifndef APM_B200_H
+#define APM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct apm_ctx apm_ctx;
+
+typedef enum {
+    APM_OK = 0,
+    APM_ERR_INVALID = 1,   /* bad argument */
+    APM_ERR_CUDA = 2,      /* CUDA runtime error (message in apm_last_error) */
+    APM_ERR_NOMEM = 3,     /* device allocation failed */
+    APM_ERR_NOGPU = 4      /* no CUDA device visible: there is NO CPU fallback */
+} apm_status;
+
+typedef enum {
+    APM_KERNEL_ISO = 0,    /* gpdemo/kernels.pyx:12-49  theta = [log sigma, log tau]            */
+    APM_KERNEL_ARD = 1     /* gpdemo/kernels.pyx:52-90  theta = [log sigma, log tau_1..tau_D]   */
+} apm_kernel_kind;
+
+enum { APM_CHAIN_OK = 0, APM_CHAIN_CHOL_K = 1, APM_CHAIN_NEWTON_MAXIT = 2, APM_CHAIN_CHOL_C = 3,
+       APM_CHAIN_NONFINITE = 4, APM_CHAIN_CHOL_B = 5 };
+
+/* library / build info: returns a static string "apm_b200 <version> sm_100a ..." */
+const char* apm_version(void);
+/* message for the last failing call on this thread */
+const char* apm_last_error(void);
+
+/*
+ * Create an engine for one data set on one GPU.
+ * Replaces the constructor state of gpdemo/estimators.py:112-144 (X, y, scratch K) for
+ * `max_chains` chains at once.  X (n x D) and y (n) are HOST pointers, copied to the device.
+ * n_slots cache slots are allocated (>= 2*max_chains for APM samplers); max_nimp is the largest
+ * importance-sample count N that will be used.  device = CUDA ordinal.
+ */
+int apm_create(const double* X, const double* y, int n, int D, int kernel_kind, double epsilon,
+               int max_chains, int n_slots, int max_nimp, int device, apm_ctx** out);
+int apm_destroy(apm_ctx* ctx);
+
+/* Run all work of this context on the given CUDA stream (cudaStream_t as an integer, e.g.
+ * torch.cuda.current_stream().cuda_stream).  0 = the legacy default stream. */
+int apm_set_stream(apm_ctx* ctx, uint64_t cuda_stream);
+/* Block the host until everything queued by this context has finished. */
+int apm_synchronize(apm_ctx* ctx);
+
+/* Laplace/Newton controls, defaults as lpa.py:22-23: diff_f_tol = 1e-4, max_iters = 1000. */
+int apm_set_newton(apm_ctx* ctx, double diff_f_tol, int max_iters);
+
+/* Problem geometry: n, D, padded n, number of theta components, slots, max chains. */
+int apm_get_info(apm_ctx* ctx, int* n, int* D, int* n_pad, int* n_theta, int* n_slots,
+                 int* max_chains, int* max_nimp);
+
+/*
+ * K(theta) builders -- replace gpdemo.kernels.{isotropic,diagonal}_squared_exponential_kernel
+ * (gpdemo/kernels.pyx:12-49, 52-90).  theta: HOST [B][n_theta].  K_out: [B][n][n] dense symmetric,
+ * written to host memory (K_on_device = 0) or device memory (1).  kernel_kind / epsilon override the
+ * context's (pass kernel_kind < 0 / epsilon < 0 to keep them).
+ */
+int apm_kernel_build(apm_ctx* ctx, const double* theta, int B, int kernel_kind, double epsilon,
+                     double* K_out, int K_on_device);
+
+/*
+ * Laplace approximation for caller-supplied covariance matrices -- replaces
+ * gpdemo.latent_posterior_approximations.laplace_approximation (lpa.py:22-124).
+ * K: [B][n][n] host or device.  Outputs (any may be NULL): f_out HOST [B][n] posterior mode;
+ * C_out [B][n][n] posterior covariance (host or device, only if calc_cov); lml_out HOST [B]
+ * (only if calc_lml); cubic_ops_out HOST [B] = iterations (+1 if calc_cov), lpa.py:113-124;
+ * chain_status HOST [B].
+ */
+int apm_laplace(apm_ctx* ctx, const double* K, int K_on_device, int B, int calc_cov, int calc_lml,
+                double* f_out, double* C_out, int C_on_device, double* lml_out, int* cubic_ops_out,
+                int* chain_status);
+
+/*
+ * FULL importance-sampling estimate -- replaces
+ * LogMarginalLikelihoodApproxPosteriorISEstimator.__call__ with cached_results=None
+ * (gpdemo/estimators.py:203-241): K(theta) -> chol K -> Laplace (Newton + covariance) -> chol C ->
+ * f = mu + L_C u -> probit log-lik, log p(f), log q(f) -> logsumexp - log N.
+ *   theta   HOST [B][n_theta]
+ *   u       [B][n][N] (reference layout, element (i,s) at i*N+s), host or device
+ *   slots   HOST [B]: cache slot written for chain b (the returned cached_results)
+ *   logml_out HOST [B]; cubic_ops_out HOST [B] = newton iters + 1 + 2 (est.py:217), may be NULL;
+ *   chain_status HOST [B].
+ * Chains with a non-zero status get logml = NaN and leave their slot invalid.
+ */
+int apm_estimate_full(apm_ctx* ctx, const double* theta, const double* u, int u_on_device, int N,
+                      int B, const int* slots, double* logml_out, int* cubic_ops_out,
+                      int* chain_status);
+
+/*
+ * CACHED estimate (u changed only) -- gpdemo/estimators.py:218-241 with cached_results given.
+ * O(n^2 N) per chain: reads the slot's chol K / chol C / f_post.
+ */
+int apm_estimate_cached(apm_ctx* ctx, const int* slots, const double* u, int u_on_device, int N,
+                        int B, double* logml_out, int* chain_status);
+
+/*
+ * As the two calls above but also returns the per-importance-sample log weights
+ * (est.py:238-239, before the logsumexp) into logw_out HOST [B][N]; used by tests.
+ */
+int apm_estimate_cached_weights(apm_ctx* ctx, const int* slots, const double* u, int u_on_device,
+                                int N, int B, double* logw_out);
+
+/*
+ * Deterministic Laplace log-marginal-likelihood -- replaces
+ * LogMarginalLikelihoodLaplaceEstimator.__call__ (gpdemo/estimators.py:65-82):
+ * K(theta) -> Newton (calc_cov=False, calc_lml=True).  cubic_ops_out = newton iterations.
+ */
+int apm_laplace_lml(apm_ctx* ctx, const double* theta, int B, double* lml_out, int* cubic_ops_out,
+                    int* chain_status);
+
+/*
+ * Prior Monte-Carlo estimate -- replaces LogMarginalLikelihoodPriorMCEstimator.__call__
+ * (gpdemo/estimators.py:297-325): f = L_K u, logsumexp_s sum_i log Phi(y_i f_is) - log N.
+ * If theta != NULL the slot's chol K is (re)built first (one cubic op), else the slot is reused.
+ */
+int apm_estimate_prior_mc(apm_ctx* ctx, const double* theta, const int* slots, const double* u,
+                          int u_on_device, int N, int B, double* logml_out, int* chain_status);
+
+/*
+ * Export one slot's cache to HOST memory in the reference's format (est.py:240-241):
+ * K_chol, C_chol [n][n] lower triangular with zeroed upper triangle, f_post [n].  NULL = skip.
+ */
+int apm_slot_export(apm_ctx* ctx, int slot, double* K_chol, double* C_chol, double* f_post,
+                    double* logdets2);
+/* Import a cache from host arrays (a cached_results tuple produced elsewhere) into a slot. */
+int apm_slot_import(apm_ctx* ctx, int slot, const double* K_chol, const double* C_chol,
+                    const double* f_post);
+/* Copy slot src -> dst on the device (accepting a proposal: cached_res_curr = cached_res_prop,
+ * auxpm/samplers.py:413-417), for B (src,dst) pairs given as HOST arrays. */
+int apm_slot_copy(apm_ctx* ctx, const int* src, const int* dst, int B);
+
+/* Number of kernels this context has launched since creation / the last reset (bench.py reports
+ * it as gpu_launches). */
+int64_t apm_launch_count(apm_ctx* ctx, int reset);
+
+/* Micro-benchmarks used by bench.py to measure the fp64 roofline denominators on the box:
+ * kind 0: DMMA m8n8k4 issue peak, 1: DFMA peak.  Returns TFLOP/s in *tflops. */
+int apm_measure_fp64_peak(int device, int kind, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APM_B200_H */
