@@ -14,7 +14,7 @@ EXPORTS = [
     'apm_version', 'apm_last_error', 'apm_create', 'apm_destroy', 'apm_set_stream', 'apm_synchronize',
     'apm_set_newton', 'apm_get_info', 'apm_kernel_build', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
-    'apm_slot_export', 'apm_slot_import', 'apm_slot_copy', 'apm_launch_count', 'apm_measure_fp64_peak',
+    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_launch_count', 'apm_measure_fp64_peak',
 ]
 
 KERNEL_ISO, KERNEL_ARD = 0, 1
@@ -56,6 +56,7 @@ def lib():
     L.apm_estimate_prior_mc.argtypes = [vp, vp, vp, vp, ct.c_int, ct.c_int, ct.c_int, vp, vp]
     L.apm_slot_export.argtypes = [vp, ct.c_int, vp, vp, vp, vp]
     L.apm_slot_import.argtypes = [vp, ct.c_int, vp, vp, vp]
+    L.apm_slot_factor.argtypes = [vp, ct.c_int, vp, vp, ct.c_int, vp, vp]
     L.apm_slot_copy.argtypes = [vp, vp, vp, ct.c_int]
     L.apm_launch_count.argtypes = [vp, ct.c_int]
     L.apm_launch_count.restype = ct.c_int64
@@ -269,6 +270,16 @@ class Engine(object):
         fp = f64(f_post) if f_post is not None else None
         check(self._L.apm_slot_import(self._h, int(slot), _ptr(Kc), _ptr(Cc) if Cc is not None else None,
                                       _ptr(fp) if fp is not None else None))
+
+    def slot_factor(self, slot, K, C, f_post):
+        kp, kdev, k1 = self._bulk(K)
+        cp, cdev, k2 = self._bulk(C)
+        if kdev != cdev:
+            raise ValueError('K and C must both be host or both be device buffers')
+        fp = f64(f_post)
+        st = np.zeros(1, dtype=np.int32)
+        check(self._L.apm_slot_factor(self._h, int(slot), kp, cp, kdev, _ptr(fp), _ptr(st)))
+        return int(st[0])
 
     def slot_copy(self, src, dst):
         s, d = i32(np.atleast_1d(src)), i32(np.atleast_1d(dst))

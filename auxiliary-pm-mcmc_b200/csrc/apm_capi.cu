@@ -710,6 +710,32 @@ extern "C" int apm_slot_import(apm_ctx* c, int slot, const double* K_chol, const
     return APM_OK;
 }
 
+extern "C" int apm_slot_factor(apm_ctx* c, int slot, const double* K, const double* C, int on_device, const double* f_post,
+                               int* chain_status) {
+    if (!c || slot < 0 || slot >= c->nslots || !K || !C || !f_post) return APM_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->device));
+    c->slot_valid[slot] = 0;
+    APM_TRY(reset_status(c, 1));
+    c->hInts[0] = slot;
+    CU_TRY(cudaMemcpyAsync(c->dSlotsA, c->hInts, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    APM_TRY(import_matrices(c, K, on_device, 1, c->dK, (long long)c->mat));
+    APM_TRY(import_matrices(c, C, on_device, 1, c->dLB, (long long)c->mat));
+    APM_TRY(run_chol(c, 1, c->dK, (long long)c->mat, nullptr, c->dSlotLK, (long long)c->mat, c->dSlotsA, nullptr, 0,
+                     c->dSlotLdK, c->dSlotsA, APM_CHAIN_CHOL_K, nullptr));
+    APM_TRY(run_chol(c, 1, c->dLB, (long long)c->mat, nullptr, c->dSlotLC, (long long)c->mat, c->dSlotsA, nullptr, 0,
+                     c->dSlotLdC, c->dSlotsA, APM_CHAIN_CHOL_C, nullptr));
+    CU_TRY(cudaMemsetAsync(c->dSlotMu + (size_t)slot * c->np, 0, sizeof(double) * c->np, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->dSlotMu + (size_t)slot * c->np, f_post, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+    int st = 0;
+    CU_TRY(cudaMemcpyAsync(c->hInts, c->dStatus, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    st = c->hInts[0];
+    c->slot_valid[slot] = (st == 0);
+    if (chain_status) chain_status[0] = st;
+    return APM_OK;
+}
+
 extern "C" int apm_slot_copy(apm_ctx* c, const int* src, const int* dst, int B) {
     if (!c || !src || !dst || B <= 0) return APM_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->device));

@@ -154,6 +154,12 @@ int apm_slot_export(apm_ctx* ctx, int slot, double* K_chol, double* C_chol, doub
 /* Import a cache from host arrays (a cached_results tuple produced elsewhere) into a slot. */
 int apm_slot_import(apm_ctx* ctx, int slot, const double* K_chol, const double* C_chol,
                     const double* f_post);
+/* Build a slot from caller-supplied dense matrices: chol(K) and chol(C) are computed on the device and
+ * stored with f_post -- the cache a foreign `post_approx_func(K, y) -> (f_post, C, ops)` plug-in
+ * (gpdemo/estimators.py:126-139, 206-209) needs.  K, C: [n][n] host or device; f_post HOST [n].
+ * chain_status HOST [1] receives 0 / 1 (chol K failed) / 3 (chol C failed). */
+int apm_slot_factor(apm_ctx* ctx, int slot, const double* K, const double* C, int on_device,
+                    const double* f_post, int* chain_status);
 /* Copy slot src -> dst on the device (accepting a proposal: cached_res_curr = cached_res_prop,
  * auxpm/samplers.py:413-417), for B (src,dst) pairs given as HOST arrays. */
 int apm_slot_copy(apm_ctx* ctx, const int* src, const int* dst, int B);

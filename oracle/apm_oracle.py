@@ -17,6 +17,10 @@ scipy logsumexp.  Here they are this container's numpy 2.3 / scipy 1.18 (OpenBLA
 
 Each function cites the reference file:line it restates (paths relative to /root/reference).
 """
+import ctypes as ct
+import os
+import subprocess
+
 import numpy as np
 import scipy.linalg as la
 from scipy.special import log_ndtr, logsumexp, gammaln
@@ -36,32 +40,46 @@ class InvalidCovarianceMatrixError(Exception):
 # covariance builders  (gpdemo/kernels.pyx)
 # ----------------------------------------------------------------------------------------------
 
-def isotropic_squared_exponential_kernel(K, X, theta, epsilon=1e-8):
-    """gpdemo/kernels.pyx:12-49.  In place; same operation order as the scalar loop:
-    acc = sum_k (x_ik - x_jk)^2 accumulated for k ascending, then sigma * exp(-acc / (2 tau^2))."""
-    sigma = np.exp(theta[0])
-    tau = np.exp(theta[1])
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_clib = None
+
+
+def _kernels_clib():
+    """Plain-C restatement (oracle/kernels_oracle.c), compiled on first use with gcc."""
+    global _clib
+    if _clib is None:
+        so = os.path.join(_HERE, 'libkernels_oracle.so')
+        src = os.path.join(_HERE, 'kernels_oracle.c')
+        if not os.path.isfile(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(['gcc', '-O2', '-ffp-contract=off', '-fPIC', '-shared', src, '-o', so, '-lm'])
+        _clib = ct.CDLL(so)
+        for fn in (_clib.oracle_iso_se_kernel, _clib.oracle_ard_se_kernel):
+            fn.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_double, ct.c_int, ct.c_int]
+            fn.restype = None
+    return _clib
+
+
+def _call_kernel(fn, K, X, theta, epsilon, n_theta):
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
     n, D = X.shape
-    acc = np.zeros((n, n))
-    for k in range(D):                       # kernels.pyx:46-47 (k ascending, no FMA)
-        d = X[:, None, k] - X[None, :, k]
-        acc += d * d
-    K[:, :] = sigma * np.exp(-acc / (2. * (tau * tau)))   # kernels.pyx:48 (tau**2 == tau*tau)
-    K[np.diag_indices(n)] = sigma + epsilon               # kernels.pyx:43
+    assert theta.shape == (n_theta(D),) and K.shape == (n, n) and K.dtype == np.float64
+    out = K if K.flags.c_contiguous else np.empty((n, n))
+    fn(out.ctypes.data, X.ctypes.data, theta.ctypes.data, float(epsilon), n, D)
+    if out is not K:
+        K[:, :] = out
+
+
+def isotropic_squared_exponential_kernel(K, X, theta, epsilon=1e-8):
+    """gpdemo/kernels.pyx:12-49, in place.  Scalar C restatement (oracle/kernels_oracle.c): libm exp and
+    the reference's operation order, so the result is bit-identical to the Cython module."""
+    _call_kernel(_kernels_clib().oracle_iso_se_kernel, K, X, theta, epsilon, lambda D: 2)
     return None
 
 
 def diagonal_squared_exponential_kernel(K, X, theta, epsilon=1e-8):
-    """gpdemo/kernels.pyx:52-90 (ARD).  acc += ((x_ik - x_jk) / exp(theta[k+1]))^2, k ascending,
-    then sigma * exp(-acc / 2)."""
-    sigma = np.exp(theta[0])
-    n, D = X.shape
-    acc = np.zeros((n, n))
-    for k in range(D):                       # kernels.pyx:87-88
-        d = (X[:, None, k] - X[None, :, k]) / np.exp(theta[k + 1])
-        acc += d * d
-    K[:, :] = sigma * np.exp(-acc / 2.)      # kernels.pyx:89
-    K[np.diag_indices(n)] = sigma + epsilon  # kernels.pyx:84
+    """gpdemo/kernels.pyx:52-90 (ARD), in place; see isotropic_squared_exponential_kernel."""
+    _call_kernel(_kernels_clib().oracle_ard_se_kernel, K, X, theta, epsilon, lambda D: D + 1)
     return None
 
 

@@ -1,0 +1,199 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (via oracle/ref_loader.py).
+
+Run in the build container only (needs /root/reference):
+    OPENBLAS_NUM_THREADS=1 python oracle/gen_golden.py
+
+The reference has no tests or fixtures of its own, so these vectors -- outputs of the
+reference itself on seeded synthetic inputs -- are what pins both the oracle restatement
+(oracle/apm_oracle.py) and the CUDA path.  Inputs are stored in the fixture (X, y, theta) or regenerated
+from `numpy.random.RandomState(seed)` legacy streams, which are frozen across numpy versions.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+warnings.simplefilter('ignore', SyntaxWarning)
+import ref_loader  # noqa: E402
+from apm_b200 import synth  # noqa: E402  (data generation only)
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+EPS = 1e-8
+
+
+def kernels_of(ref, kind):
+    if kind == 'iso':
+        return lambda K, X, th: ref.kernels.isotropic_squared_exponential_kernel(K, X, th, EPS)
+    return lambda K, X, th: ref.kernels.diagonal_squared_exponential_kernel(K, X, th, EPS)
+
+
+def gen_kernels(ref):
+    rs = np.random.RandomState(101)
+    out = {}
+    for tag, (n, D) in {'a': (13, 3), 'b': (70, 9)}.items():
+        X = rs.normal(size=(n, D))
+        th_iso = rs.normal(size=(3, 2)) * 0.7
+        th_ard = rs.normal(size=(3, D + 1)) * 0.7
+        K_iso = np.empty((3, n, n))
+        K_ard = np.empty((3, n, n))
+        for t in range(3):
+            ref.kernels.isotropic_squared_exponential_kernel(K_iso[t], X, th_iso[t], EPS)
+            ref.kernels.diagonal_squared_exponential_kernel(K_ard[t], X, th_ard[t], 1e-6)
+        out.update({'X_' + tag: X, 'th_iso_' + tag: th_iso, 'th_ard_' + tag: th_ard,
+                    'K_iso_' + tag: K_iso, 'K_ard_' + tag: K_ard})
+    out['eps_iso'] = EPS
+    out['eps_ard'] = 1e-6
+    np.savez_compressed(os.path.join(OUT, 'kernels.npz'), **out)
+
+
+def gen_laplace(ref):
+    out = {}
+    for tag, (n, D, seed) in {'a': (40, 3, 5), 'b': (150, 6, 6)}.items():
+        X, y, th = synth.make_dataset(n, D, seed)
+        K = np.empty((n, n))
+        ref.kernels.diagonal_squared_exponential_kernel(K, X, th, EPS)
+        f, C, lml, ops = ref.lpa.laplace_approximation(K, y, calc_cov=True, calc_lml=True)
+        f2, lml2, ops2 = ref.lpa.laplace_approximation(K, y, calc_cov=False, calc_lml=True)
+        assert np.array_equal(f, f2)
+        out.update({'K_' + tag: K, 'y_' + tag: y, 'f_' + tag: f, 'C_' + tag: C, 'lml_' + tag: lml,
+                    'ops_cov_' + tag: ops, 'ops_nocov_' + tag: ops2})
+    np.savez_compressed(os.path.join(OUT, 'laplace.npz'), **out)
+
+
+def gen_estimator(ref, name, n, D, kind, Ns, n_theta, seed, keep_mats):
+    X, y, th_true = synth.make_dataset(n, D, seed)
+    P = D + 1 if kind == 'ard' else 2
+    rs = np.random.RandomState(seed + 1000)
+    thetas = th_true[:P][None] + 0.3 * rs.normal(size=(n_theta, P))
+    kf = kernels_of(ref, kind)
+    out = dict(X=X, y=y, thetas=thetas, Ns=np.array(Ns), kind=kind, eps=EPS)
+    for t in range(n_theta):
+        for N in Ns:
+            est = ref.est.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf, ref.lpa.laplace_approximation)
+            u1 = np.random.RandomState(7000 + 10 * t + N).normal(size=(n, N))
+            u2 = np.random.RandomState(8000 + 10 * t + N).normal(size=(n, N))
+            full, cache = est(u1, thetas[t])
+            cached, _ = est(u2, None, cache)
+            key = 't%d_N%d_' % (t, N)
+            out[key + 'full'] = full
+            out[key + 'cached'] = cached
+            out[key + 'cubic_ops'] = est.n_cubic_ops
+        # per-theta cache summaries (from the last N; caches do not depend on u)
+        out['t%d_f_post' % t] = cache[2]
+        out['t%d_diagK' % t] = cache[0].diagonal().copy()
+        out['t%d_diagC' % t] = cache[1].diagonal().copy()
+        if keep_mats:
+            out['t%d_K_chol' % t] = cache[0]
+            out['t%d_C_chol' % t] = cache[1]
+        lap = ref.est.LogMarginalLikelihoodLaplaceEstimator(X, y, kf)
+        out['t%d_laplace_lml' % t] = lap(thetas[t])
+        out['t%d_laplace_ops' % t] = lap.n_cubic_ops
+        pm = ref.est.LogMarginalLikelihoodPriorMCEstimator(X, y, kf)
+        u3 = np.random.RandomState(9000 + t).normal(size=(n, Ns[-1]))
+        out['t%d_prior_mc' % t], _ = pm(u3, thetas[t])
+    np.savez_compressed(os.path.join(OUT, 'estimator_%s.npz' % name), **out)
+
+
+def build_sampler(ref, method, X, y, N, prng, est_holder):
+    """The wiring of the reference notebooks (cells 8-12) on a given data set."""
+    D = X.shape[1]
+    prior = synth.prior_params(D)
+    lg = ref.utils.log_gamma_log_pdf
+    kf = kernels_of(ref, 'iso')
+    ml = ref.est.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf, ref.lpa.laplace_approximation)
+    est_holder.append(ml)
+
+    def log_prior(theta):
+        return lg(theta[0], prior['a_sigma'], prior['b_sigma']) + lg(theta[1], prior['a_tau'], prior['b_tau'])
+
+    def log_f_estimator(u, theta=None, cached_res=None):
+        v, c = ml(u, theta, cached_res)
+        return v + log_prior(theta), c
+
+    u_sampler = lambda: prng.normal(size=(y.shape[0], N))  # noqa: E731
+    prop_sampler = lambda th, s: np.r_[th[0] + s[0] * prng.normal(), th[1] + s[1] * prng.normal()]  # noqa: E731
+    log_prop_density = lambda tp, tc, s: -0.5 * (((tp[0] - tc[0]) / s[0])**2 + ((tp[1] - tc[1]) / s[1])**2)  # noqa: E731
+    scales = np.array([0.5, 0.5])
+
+    def dir_and_w():
+        d = prng.normal(size=2)
+        d /= d.dot(d)**0.5
+        return d, 1.
+
+    if method == 'mi+mh':
+        return ref.smp.APMMetIndPlusMHSampler(log_f_estimator, log_prop_density, prop_sampler, scales, u_sampler, prng)
+    if method == 'ess+mh':
+        return ref.smp.APMEllSSPlusMHSampler(log_f_estimator, log_prop_density, prop_sampler, scales, u_sampler, prng)
+    if method == 'mi+rdss':
+        return ref.smp.APMMetIndPlusRandDirSliceSampler(log_f_estimator, u_sampler, prng, dir_and_w, 0)
+    if method == 'ess+rdss':
+        return ref.smp.APMEllSSPlusRandDirSliceSampler(log_f_estimator, u_sampler, prng, dir_and_w, 0)
+    if method == 'pmmh':
+        main = lambda th: ml(prng.normal(size=(y.shape[0], N)), th)[0] + log_prior(th)  # noqa: E731
+        return ref.smp.PMMHSampler(main, log_prop_density, prop_sampler, scales, prng)
+    raise ValueError(method)
+
+
+def gen_samplers(ref):
+    n, D, n_iter = 60, 3, 1000
+    X, y, _ = synth.make_dataset(n, D, seed=21)
+    out = dict(X=X, y=y, n_iter=n_iter)
+    for method in ['mi+mh', 'ess+mh', 'mi+rdss', 'ess+rdss', 'pmmh']:
+        for N in (1, 4):
+            prng = np.random.RandomState()
+            holder = []
+            smp = build_sampler(ref, method, X, y, N, prng, holder)
+            prng.seed(1000 + N)
+            theta_init = synth.draw_theta_prior(prng, D, ard=False)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                res = smp.get_samples(theta_init, n_iter)
+            thetas = res[0] if isinstance(res, tuple) else res
+            n_rej = np.atleast_1d(res[1]) if isinstance(res, tuple) else np.zeros(0)
+            key = '%s_N%d_' % (method, N)
+            out[key + 'thetas'] = thetas
+            out[key + 'n_reject'] = np.asarray(n_rej, dtype=np.int64)
+            out[key + 'cubic_ops'] = holder[0].n_cubic_ops
+            print(method, N, 'final theta', thetas[-1], 'rej', n_rej, 'ops', holder[0].n_cubic_ops)
+    # adaptive MH run (smp.py:68-156 + utils.py:62-83) for the MI+MH sampler
+    prng = np.random.RandomState()
+    holder = []
+    smp = build_sampler(ref, 'mi+mh', X, y, 1, prng, holder)
+    prng.seed(4242)
+    theta_init = synth.draw_theta_prior(prng, D, ard=False)
+    smp.prop_scales = np.array([0.5, 0.5])
+    th, sc, acc = smp.adaptive_run(theta_init, 25, 8, 0.15, 0.30, ref.utils.adapt_factor_func)
+    out['adapt_thetas'] = th
+    out['adapt_scales'] = sc
+    out['adapt_accept'] = acc
+    np.savez_compressed(os.path.join(OUT, 'samplers.npz'), **out)
+
+
+def gen_utils(ref):
+    xs = np.linspace(-3, 3, 13)
+    np.savez_compressed(
+        os.path.join(OUT, 'utils.npz'), xs=xs,
+        lg_11_01=ref.utils.log_gamma_log_pdf(xs, 1.1, 0.1), lg_1_03=ref.utils.log_gamma_log_pdf(xs, 1., 0.3),
+        adapt=np.array([ref.utils.adapt_factor_func(b, 20) for b in range(20)]))
+
+
+if __name__ == '__main__':
+    if os.environ.get('OPENBLAS_NUM_THREADS') != '1':
+        print('warning: run with OPENBLAS_NUM_THREADS=1 for a deterministic oracle', file=sys.stderr)
+    ref = ref_loader.load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    gen_utils(ref)
+    gen_kernels(ref)
+    gen_laplace(ref)
+    gen_estimator(ref, 'small_ard', 100, 4, 'ard', (1, 8), 3, 31, True)
+    gen_estimator(ref, 'small_iso', 90, 3, 'iso', (1, 70), 3, 32, True)
+    gen_estimator(ref, 'pima_ard', 768, 8, 'ard', (1, 64), 3, 0, False)
+    gen_estimator(ref, 'pima_iso', 768, 8, 'iso', (1, 64), 2, 0, False)
+    gen_estimator(ref, 'breast_ard', 682, 9, 'ard', (64,), 2, 1, False)
+    gen_samplers(ref)
+    print('golden vectors written to', OUT)

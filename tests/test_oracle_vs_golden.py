@@ -1,0 +1,89 @@
+"""The CPU oracle (oracle/apm_oracle.py) against golden vectors produced by the UNMODIFIED reference
+(oracle/gen_golden.py).  This is what pins the oracle: the reference has no tests of its own."""
+import numpy as np
+import pytest
+
+import apm_oracle as orc
+from conftest import load_golden
+
+RTOL_LA = 1e-11   # quantities that go through LAPACK (thread count / kernel choice can move last bits)
+
+
+def test_kernels_bit_exact():
+    g = load_golden('kernels')
+    for tag in 'ab':
+        X = g['X_' + tag]
+        n = X.shape[0]
+        for t in range(3):
+            K = np.empty((n, n))
+            orc.isotropic_squared_exponential_kernel(K, X, g['th_iso_' + tag][t], float(g['eps_iso']))
+            assert np.array_equal(K, g['K_iso_' + tag][t])
+            orc.diagonal_squared_exponential_kernel(K, X, g['th_ard_' + tag][t], float(g['eps_ard']))
+            assert np.array_equal(K, g['K_ard_' + tag][t])
+
+
+def test_laplace():
+    g = load_golden('laplace')
+    for tag in 'ab':
+        K, y = g['K_' + tag], g['y_' + tag]
+        f, C, lml, ops = orc.laplace_approximation(K, y, calc_cov=True, calc_lml=True)
+        np.testing.assert_allclose(f, g['f_' + tag], rtol=RTOL_LA, atol=1e-13)
+        np.testing.assert_allclose(C, g['C_' + tag], rtol=RTOL_LA, atol=1e-13)
+        assert abs(lml - g['lml_' + tag]) <= RTOL_LA * abs(g['lml_' + tag])
+        assert ops == int(g['ops_cov_' + tag])
+        f2, lml2, ops2 = orc.laplace_approximation(K, y, calc_cov=False, calc_lml=True)
+        assert ops2 == int(g['ops_nocov_' + tag]) == ops - 1
+        f3, ops3 = orc.laplace_approximation(K, y, calc_cov=False)
+        assert ops3 == ops2 and np.array_equal(f2, f3)
+
+
+def test_laplace_max_iters():
+    g = load_golden('laplace')
+    with pytest.raises(orc.MaximumIterationsExceededError):
+        orc.laplace_approximation(g['K_a'], g['y_a'], max_iters=1)
+
+
+@pytest.mark.parametrize('name', ['small_ard', 'small_iso', 'pima_ard', 'pima_iso', 'breast_ard'])
+def test_estimators(name):
+    g = load_golden('estimator_' + name)
+    X, y, thetas, kind = g['X'], g['y'], g['thetas'], str(g['kind'])
+    n = X.shape[0]
+    base = orc.diagonal_squared_exponential_kernel if kind == 'ard' else orc.isotropic_squared_exponential_kernel
+    kf = lambda K, X_, th: base(K, X_, th, float(g['eps']))  # noqa: E731
+    n_theta = thetas.shape[0] if n < 500 else 1     # keep the CPU suite short at the pima/breast shapes
+    for t in range(n_theta):
+        for N in g['Ns']:
+            est = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf, orc.laplace_approximation)
+            u1 = np.random.RandomState(7000 + 10 * t + int(N)).normal(size=(n, int(N)))
+            u2 = np.random.RandomState(8000 + 10 * t + int(N)).normal(size=(n, int(N)))
+            full, cache = est(u1, thetas[t])
+            cached, _ = est(u2, None, cache)
+            key = 't%d_N%d_' % (t, N)
+            assert abs(full - g[key + 'full']) <= 1e-10 * abs(g[key + 'full'])
+            assert abs(cached - g[key + 'cached']) <= 1e-10 * abs(g[key + 'cached'])
+            assert est.n_cubic_ops == int(g[key + 'cubic_ops'])
+        np.testing.assert_allclose(cache[2], g['t%d_f_post' % t], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(cache[0].diagonal(), g['t%d_diagK' % t], rtol=1e-9)
+        np.testing.assert_allclose(cache[1].diagonal(), g['t%d_diagC' % t], rtol=1e-9)
+        lap = orc.LogMarginalLikelihoodLaplaceEstimator(X, y, kf)
+        assert abs(lap(thetas[t]) - g['t%d_laplace_lml' % t]) <= 1e-10 * abs(g['t%d_laplace_lml' % t])
+        assert lap.n_cubic_ops == int(g['t%d_laplace_ops' % t])
+        pm = orc.LogMarginalLikelihoodPriorMCEstimator(X, y, kf)
+        u3 = np.random.RandomState(9000 + t).normal(size=(n, int(g['Ns'][-1])))
+        v, _ = pm(u3, thetas[t])
+        assert abs(v - g['t%d_prior_mc' % t]) <= 1e-10 * abs(g['t%d_prior_mc' % t])
+
+
+def test_estimator_errors():
+    g = load_golden('estimator_small_ard')
+    est = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(
+        g['X'], g['y'], orc.diagonal_squared_exponential_kernel, orc.laplace_approximation)
+    with pytest.raises(ValueError):
+        est(np.zeros((g['X'].shape[0], 1)))
+
+
+def test_utils():
+    g = load_golden('utils')
+    assert np.array_equal(orc.log_gamma_log_pdf(g['xs'], 1.1, 0.1), g['lg_11_01'])
+    assert np.array_equal(orc.log_gamma_log_pdf(g['xs'], 1., 0.3), g['lg_1_03'])
+    assert np.array_equal(np.array([orc.adapt_factor_func(b, 20) for b in range(20)]), g['adapt'])
