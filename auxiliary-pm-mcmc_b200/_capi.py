@@ -14,7 +14,7 @@ EXPORTS = [
     'apm_version', 'apm_last_error', 'apm_create', 'apm_destroy', 'apm_set_stream', 'apm_synchronize',
     'apm_set_newton', 'apm_get_info', 'apm_kernel_build', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
-    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_launch_count', 'apm_measure_fp64_peak',
+    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_measure_fp64_peak',
 ]
 
 KERNEL_ISO, KERNEL_ARD = 0, 1
@@ -58,6 +58,8 @@ def lib():
     L.apm_slot_import.argtypes = [vp, ct.c_int, vp, vp, vp]
     L.apm_slot_factor.argtypes = [vp, ct.c_int, vp, vp, ct.c_int, vp, vp]
     L.apm_slot_copy.argtypes = [vp, vp, vp, ct.c_int]
+    L.apm_profile.argtypes = [vp, ct.c_int]
+    L.apm_profile_read.argtypes = [vp, ct.c_int, ct.c_char_p, vp, vp, ct.c_int]
     L.apm_launch_count.argtypes = [vp, ct.c_int]
     L.apm_launch_count.restype = ct.c_int64
     L.apm_measure_fp64_peak.argtypes = [ct.c_int, ct.c_int, dp]
@@ -143,6 +145,24 @@ class Engine(object):
 
     def set_newton(self, diff_f_tol=1e-4, max_iters=1000):
         check(self._L.apm_set_newton(self._h, float(diff_f_tol), int(max_iters)))
+
+    def profile(self, enable=True):
+        check(self._L.apm_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self, reset=True):
+        """{kernel family: (total ms, launches)} accumulated while profiling was enabled."""
+        m = 32
+        names = ct.create_string_buffer(32 * m)
+        ms = np.zeros(m)
+        cnt = np.zeros(m, dtype=np.int64)
+        k = self._L.apm_profile_read(self._h, m, names, _ptr(ms), _ptr(cnt), 1 if reset else 0)
+        if k < 0:
+            raise ApmError('apm_profile_read failed')
+        out = {}
+        for i in range(k):
+            name = names.raw[32 * i:32 * (i + 1)].split(b'\0')[0].decode()
+            out[name] = (float(ms[i]), int(cnt[i]))
+        return out
 
     def launch_count(self, reset=False):
         return int(self._L.apm_launch_count(self._h, 1 if reset else 0))

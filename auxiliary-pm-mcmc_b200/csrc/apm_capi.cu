@@ -39,6 +39,13 @@ static void set_err(const std::string& s) { g_err = s; }
 
 enum { V_F = 0, V_W, V_WS, V_B, V_A, V_T, V_S, V_FNEW, V_COUNT };
 
+// kernel ids for launch accounting / profiling
+enum { KID_BUILD_K = 0, KID_CHOL, KID_TRSM, KID_SYRK, KID_GEMM_TRI, KID_MATVEC, KID_TRSV, KID_NEWTON_VEC, KID_EPILOGUE,
+       KID_TRANSPOSE, KID_MISC, KID_COUNT };
+static const char* const KID_NAMES[KID_COUNT] = {"k_build_K", "k_chol_step", "k_trsm_rows", "k_syrk_sub", "k_gemm_tri",
+                                                 "k_matvec", "k_trsv2", "k_newton_vec", "k_is_epilogue",
+                                                 "k_transpose_u", "misc"};
+
 struct apm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -62,6 +69,13 @@ struct apm_ctx {
     std::vector<char> slot_valid;
     int64_t launches = 0;
     std::vector<void*> allocs;
+    // optional per-kernel CUDA-event timing (apm_profile): events bracket every launch on ctx->stream
+    bool prof = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Pending { int kid; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    double prof_ms[KID_COUNT] = {0};
+    int64_t prof_n[KID_COUNT] = {0};
 };
 
 template <typename T>
@@ -77,8 +91,43 @@ static int dev_alloc(apm_ctx* c, T** p, size_t count) {
     return APM_OK;
 }
 
+static cudaEvent_t prof_event(apm_ctx* c) {
+    if (!c->ev_pool.empty()) {
+        cudaEvent_t e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+static void prof_begin(apm_ctx* c, int kid) {
+    if (!c->prof) return;
+    apm_ctx::Pending p;
+    p.kid = kid;
+    p.a = prof_event(c);
+    p.b = prof_event(c);
+    cudaEventRecord(p.a, c->stream);
+    c->pending.push_back(p);
+}
+// fold finished launches into the per-kernel totals (call only after a stream synchronisation)
+static void prof_resolve(apm_ctx* c) {
+    for (auto& p : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            c->prof_ms[p.kid] += ms;
+            c->prof_n[p.kid] += 1;
+        } else {
+            cudaGetLastError();
+        }
+        c->ev_pool.push_back(p.a);
+        c->ev_pool.push_back(p.b);
+    }
+    c->pending.clear();
+}
 static int check_launch(apm_ctx* c, const char* what) {
     c->launches++;
+    if (c->prof && !c->pending.empty()) cudaEventRecord(c->pending.back().b, c->stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_err(std::string("launch ") + what + ": " + cudaGetErrorString(e));
@@ -206,6 +255,8 @@ extern "C" int apm_destroy(apm_ctx* c) {
     if (!c) return APM_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    prof_resolve(c);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (void* p : c->allocs) cudaFree(p);
     if (c->hKp) cudaFreeHost(c->hKp);
     if (c->hOut) cudaFreeHost(c->hOut);
@@ -243,6 +294,32 @@ extern "C" int apm_get_info(apm_ctx* c, int* n, int* D, int* n_pad, int* n_theta
     if (max_chains) *max_chains = c->maxB;
     if (max_nimp) *max_nimp = c->maxN;
     return APM_OK;
+}
+extern "C" int apm_profile(apm_ctx* c, int enable) {
+    if (!c) return APM_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    prof_resolve(c);
+    c->prof = enable != 0;
+    return APM_OK;
+}
+extern "C" int apm_profile_read(apm_ctx* c, int max_entries, char* names, double* ms, int64_t* counts, int reset) {
+    if (!c || !names || !ms || !counts) return -1;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    prof_resolve(c);
+    int k = 0;
+    for (; k < KID_COUNT && k < max_entries; k++) {
+        strncpy(names + 32 * k, KID_NAMES[k], 31);
+        names[32 * k + 31] = 0;
+        ms[k] = c->prof_ms[k];
+        counts[k] = c->prof_n[k];
+        if (reset) {
+            c->prof_ms[k] = 0;
+            c->prof_n[k] = 0;
+        }
+    }
+    return k;
 }
 extern "C" int64_t apm_launch_count(apm_ctx* c, int reset) {
     if (!c) return 0;
@@ -299,6 +376,7 @@ static int build_K(apm_ctx* c, int B, int kind, double eps) {
         set_err("build_K: feature dimension too large for the shared-memory staging of X");
         return APM_ERR_INVALID;
     }
+    prof_begin(c, KID_BUILD_K);
     k_build_K<<<B * p.ntiles, 256, smem, c->stream>>>(p);
     return check_launch(c, "k_build_K");
 }
@@ -318,6 +396,7 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     p.nchains = B;
     for (int k = -1; k <= c->nb - 2; k++) {
         const int grid = (k < 0) ? B : B * (c->nb - k - 1);
+        prof_begin(c, KID_CHOL);
         k_chol_step<<<grid, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(p, k);
         APM_TRY(check_launch(c, "k_chol_step"));
     }
@@ -340,8 +419,10 @@ static int run_newton(apm_ctx* c, int B) {
     NewtonVecs nv = make_nv(c);
     CU_TRY(cudaMemsetAsync(nv.f, 0, sizeof(double) * (size_t)B * c->np, c->stream));
     CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
+    prof_begin(c, KID_MISC);
     k_fill_int<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dActive, 1, B);
     APM_TRY(check_launch(c, "k_fill_int"));
+    prof_begin(c, KID_MISC);
     k_fill_int<<<1, 32, 0, c->stream>>>(c->dNActive, B, 1);
     APM_TRY(check_launch(c, "k_fill_int"));
     const size_t trsv_smem = (size_t)(c->np + 64 * TSP + 64) * sizeof(double);
@@ -351,9 +432,11 @@ static int run_newton(apm_ctx* c, int B) {
     }
     const dim3 mv_grid(c->np / 32, B);
     for (int it = 0; it < c->max_iters; it++) {
+        prof_begin(c, KID_NEWTON_VEC);
         k_newton_prep<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_prep"));
         // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b))
+        prof_begin(c, KID_MATVEC);
         k_matvec<<<mv_grid, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, c->np, nv.bvec, nv.Ws, nv.t, c->np,
                                                  c->dActive, c->dStatus);
         APM_TRY(check_launch(c, "k_matvec"));
@@ -361,12 +444,15 @@ static int run_newton(apm_ctx* c, int B) {
         APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
                          nullptr, APM_CHAIN_CHOL_B, c->dActive));
         // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
+        prof_begin(c, KID_TRSV);
         k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, nv);
         APM_TRY(check_launch(c, "k_trsv2"));
         // f_new = K a                                              (lpa.py:95)
+        prof_begin(c, KID_MATVEC);
         k_matvec<<<mv_grid, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, c->np, nv.a, nullptr, nv.fnew, c->np,
                                                  c->dActive, c->dStatus);
         APM_TRY(check_launch(c, "k_matvec"));
+        prof_begin(c, KID_NEWTON_VEC);
         k_newton_finish<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_finish"));
         CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -385,6 +471,7 @@ static int run_covariance(apm_ctx* c, int B, double* dst, long long dst_bs, cons
     t.L = c->dLB; t.l_bs = (long long)c->mat; t.ldl = c->np; t.l_idx = nullptr;
     t.nb = c->nb; t.row_blocks = c->nb;
     t.status = c->dStatus; t.active = nullptr;
+    prof_begin(c, KID_TRSM);
     k_trsm_rows<<<B * c->nb, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
     APM_TRY(check_launch(c, "k_trsm_rows"));
     SyrkParams s;
@@ -393,6 +480,7 @@ static int run_covariance(apm_ctx* c, int B, double* dst, long long dst_bs, cons
     s.C = dst; s.c_bs = dst_bs; s.ldc = c->np; s.c_idx = dst_idx;
     s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
     s.status = c->dStatus;
+    prof_begin(c, KID_SYRK);
     k_syrk_sub<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
     return check_launch(c, "k_syrk_sub");
 }
@@ -410,6 +498,7 @@ static int stage_u(apm_ctx* c, const double* u, int u_on_device, int N, int B) {
     }
     const int Npad = (N + TB - 1) / TB * TB;
     dim3 grid(c->np / 32, Npad / 32, B), block(32, 8);
+    prof_begin(c, KID_TRANSPOSE);
     k_transpose_u<<<grid, block, 0, c->stream>>>(du, (long long)c->n * N, c->n, N, c->dUT, (long long)Npad * c->np, c->np,
                                                  Npad);
     return check_launch(c, "k_transpose_u");
@@ -427,6 +516,7 @@ static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_lo
     g.F = c->dF; g.f_bs = ubs; g.ldf = c->np;
     g.nb = c->nb; g.row_blocks = rblocks;
     g.status = c->dStatus;
+    prof_begin(c, KID_GEMM_TRI);
     k_gemm_tri<<<B * c->nb * rblocks, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(g);
     APM_TRY(check_launch(c, "k_gemm_tri"));
     if (mode == 0) {
@@ -437,6 +527,7 @@ static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_lo
         t.L = c->dSlotLK; t.l_bs = (long long)c->mat; t.ldl = c->np; t.l_idx = dSlots;
         t.nb = c->nb; t.row_blocks = rblocks;
         t.status = c->dStatus; t.active = nullptr;
+        prof_begin(c, KID_TRSM);
         k_trsm_rows<<<B * rblocks, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
         APM_TRY(check_launch(c, "k_trsm_rows"));
     }
@@ -447,6 +538,7 @@ static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_lo
     e.status = c->dStatus;
     e.logml = d_logml; e.logw = d_logw;
     e.mode = mode;
+    prof_begin(c, KID_EPILOGUE);
     k_is_epilogue<<<B, 256, sizeof(double) * N, c->stream>>>(e);
     return check_launch(c, "k_is_epilogue");
 }
@@ -475,6 +567,7 @@ static int fetch_results(apm_ctx* c, int B, double* out_d, int n_out, double* ou
     CU_TRY(cudaMemcpyAsync(c->hInts, c->dIters, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaMemcpyAsync(c->hInts + B, c->dStatus, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    if (c->prof) prof_resolve(c);
     if (out_h) memcpy(out_h, c->hOut, sizeof(double) * (size_t)B * n_out);
     for (int b = 0; b < B; b++) {
         if (iters_h) iters_h[b] = c->hInts[b] + iters_add;
@@ -513,6 +606,7 @@ static int import_matrices(apm_ctx* c, const double* M, int on_device, int B, do
     }
     if (c->np > c->n) {
         dim3 grid(64, B);
+        prof_begin(c, KID_MISC);
         k_pad_identity<<<grid, 256, 0, c->stream>>>(dst, dst_bs, c->n, c->np);
         APM_TRY(check_launch(c, "k_pad_identity"));
     }
@@ -528,6 +622,7 @@ extern "C" int apm_laplace(apm_ctx* c, const double* K, int K_on_device, int B, 
     APM_TRY(run_newton(c, B));
     NewtonVecs nv = make_nv(c);
     if (calc_lml) {
+        prof_begin(c, KID_NEWTON_VEC);
         k_laplace_lml<<<B, 256, 0, c->stream>>>(nv, c->dLdB, c->nb, c->nb, c->dOut);
         APM_TRY(check_launch(c, "k_laplace_lml"));
     }
@@ -537,6 +632,7 @@ extern "C" int apm_laplace(apm_ctx* c, const double* K, int K_on_device, int B, 
         const size_t n = c->n;
         for (int b = 0; b < B; b++) {
             dim3 grid((c->n + 255) / 256, c->n);
+            prof_begin(c, KID_MISC);
             k_export_lower<<<grid, 256, 0, c->stream>>>(c->dLB + (size_t)b * c->mat, c->np, c->n, c->dZ + (size_t)b * c->mat, 1);
             APM_TRY(check_launch(c, "k_export_lower"));
             CU_TRY(cudaMemcpyAsync(C_out + (size_t)b * n * n, c->dZ + (size_t)b * c->mat, sizeof(double) * n * n,
@@ -576,6 +672,7 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
     APM_TRY(run_chol(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA, c->dSlotLC, (long long)c->mat, c->dSlotsA, nullptr,
                      0, c->dSlotLdC, c->dSlotsA, APM_CHAIN_CHOL_C, nullptr));
     dim3 cg((c->np + 255) / 256, B);
+    prof_begin(c, KID_MISC);
     k_copy_vec<<<cg, 256, 0, c->stream>>>(c->dVec[V_F], c->np, nullptr, c->dSlotMu, c->np, c->dSlotsA, c->np, c->dStatus);
     APM_TRY(check_launch(c, "k_copy_vec"));
     APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, nullptr, 0));
@@ -622,6 +719,7 @@ extern "C" int apm_laplace_lml(apm_ctx* c, const double* theta, int B, double* l
     APM_TRY(build_K(c, B, c->kind, c->eps));
     APM_TRY(run_newton(c, B));
     NewtonVecs nv = make_nv(c);
+    prof_begin(c, KID_NEWTON_VEC);
     k_laplace_lml<<<B, 256, 0, c->stream>>>(nv, c->dLdB, c->nb, c->nb, c->dOut);
     APM_TRY(check_launch(c, "k_laplace_lml"));
     return fetch_results(c, B, c->dOut, 1, lml_out, cubic_ops_out, 0, chain_status);
@@ -663,12 +761,14 @@ extern "C" int apm_slot_export(apm_ctx* c, int slot, double* K_chol, double* C_c
     dim3 grid((c->n + 255) / 256, c->n);
     double* stage = c->dZ;  // scratch (dense n x n)
     if (K_chol) {
+        prof_begin(c, KID_MISC);
         k_export_lower<<<grid, 256, 0, c->stream>>>(c->dSlotLK + (size_t)slot * c->mat, c->np, c->n, stage, 0);
         APM_TRY(check_launch(c, "k_export_lower"));
         CU_TRY(cudaMemcpyAsync(K_chol, stage, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
     }
     if (C_chol) {
+        prof_begin(c, KID_MISC);
         k_export_lower<<<grid, 256, 0, c->stream>>>(c->dSlotLC + (size_t)slot * c->mat, c->np, c->n, stage, 0);
         APM_TRY(check_launch(c, "k_export_lower"));
         CU_TRY(cudaMemcpyAsync(C_chol, stage, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
@@ -694,10 +794,12 @@ extern "C" int apm_slot_import(apm_ctx* c, int slot, const double* K_chol, const
     if (!c || slot < 0 || slot >= c->nslots || !K_chol) return APM_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->device));
     APM_TRY(import_matrices(c, K_chol, 0, 1, c->dSlotLK + (size_t)slot * c->mat, (long long)c->mat));
+    prof_begin(c, KID_MISC);
     k_logdet_parts<<<c->nb, 64, 0, c->stream>>>(c->dSlotLK + (size_t)slot * c->mat, c->np, c->dSlotLdK + (size_t)slot * c->nb);
     APM_TRY(check_launch(c, "k_logdet_parts"));
     if (C_chol) {
         APM_TRY(import_matrices(c, C_chol, 0, 1, c->dSlotLC + (size_t)slot * c->mat, (long long)c->mat));
+        prof_begin(c, KID_MISC);
         k_logdet_parts<<<c->nb, 64, 0, c->stream>>>(c->dSlotLC + (size_t)slot * c->mat, c->np, c->dSlotLdC + (size_t)slot * c->nb);
         APM_TRY(check_launch(c, "k_logdet_parts"));
     }

@@ -164,6 +164,13 @@ int apm_slot_factor(apm_ctx* ctx, int slot, const double* K, const double* C, in
  * auxpm/samplers.py:413-417), for B (src,dst) pairs given as HOST arrays. */
 int apm_slot_copy(apm_ctx* ctx, const int* src, const int* dst, int B);
 
+/* Per-kernel device timing: when enabled every launch on the context's stream is bracketed by CUDA
+ * events; apm_profile_read returns, per kernel family, the accumulated milliseconds and launch counts
+ * (names: max_entries x 32 chars).  Returns the number of entries, < 0 on error.  bench.py uses this for the
+ * live roofline numbers. */
+int apm_profile(apm_ctx* ctx, int enable);
+int apm_profile_read(apm_ctx* ctx, int max_entries, char* names, double* ms, int64_t* counts, int reset);
+
 /* Number of kernels this context has launched since creation / the last reset (bench.py reports
  * it as gpu_launches). */
 int64_t apm_launch_count(apm_ctx* ctx, int reset);

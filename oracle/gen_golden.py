@@ -81,9 +81,20 @@ def gen_estimator(ref, name, n, D, kind, Ns, n_theta, seed, keep_mats):
             cached, _ = est(u2, None, cache)
             key = 't%d_N%d_' % (t, N)
             out[key + 'full'] = full
+            # noise floor of this case: how far the REFERENCE's own answer moves when every K entry is
+            # perturbed by <= 1 ulp (device exp vs libm exp differ by that much).  ~cond(K) * 1e-16.
+            def kf_ulp(K_out, X_, th_):
+                kf(K_out, X_, th_)
+                E = np.random.RandomState(1).uniform(-1, 1, size=K_out.shape) * 1.1e-16
+                K_out *= 1 + (E + E.T) / 2
+            est_p = ref.est.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf_ulp, ref.lpa.laplace_approximation)
+            out[key + 'ulp_sens'] = abs(est_p(u1, thetas[t])[0] - full)
             out[key + 'cached'] = cached
             out[key + 'cubic_ops'] = est.n_cubic_ops
         # per-theta cache summaries (from the last N; caches do not depend on u)
+        K_tmp = np.empty((n, n))
+        kf(K_tmp, X, thetas[t])
+        out['t%d_condK' % t] = np.linalg.cond(K_tmp)
         out['t%d_f_post' % t] = cache[2]
         out['t%d_diagK' % t] = cache[0].diagonal().copy()
         out['t%d_diagC' % t] = cache[1].diagonal().copy()
