@@ -59,6 +59,7 @@ struct apm_ctx {
     double *dK = nullptr, *dLB = nullptr, *dZ = nullptr;
     double *dSlotLK = nullptr, *dSlotLC = nullptr, *dSlotMu = nullptr, *dSlotLdK = nullptr, *dSlotLdC = nullptr;
     double* dLdB = nullptr;
+    double* dInvB = nullptr;   // (L_kk^{-1})^T diagonal blocks of chol(B): [max_chains][nb][64*64]
     double* dVec[V_COUNT] = {nullptr};
     double *dUT = nullptr, *dF = nullptr, *dZf = nullptr, *dUstage = nullptr;
     double *dKp = nullptr, *dOut = nullptr, *dLogw = nullptr;
@@ -201,6 +202,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     A(dev_alloc(c, &c->dSlotLdK, (size_t)n_slots * c->nb));
     A(dev_alloc(c, &c->dSlotLdC, (size_t)n_slots * c->nb));
     A(dev_alloc(c, &c->dLdB, B * c->nb));
+    A(dev_alloc(c, &c->dInvB, B * (size_t)c->nb * TB * TB));
     for (int v = 0; v < V_COUNT; v++) A(dev_alloc(c, &c->dVec[v], B * np));
     const size_t usz = B * (size_t)c->maxNpad * np;
     A(dev_alloc(c, &c->dUT, usz));
@@ -371,7 +373,7 @@ static int build_K(apm_ctx* c, int B, int kind, double eps) {
     p.ard = (kind == APM_KERNEL_ARD); p.eps = eps;
     p.K = c->dK; p.k_bs = (long long)c->mat;
     p.ntiles = c->nb * (c->nb + 1) / 2;
-    const size_t smem = (size_t)(2 * 64 * c->D + 64 * TSP + c->D + 1) * sizeof(double);
+    const size_t smem = (size_t)(2 * 64 * c->D + 64 * VSP + c->D + 1) * sizeof(double);
     if (smem > 96 * 1024) {
         set_err("build_K: feature dimension too large for the shared-memory staging of X");
         return APM_ERR_INVALID;
@@ -383,7 +385,7 @@ static int build_K(apm_ctx* c, int B, int kind, double eps) {
 
 static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, const int* src_idx, double* dst,
                     long long dst_bs, const int* dst_idx, const double* scale, int add_identity, double* logdet_parts,
-                    const int* logdet_idx, int fail_code, const int* active) {
+                    const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr) {
     CholParams p;
     p.src = src; p.src_bs = src_bs; p.lds = c->np; p.src_idx = src_idx;
     p.dst = dst; p.dst_bs = dst_bs; p.ldd = c->np; p.dst_idx = dst_idx;
@@ -391,6 +393,7 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     p.add_identity = add_identity;
     p.nb = c->nb;
     p.logdet_parts = logdet_parts; p.logdet_stride = c->nb; p.logdet_idx = logdet_idx;
+    p.inv_out = inv_out; p.inv_bs = (long long)c->nb * TB * TB;
     p.status = c->dStatus; p.fail_code = fail_code;
     p.active = active;
     p.nchains = B;
@@ -425,7 +428,7 @@ static int run_newton(apm_ctx* c, int B) {
     prof_begin(c, KID_MISC);
     k_fill_int<<<1, 32, 0, c->stream>>>(c->dNActive, B, 1);
     APM_TRY(check_launch(c, "k_fill_int"));
-    const size_t trsv_smem = (size_t)(c->np + 64 * TSP + 64) * sizeof(double);
+    const size_t trsv_smem = (size_t)(c->np + 64 + 8 * 64) * sizeof(double);
     if (trsv_smem > 160 * 1024) {
         set_err("run_newton: n too large for the single-CTA triangular solve");
         return APM_ERR_INVALID;
@@ -442,10 +445,11 @@ static int run_newton(apm_ctx* c, int B) {
         APM_TRY(check_launch(c, "k_matvec"));
         // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
         APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
-                         nullptr, APM_CHAIN_CHOL_B, c->dActive));
+                         nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB));
         // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
         prof_begin(c, KID_TRSV);
-        k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, nv);
+        k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                  (long long)c->nb * TB * TB, nv);
         APM_TRY(check_launch(c, "k_trsv2"));
         // f_new = K a                                              (lpa.py:95)
         prof_begin(c, KID_MATVEC);

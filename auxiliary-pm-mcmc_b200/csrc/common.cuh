@@ -9,11 +9,13 @@ namespace apm {
 constexpr int TB = 64;          // tile edge of every blocked kernel; matrices are padded to a multiple
 constexpr int KC = 16;          // k-chunk (doubles) staged per pipeline stage
 constexpr int KCP = 20;         // padded smem row stride of a k-chunk: 160 B == 32 (mod 128) -> conflict-free DMMA fragment loads
-constexpr int STAGES = 4;       // cp.async pipeline depth
+constexpr int STAGES = 3;       // cp.async pipeline depth
 constexpr int TILE_THREADS = 128;
-constexpr int TSP = 65;         // padded row stride of the 64x64 fp64 work tile (thread-per-row access is conflict-free)
+constexpr int TSP = 68;         // row stride of the 64x64 fp64 work tile: 68 == 4 (mod 16) -> conflict-free DMMA fragment loads
+constexpr int VSP = 65;         // row stride of tiles accessed one row / one column per thread (vec kernels)
 constexpr int GEMM_SMEM_DOUBLES = 2 * STAGES * TB * KCP;             // A and B stages
-constexpr int TILE_SMEM_BYTES = GEMM_SMEM_DOUBLES * 8;                 // 81920 B, re-used by the tile epilogues
+constexpr int TILE_SCRATCH_DOUBLES = 2 * TB * TSP + TB + 8;          // work tile + diagonal block + reciprocals + flags
+constexpr int TILE_SMEM_BYTES = (GEMM_SMEM_DOUBLES > TILE_SCRATCH_DOUBLES ? GEMM_SMEM_DOUBLES : TILE_SCRATCH_DOUBLES) * 8;  // 70208 B -> 3 CTAs / SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

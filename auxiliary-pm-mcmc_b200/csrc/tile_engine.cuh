@@ -150,94 +150,142 @@ __device__ __forceinline__ void tile_add_acc(double* Ts, const Acc& acc, double 
 }
 
 // ------------------------------------------------------------------------------------------------
-// 64x64 Cholesky, one row per thread in registers (threads 0..63 = warps 0 and 1 take part, one
-// named barrier per column).  Right-looking: after column j is scaled every row subtracts its multiple
-// of the column, which it reads as a shared-memory broadcast.  The thread that owns row j+1 finishes
-// pivot j+1 early so the next column's reciprocal is published by the same barrier.
-// On exit Ts holds L (zeros above the diagonal).  Returns false through *sh_fail if a pivot is <= 0 / NaN.
+// In-shared-memory 64x64 Cholesky and triangular solve, blocked by 8-column panels (runtime loop of 8
+// panels -> compact code).  Per panel: a left-looking DMMA update of the 64x8 panel with everything to its
+// left, then a thread-per-row step on the 8x8 diagonal sub-block (each thread re-derives the 8x8 factor in
+// registers from a shared-memory broadcast, so the only communication is the block barrier).
 // ------------------------------------------------------------------------------------------------
 struct PotrfScratch {
-    double colbuf[2][TB];
-    double inv[TB];
     int fail;
 };
 
-__device__ __forceinline__ void potrf64_rows(double* Ts, PotrfScratch* sc) {
-    const int r = threadIdx.x;  // < 64
-    double a[TB];
+// Cholesky factor of an 8x8 SPD block held in d[i][j] (i >= j used); returns L in l[][] and 1/L_jj in inv[].
+// L_jj = d * rsqrt(d) (<= 1.5 ulp from sqrt), non-positive / NaN pivots reported through `bad`.
+__device__ __forceinline__ void chol8_regs(const double (&d)[8][8], double (&l)[8][8], double (&inv)[8], bool& bad) {
 #pragma unroll
-    for (int c = 0; c < TB; c++) a[c] = Ts[r * TSP + c];
-    if (r == 0) {
-        const double d = a[0];
-        if (!(d > 0.0)) sc->fail = 1;
-        const double s = sqrt(d);
-        a[0] = s;
-        sc->inv[0] = 1.0 / s;
-    }
-    named_bar_sync(1, 64);
+    for (int j = 0; j < 8; j++) {
+        double piv = d[j][j];
 #pragma unroll
-    for (int j = 0; j < TB - 1; j++) {
-        double l = 0.0;
-        if (r > j) {
-            l = a[j] * sc->inv[j];
-            a[j] = l;
-            sc->colbuf[j & 1][r] = l;
-            if (r == j + 1) {
-                const double d = a[j + 1] - l * l;
-                if (!(d > 0.0)) sc->fail = 1;
-                const double s = sqrt(d);
-                a[j + 1] = s;
-                sc->inv[j + 1] = 1.0 / s;
-            }
-        }
-        named_bar_sync(1, 64);
-        if (r > j + 1) {
-            const double2* cb = reinterpret_cast<const double2*>(sc->colbuf[j & 1]);
+        for (int k = 0; k < j; k++) piv = fma(-l[j][k], l[j][k], piv);
+        if (!(piv > 0.0)) bad = true;
+        const double r = rsqrt(piv);
+        inv[j] = r;
+        l[j][j] = piv * r;
 #pragma unroll
-            for (int cp = (j + 1) >> 1; cp < TB / 2; cp++) {
-                const double2 v = cb[cp];
-                if (2 * cp >= j + 1) a[2 * cp] = fma(-l, v.x, a[2 * cp]);
-                a[2 * cp + 1] = fma(-l, v.y, a[2 * cp + 1]);
-            }
+        for (int i = j + 1; i < 8; i++) {
+            double v = d[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) v = fma(-l[i][k], l[j][k], v);
+            l[i][j] = v * r;
         }
     }
-#pragma unroll
-    for (int c = 0; c < TB; c++) Ts[r * TSP + c] = (c <= r) ? a[c] : 0.0;
 }
 
-// X = T * L^{-T} for a 64x64 tile, one row of T per thread (threads 0..63).  LT[c*LTS + c'] = L[c'][c],
-// invd[c] = 1 / L[c][c].
-constexpr int LTS = 66;
-__device__ __forceinline__ void trsm64_rows(double* Ts, const double* LT, const double* invd) {
-    const int r = threadIdx.x;  // < 64
-    double x[TB];
+// Ts (64x64, stride TSP) <- chol(Ts) in place; strict upper triangle zeroed.  All 128 threads call this.
+__device__ __forceinline__ void potrf64_smem(double* Ts, PotrfScratch* sc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int p = 0; p < 8; p++) {
+        const int c0 = p * 8;
+        if (p > 0) {
+            // panel(64x8) -= L[:, 0:c0] * L[c0:c0+8, 0:c0]^T   (rows >= c0 only)
 #pragma unroll
-    for (int c = 0; c < TB; c++) x[c] = Ts[r * TSP + c];
-#pragma unroll
-    for (int c = 0; c < TB; c++) {
-        x[c] *= invd[c];
-        const double xc = x[c];
-        const double2* lt = reinterpret_cast<const double2*>(LT + c * LTS);
-#pragma unroll
-        for (int cp = (c + 1) >> 1; cp < TB / 2; cp++) {
-            const double2 v = lt[cp];
-            if (2 * cp >= c + 1) x[2 * cp] = fma(-xc, v.x, x[2 * cp]);
-            x[2 * cp + 1] = fma(-xc, v.y, x[2 * cp + 1]);
+            for (int mi = 0; mi < 2; mi++) {
+                const int mt = warp + 4 * mi;
+                if (mt >= p) {
+                    double* dp = Ts + (mt * 8 + g) * TSP + c0 + 2 * t;
+                    double d0 = dp[0], d1 = dp[1];
+                    const double* ap = Ts + (mt * 8 + g) * TSP + t;
+                    const double* bp = Ts + (c0 + g) * TSP + t;
+                    for (int k0 = 0; k0 < c0; k0 += 4) dmma884(d0, d1, -ap[k0], bp[k0]);
+                    dp[0] = d0;
+                    dp[1] = d1;
+                }
+            }
+            __syncthreads();
         }
-    }
+        double x[8];
+        bool bad = false;
+        const bool mine = tid < 64 && tid >= c0;
+        if (mine) {
+            double d[8][8], l[8][8], inv[8];
 #pragma unroll
-    for (int c = 0; c < TB; c++) Ts[r * TSP + c] = x[c];
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) d[i][j] = Ts[(c0 + i) * TSP + c0 + j];
+            chol8_regs(d, l, inv, bad);
+            const double* row = Ts + tid * TSP + c0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double v = row[j];
+#pragma unroll
+                for (int k = 0; k < j; k++) v = fma(-x[k], l[j][k], v);
+                x[j] = v * inv[j];
+            }
+        }
+        __syncthreads();  // every reader of the 8x8 block is done before its rows are overwritten
+        if (mine) {
+            double* row = Ts + tid * TSP + c0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) row[j] = (c0 + j <= tid) ? x[j] : 0.0;
+            if (bad && tid == c0) sc->fail = 1;
+        } else if (tid < c0 && tid < 64) {
+            double* row = Ts + tid * TSP + c0;  // strictly above the diagonal block: zeros
+#pragma unroll
+            for (int j = 0; j < 8; j++) row[j] = 0.0;
+        }
+        __syncthreads();
+    }
 }
 
-// load the diagonal block L_kk (row-major, ld) transposed into LT, and its reciprocal diagonal
-__device__ __forceinline__ void load_diag_transposed(double* LT, double* invd, const double* __restrict__ Lkk, int ld) {
+// Ts <- Ts * L^{-T} for a 64x64 tile; Ld = L (64x64 lower, row-major, stride TSP), invd[c] = 1 / L[c][c].
+// All 128 threads call this.
+__device__ __forceinline__ void trsm64_smem(double* Ts, const double* Ld, const double* invd) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int p = 0; p < 8; p++) {
+        const int c0 = p * 8;
+        if (p > 0) {
+            // X[:, c0:c0+8] -= X[:, 0:c0] * L[c0:c0+8, 0:c0]^T
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                const int mt = warp * 2 + mi;
+                double* dp = Ts + (mt * 8 + g) * TSP + c0 + 2 * t;
+                double d0 = dp[0], d1 = dp[1];
+                const double* ap = Ts + (mt * 8 + g) * TSP + t;
+                const double* bp = Ld + (c0 + g) * TSP + t;
+                for (int k0 = 0; k0 < c0; k0 += 4) dmma884(d0, d1, -ap[k0], bp[k0]);
+                dp[0] = d0;
+                dp[1] = d1;
+            }
+            __syncthreads();
+        }
+        if (tid < 64) {
+            double* row = Ts + tid * TSP + c0;
+            double x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double v = row[j];
+#pragma unroll
+                for (int k = 0; k < j; k++) v = fma(-x[k], Ld[(c0 + j) * TSP + c0 + k], v);
+                x[j] = v * invd[c0 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) row[j] = x[j];
+        }
+        __syncthreads();
+    }
+}
+
+// stage the diagonal block L_kk (row-major, ld) into Ld (stride TSP) with its reciprocal diagonal
+__device__ __forceinline__ void load_diag_block(double* Ld, double* invd, const double* __restrict__ Lkk, int ld) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 4
     for (int rr = 0; rr < 16; rr++) {
         const int r = warp * 16 + rr;
         const double2 v = *reinterpret_cast<const double2*>(Lkk + (size_t)r * ld + lane * 2);
-        LT[(lane * 2) * LTS + r] = v.x;
-        LT[(lane * 2 + 1) * LTS + r] = v.y;
+        Ld[r * TSP + lane * 2] = v.x;
+        Ld[r * TSP + lane * 2 + 1] = v.y;
         if (r == lane * 2) invd[r] = 1.0 / v.x;
         if (r == lane * 2 + 1) invd[r] = 1.0 / v.y;
     }
@@ -252,13 +300,13 @@ struct TileScratch {
 };
 __device__ __forceinline__ TileScratch carve_scratch(double* smem) {
     TileScratch s;
-    s.Ts = smem;                          // 64*65
-    s.LT = smem + TB * TSP;               // 4160 doubles = 33280 B, 16-byte aligned
-    s.invd = s.LT + TB * LTS;             // 4224 doubles
+    s.Ts = smem;                          // 64 x TSP
+    s.LT = smem + TB * TSP;               // diagonal block L_kk, 64 x TSP
+    s.invd = s.LT + TB * TSP;
     s.potrf = reinterpret_cast<PotrfScratch*>(s.invd + TB);
     return s;
 }
-static_assert((TB * TSP + TB * LTS + TB) * 8 + sizeof(PotrfScratch) <= TILE_SMEM_BYTES, "tile scratch exceeds GEMM smem");
+static_assert((2 * TB * TSP + TB) * 8 + sizeof(PotrfScratch) <= TILE_SMEM_BYTES, "tile scratch exceeds GEMM smem");
 
 // ------------------------------------------------------------------------------------------------
 // Blocked left-looking Cholesky, launch `k` of nb (k = -1 .. nb-2):
@@ -274,12 +322,13 @@ struct CholParams {
     int add_identity;
     int nb;
     double* logdet_parts; int logdet_stride; const int* logdet_idx;   // [chain or slot][nb] partial sums of log L_jj
+    double* inv_out; long long inv_bs;          // optional: (L_kk^{-1})^T of every diagonal block, [chain][nb][64*64]
     int* status; int fail_code;                 // per-chain status (skip chain if non-zero)
     const int* active;                          // optional Newton mask (skip chain if 0)
     int nchains;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_chol_step(CholParams p, int k) {
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_step(CholParams p, int k) {
     extern __shared__ __align__(16) double smem[];
     // heavy CTAs (the look-ahead diagonal) first in launch order
     const int rows_per_chain = p.nb - k - 1;
@@ -304,11 +353,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_chol_step(CholParams p, int
         gemm_nt_64x64(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
         tile_load(s.Ts, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
                   sc ? sc + k * TB : nullptr, false);
-        load_diag_transposed(s.LT, s.invd, dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
+        load_diag_block(s.LT, s.invd, dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
         __syncthreads();
         tile_add_acc(s.Ts, acc, -1.0);
         __syncthreads();
-        if (threadIdx.x < 64) trsm64_rows(s.Ts, s.LT, s.invd);
+        trsm64_smem(s.Ts, s.LT, s.invd);
         __syncthreads();
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + k * TB, p.ldd);
     }
@@ -325,7 +374,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_chol_step(CholParams p, int
         __syncthreads();
         tile_add_acc(s.Ts, acc, -1.0);
         __syncthreads();
-        if (threadIdx.x < 64) potrf64_rows(s.Ts, s.potrf);
+        potrf64_smem(s.Ts, s.potrf);
         __syncthreads();
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + i * TB, p.ldd);
         if (threadIdx.x < 64) {
@@ -338,6 +387,19 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_chol_step(CholParams p, int
             if (p.logdet_parts)
                 p.logdet_parts[(size_t)chain_index(p.logdet_idx, b) * p.logdet_stride + i] = s.invd[0] + s.invd[1];
             if (s.potrf->fail) atomicMax(&p.status[b], p.fail_code);
+        }
+        if (p.inv_out) {
+            // (L_ii^{-1})^T = I * L_ii^{-T}: lets the single right-hand-side solves of the Newton step
+            // (k_trsv2) replace 64-step substitutions on the diagonal blocks by parallel 64x64 mat-vecs
+            __syncthreads();
+            for (int e = threadIdx.x; e < TB * TB; e += TILE_THREADS) {
+                const int r = e >> 6, c = e & 63;
+                s.LT[r * TSP + c] = (r == c) ? 1.0 : 0.0;
+            }
+            if (threadIdx.x < 64) s.invd[threadIdx.x] = 1.0 / s.Ts[threadIdx.x * TSP + threadIdx.x];
+            __syncthreads();
+            trsm64_smem(s.LT, s.Ts, s.invd);
+            tile_store(s.LT, p.inv_out + (long long)b * p.inv_bs + (size_t)i * TB * TB, TB);
         }
     }
 }
@@ -357,7 +419,7 @@ struct TrsmParams {
     const int* status; const int* active;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_trsm_rows(TrsmParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_trsm_rows(TrsmParams p) {
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.x / p.row_blocks, rb = blockIdx.x % p.row_blocks;
     if (p.status[b] != 0) return;
@@ -372,11 +434,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_trsm_rows(TrsmParams p) {
         acc.zero();
         gemm_nt_64x64(acc, X, p.ldx, L + (size_t)k * TB * p.ldl, p.ldl, k * TB, smem);
         tile_load(s.Ts, R + k * TB, p.ldr, nullptr, cs ? cs + k * TB : nullptr, false);
-        load_diag_transposed(s.LT, s.invd, L + (size_t)k * TB * p.ldl + k * TB, p.ldl);
+        load_diag_block(s.LT, s.invd, L + (size_t)k * TB * p.ldl + k * TB, p.ldl);
         __syncthreads();
         tile_add_acc(s.Ts, acc, -1.0);
         __syncthreads();
-        if (threadIdx.x < 64) trsm64_rows(s.Ts, s.LT, s.invd);
+        trsm64_smem(s.Ts, s.LT, s.invd);
         __syncthreads();
         tile_store(s.Ts, X + k * TB, p.ldx);
         __threadfence();
@@ -395,7 +457,7 @@ struct SyrkParams {
     const int* status;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_syrk_sub(SyrkParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_syrk_sub(SyrkParams p) {
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.x / p.ntiles;
     int tix = blockIdx.x % p.ntiles;
@@ -432,7 +494,7 @@ struct GemmTriParams {
     const int* status;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_gemm_tri(GemmTriParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_gemm_tri(GemmTriParams p) {
     extern __shared__ __align__(16) double smem[];
     const int per_chain = p.nb * p.row_blocks;
     const int b = blockIdx.x / per_chain;

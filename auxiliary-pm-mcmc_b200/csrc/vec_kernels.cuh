@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
     double* Xi = smem;                    // [64][D]
     double* XjT = Xi + 64 * D;            // [D][64]
     double* Ts = XjT + 64 * D;            // [64][65] mirror staging
-    double* prm = Ts + 64 * TSP;          // [D+1]
+    double* prm = Ts + 64 * VSP;          // [D+1]
     const int tid = threadIdx.x;
     for (int e = tid; e < 64 * D; e += 256) {
         const int r = e / D, k = e % D;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
     const double sigma = prm[0];
     const int tx = tid & 31, ty = tid >> 5;
     double* Kb = p.K + (long long)b * p.k_bs;
-#pragma unroll
+#pragma unroll 1
     for (int rr = 0; rr < 8; rr++) {
         const int r = ty * 8 + rr;
         const int gi = ti * 64 + r;
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
             out[cc] = acc;
         }
         *reinterpret_cast<double2*>(Kb + (size_t)gi * p.np + tj * 64 + tx * 2) = make_double2(out[0], out[1]);
-        Ts[r * TSP + tx * 2] = out[0];
-        Ts[r * TSP + tx * 2 + 1] = out[1];
+        Ts[r * VSP + tx * 2] = out[0];
+        Ts[r * VSP + tx * 2 + 1] = out[1];
     }
     if (ti != tj) {
         __syncthreads();
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
         for (int cc = 0; cc < 8; cc++) {
             const int c = ty * 8 + cc;
             double2 v;
-            v.x = Ts[(tx * 2) * TSP + c];
-            v.y = Ts[(tx * 2 + 1) * TSP + c];
+            v.x = Ts[(tx * 2) * VSP + c];
+            v.y = Ts[(tx * 2 + 1) * VSP + c];
             *reinterpret_cast<double2*>(Kb + (size_t)(tj * 64 + c) * p.np + ti * 64 + tx * 2) = v;
         }
     }
@@ -172,105 +172,102 @@ __global__ void __launch_bounds__(256) k_matvec(const double* __restrict__ M, lo
 }
 
 // s = L^{-T} L^{-1} t (lpa.py:94 cho_solve with one right-hand side), then a = b - Ws * s.
-// One CTA (256 threads) per chain; dynamic smem: w[np] + Ls[64][65] + misc.
+// One CTA (256 threads) per chain walks the 64-row blocks of L twice.  The 64x64 diagonal-block solves use the
+// explicit (L_kk^{-1})^T blocks written by k_chol_step (B = I + W^1/2 K W^1/2 has eigenvalues >= 1, so its
+// diagonal blocks are well conditioned), which turns every step into coalesced, fully parallel mat-vecs.
+// dynamic smem: w[np] + rhs[64] + part[4][64]
 __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, long long l_bs, int ld, int nb,
-                                               NewtonVecs nv) {
+                                               const double* __restrict__ LinvT, long long inv_bs, NewtonVecs nv) {
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.x;
     if (!nv.active[b] || nv.status[b] != 0) return;
     const int np = nb * 64;
-    double* w = smem;                 // [np]
-    double* Ls = w + np;              // [64][65]
-    double* invd = Ls + 64 * TSP;     // [64]
+    double* w = smem;            // [np]
+    double* rhs = w + np;        // [64]
+    double* part = rhs + 64;     // [8][64]
     const double* Lb = L + (long long)b * l_bs;
+    const double* Ib = LinvT + (long long)b * inv_bs;
     const long long o = (long long)b * nv.vs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < np; i += 256) w[i] = nv.t[o + i];
     __syncthreads();
     // ---- forward: L w = t
     for (int kb = 0; kb < nb; kb++) {
-        // stage the diagonal block
-        for (int e = tid; e < 64 * 32; e += 256) {
-            const int r = e >> 5, c2 = (e & 31) * 2;
-            const double2 v = *reinterpret_cast<const double2*>(Lb + (size_t)(kb * 64 + r) * ld + kb * 64 + c2);
-            Ls[r * TSP + c2] = v.x;
-            Ls[r * TSP + c2 + 1] = v.y;
-            if (r == c2) invd[r] = 1.0 / v.x;
-            if (r == c2 + 1) invd[r] = 1.0 / v.y;
-        }
-        // rows of this block minus the already solved part
+        // rhs = t_k - L[k, 0:k] w[0:k]; warp handles 8 rows at once (independent loads in flight)
         const int kcols = kb * 64;
-        for (int rr = 0; rr < 8; rr++) {
-            const int r = kb * 64 + warp * 8 + rr;
-            const double* row = Lb + (size_t)r * ld;
-            double acc = 0.0;
-            for (int j = lane * 2; j < kcols; j += 64) {
-                const double2 m = *reinterpret_cast<const double2*>(row + j);
-                acc = fma(m.x, w[j], acc);
-                acc = fma(m.y, w[j + 1], acc);
+        double acc[8];
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) acc[rr] = 0.0;
+        const double* rows = Lb + (size_t)(kb * 64 + warp * 8) * ld;
+        for (int j = lane * 2; j < kcols; j += 64) {
+            const double w0 = w[j], w1 = w[j + 1];
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const double2 m = *reinterpret_cast<const double2*>(rows + (size_t)rr * ld + j);
+                acc[rr] = fma(m.x, w0, acc[rr]);
+                acc[rr] = fma(m.y, w1, acc[rr]);
             }
-            acc = warp_sum(acc);
-            if (lane == 0) w[r] -= acc;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) {
+            const double v = warp_sum(acc[rr]);
+            if (lane == 0) rhs[warp * 8 + rr] = w[kb * 64 + warp * 8 + rr] - v;
         }
         __syncthreads();
-        if (warp == 0) {
-            double r0 = w[kb * 64 + lane], r1 = w[kb * 64 + 32 + lane];
-#pragma unroll 8
-            for (int c = 0; c < 64; c++) {
-                const double mine = (c < 32) ? r0 : r1;
-                const double wc = __shfl_sync(0xffffffffu, mine, c & 31) * invd[c];
-                if (c < 32) {
-                    if (lane == c) r0 = wc;
-                    if (lane > c) r0 = fma(-Ls[lane * TSP + c], wc, r0);
-                    r1 = fma(-Ls[(32 + lane) * TSP + c], wc, r1);
-                } else {
-                    if (lane == c - 32) r1 = wc;
-                    if (lane > c - 32) r1 = fma(-Ls[(32 + lane) * TSP + c], wc, r1);
-                }
-            }
-            w[kb * 64 + lane] = r0;
-            w[kb * 64 + 32 + lane] = r1;
+        // w_k = L_kk^{-1} rhs :  w_c = sum_r LinvT[r][c] rhs[r]  (r <= c); 4 row chunks x 64 columns
+        {
+            const int c = tid & 63, ch = tid >> 6;
+            const double* blk = Ib + (size_t)kb * 4096;
+            double a0 = 0.0;
+#pragma unroll
+            for (int r = ch * 16; r < ch * 16 + 16; r++) a0 = fma(blk[r * 64 + c], rhs[r], a0);
+            part[ch * 64 + c] = a0;
         }
+        __syncthreads();
+        if (tid < 64) w[kb * 64 + tid] = (part[tid] + part[64 + tid]) + (part[128 + tid] + part[192 + tid]);
         __syncthreads();
     }
     // ---- backward: L^T s = w
     for (int kb = nb - 1; kb >= 0; kb--) {
-        for (int e = tid; e < 64 * 32; e += 256) {
-            const int r = e >> 5, c2 = (e & 31) * 2;
-            const double2 v = *reinterpret_cast<const double2*>(Lb + (size_t)(kb * 64 + r) * ld + kb * 64 + c2);
-            Ls[r * TSP + c2] = v.x;
-            Ls[r * TSP + c2 + 1] = v.y;
-            if (r == c2) invd[r] = 1.0 / v.x;
-            if (r == c2 + 1) invd[r] = 1.0 / v.y;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double r0 = w[kb * 64 + lane], r1 = w[kb * 64 + 32 + lane];
-#pragma unroll 8
-            for (int c = 63; c >= 0; c--) {
-                const double mine = (c < 32) ? r0 : r1;
-                const double sc = __shfl_sync(0xffffffffu, mine, c & 31) * invd[c];
-                // rhs_r -= L[c][r] * s_c for r < c
-                if (c >= 32) {
-                    if (lane == c - 32) r1 = sc;
-                    if (lane < c - 32) r1 = fma(-Ls[c * TSP + 32 + lane], sc, r1);
-                    r0 = fma(-Ls[c * TSP + lane], sc, r0);
-                } else {
-                    if (lane == c) r0 = sc;
-                    if (lane < c) r0 = fma(-Ls[c * TSP + lane], sc, r0);
-                }
+        // rhs = w_k - sum_{i > k} L[i, k]^T s_i : 8 row groups x 32 column pairs, coalesced 512-byte row segments
+        {
+            const int cg = tid & 31, rg = tid >> 5;
+            double a0 = 0.0, a1 = 0.0;
+            const int r_end = np;
+            const double* col = Lb + kb * 64 + cg * 2;
+#pragma unroll 4
+            for (int r = (kb + 1) * 64 + rg; r < r_end; r += 8) {
+                const double2 m = *reinterpret_cast<const double2*>(col + (size_t)r * ld);
+                const double sr = w[r];
+                a0 = fma(m.x, sr, a0);
+                a1 = fma(m.y, sr, a1);
             }
-            w[kb * 64 + lane] = r0;
-            w[kb * 64 + 32 + lane] = r1;
+            part[rg * 64 + cg * 2] = a0;
+            part[rg * 64 + cg * 2 + 1] = a1;
         }
         __syncthreads();
-        // w[c] -= sum_r L[kb*64 + r][c] * s[kb*64 + r]   for c < kb*64  (thread per column, coalesced rows)
-        const int kcols = kb * 64;
-        for (int c = tid; c < kcols; c += 256) {
-            double acc = 0.0;
-#pragma unroll 8
-            for (int r = 0; r < 64; r++) acc = fma(Lb[(size_t)(kb * 64 + r) * ld + c], w[kb * 64 + r], acc);
-            w[c] -= acc;
+        if (tid < 64) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) v += part[q * 64 + tid];
+            rhs[tid] = w[kb * 64 + tid] - v;
+        }
+        __syncthreads();
+        // s_k = L_kk^{-T} rhs : s_r = sum_c LinvT[r][c] rhs[c]; warp handles 8 rows
+        {
+            const double* blk = Ib + (size_t)kb * 4096 + (size_t)(warp * 8) * 64;
+            const double r0 = rhs[lane * 2], r1 = rhs[lane * 2 + 1];
+            double acc[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const double2 m = *reinterpret_cast<const double2*>(blk + rr * 64 + lane * 2);
+                acc[rr] = fma(m.x, r0, m.y * r1);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const double v = warp_sum(acc[rr]);
+                if (lane == 0) w[kb * 64 + warp * 8 + rr] = v;
+            }
         }
         __syncthreads();
     }
