@@ -59,6 +59,9 @@ struct apm_ctx {
     double *dK = nullptr, *dLB = nullptr, *dZ = nullptr;
     double *dSlotLK = nullptr, *dSlotLC = nullptr, *dSlotMu = nullptr, *dSlotLdK = nullptr, *dSlotLdC = nullptr;
     double* dLdB = nullptr;
+    int *dFlowCounter = nullptr, *dFlowProgress = nullptr, *dFlowSkip = nullptr;
+    int flow_grid = 0;        // persistent grid of k_chol_dataflow (SMs x occupancy); 0 = per-step launches
+    int flow_group = 32;      // chains per scheduling group
     double* dInvB = nullptr;   // (L_kk^{-1})^T diagonal blocks of chol(B): [max_chains][nb][64*64]
     double* dVec[V_COUNT] = {nullptr};
     double *dUT = nullptr, *dF = nullptr, *dZf = nullptr, *dUstage = nullptr;
@@ -141,6 +144,7 @@ static int g_attr_done = 0;
 static int set_kernel_attrs() {
     if (g_attr_done) return APM_OK;
     CU_TRY(cudaFuncSetAttribute(k_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_gemm_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
@@ -188,6 +192,15 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     c->maxNpad = (max_nimp + TB - 1) / TB * TB;
     c->mat = (size_t)c->np * c->np;
     c->slot_valid.assign(n_slots, 0);
+    {
+        int occ = 0, sms = 0, coop = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_dataflow, TILE_THREADS, TILE_SMEM_BYTES) == cudaSuccess &&
+            occ > 0 && coop && !getenv("APM_CHOL_STEPWISE"))
+            c->flow_grid = occ * sms;
+        if (getenv("APM_CHOL_GROUP")) c->flow_group = atoi(getenv("APM_CHOL_GROUP")) > 0 ? atoi(getenv("APM_CHOL_GROUP")) : 32;
+    }
     const size_t B = max_chains, np = c->np;
     int rc = APM_OK;
     auto A = [&](int r) { if (rc == APM_OK) rc = r; };
@@ -218,6 +231,9 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     A(dev_alloc(c, &c->dNActive, 4));
     A(dev_alloc(c, &c->dSlotsA, B));
     A(dev_alloc(c, &c->dSlotsB, B));
+    A(dev_alloc(c, &c->dFlowCounter, 4));
+    A(dev_alloc(c, &c->dFlowProgress, B * (size_t)c->nb));
+    A(dev_alloc(c, &c->dFlowSkip, B));
     if (rc != APM_OK) {
         apm_destroy(c);
         return rc;
@@ -397,6 +413,29 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     p.status = c->dStatus; p.fail_code = fail_code;
     p.active = active;
     p.nchains = B;
+    if (c->flow_grid > 0) {
+        // single cooperative launch (all CTAs co-resident: tasks wait on each other through progress counters)
+        CholFlow f;
+        f.counter = c->dFlowCounter; f.progress = c->dFlowProgress; f.skip = c->dFlowSkip;
+        f.group = c->flow_group < B ? c->flow_group : B;
+        const int ngroups = (B + f.group - 1) / f.group;
+        f.total_tasks = ngroups * f.group * (1 + c->nb * (c->nb - 1) / 2);
+        CU_TRY(cudaMemsetAsync(c->dFlowCounter, 0, sizeof(int), c->stream));
+        CU_TRY(cudaMemsetAsync(c->dFlowProgress, 0, sizeof(int) * (size_t)B * c->nb, c->stream));
+        prof_begin(c, KID_MISC);
+        k_chol_skip_snapshot<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dStatus, active, c->dFlowSkip, B);
+        APM_TRY(check_launch(c, "k_chol_skip_snapshot"));
+        const int grid = c->flow_grid < f.total_tasks ? c->flow_grid : f.total_tasks;
+        void* args[] = {(void*)&p, (void*)&f};
+        prof_begin(c, KID_CHOL);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_chol_dataflow, dim3(grid), dim3(TILE_THREADS), args,
+                                                    (size_t)TILE_SMEM_BYTES, c->stream);
+        if (e != cudaSuccess) {
+            set_err(std::string("cooperative launch k_chol_dataflow: ") + cudaGetErrorString(e));
+            return APM_ERR_CUDA;
+        }
+        return check_launch(c, "k_chol_dataflow");
+    }
     for (int k = -1; k <= c->nb - 2; k++) {
         const int grid = (k < 0) ? B : B * (c->nb - k - 1);
         prof_begin(c, KID_CHOL);

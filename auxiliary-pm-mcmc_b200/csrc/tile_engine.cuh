@@ -283,7 +283,7 @@ __device__ __forceinline__ void load_diag_block(double* Ld, double* invd, const 
 #pragma unroll 4
     for (int rr = 0; rr < 16; rr++) {
         const int r = warp * 16 + rr;
-        const double2 v = *reinterpret_cast<const double2*>(Lkk + (size_t)r * ld + lane * 2);
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(Lkk + (size_t)r * ld + lane * 2));
         Ld[r * TSP + lane * 2] = v.x;
         Ld[r * TSP + lane * 2 + 1] = v.y;
         if (r == lane * 2) invd[r] = 1.0 / v.x;
@@ -328,27 +328,52 @@ struct CholParams {
     int nchains;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_step(CholParams p, int k) {
-    extern __shared__ __align__(16) double smem[];
-    // heavy CTAs (the look-ahead diagonal) first in launch order
-    const int rows_per_chain = p.nb - k - 1;
-    int b, i;
-    if ((int)blockIdx.x < p.nchains) {
-        b = blockIdx.x;
-        i = k + 1;
-    } else {
-        const int r = blockIdx.x - p.nchains;
-        b = r / (rows_per_chain - 1);
-        i = k + 2 + r % (rows_per_chain - 1);
+// Dependency tracking of the single-launch ("dataflow") variant: progress[chain][row] = number of finished
+// column blocks of that block row; a task spins (one thread, acquire loads) until its operands exist.
+struct CholFlow {
+    int* counter;        // task queue head (zeroed before the launch)
+    int* progress;       // [nchains][nb], zeroed before the launch
+    const int* skip;     // [nchains] snapshot taken before the launch: non-zero -> chain is not factorised
+    int group;           // chains per scheduling group (group-major, step-major inside a group)
+    int total_tasks;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// all threads call; returns when *p >= need
+__device__ __forceinline__ void wait_progress(const int* p, int need) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_gpu(p) < need) __nanosleep(40);
     }
-    if (p.status[b] != 0) return;
-    if (p.active && !p.active[b]) return;
+    __syncthreads();
+}
+// all threads call after their global stores
+__device__ __forceinline__ void publish_progress(int* p, int v) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(p, v);
+}
+
+// One task of the blocked Cholesky: block L_ik of chain b (k >= 0), plus the diagonal block L_ii if i == k+1.
+template <bool FLOW>
+__device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f, int k, int b, int i, double* smem) {
     const double* src = p.src + chain_index(p.src_idx, b) * p.src_bs;
     double* dst = p.dst + chain_index(p.dst_idx, b) * p.dst_bs;
     const double* sc = p.scale ? p.scale + (long long)b * p.scale_bs : nullptr;
+    int* prog = FLOW ? f.progress + (size_t)b * p.nb : nullptr;
     TileScratch s = carve_scratch(smem);
     Acc acc;
     if (k >= 0) {
+        if (FLOW) {
+            wait_progress(prog + k, k + 1);   // block row k complete (including L_kk)
+            wait_progress(prog + i, k);       // our own row up to column block k-1
+        }
         acc.zero();
         gemm_nt_64x64(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
         tile_load(s.Ts, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
@@ -360,6 +385,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_step(CholParams p, int
         trsm64_smem(s.Ts, s.LT, s.invd);
         __syncthreads();
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + k * TB, p.ldd);
+        if (FLOW && i != k + 1) publish_progress(prog + i, k + 1);
     }
     if (i == k + 1) {
         if (k >= 0) {
@@ -377,6 +403,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_step(CholParams p, int
         potrf64_smem(s.Ts, s.potrf);
         __syncthreads();
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + i * TB, p.ldd);
+        if (FLOW) publish_progress(prog + i, i + 1);
         if (threadIdx.x < 64) {
             double lg = log(s.Ts[threadIdx.x * TSP + threadIdx.x]);
             lg = warp_sum(lg);
@@ -402,6 +429,69 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_step(CholParams p, int
             tile_store(s.LT, p.inv_out + (long long)b * p.inv_bs + (size_t)i * TB * TB, TB);
         }
     }
+    __syncthreads();  // scratch is re-used by the next task of a persistent CTA
+}
+
+// one launch per block column (k = -1 .. nb-2); the heavy CTAs (look-ahead diagonal) come first in launch order
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_step(CholParams p, int k) {
+    extern __shared__ __align__(16) double smem[];
+    const int rows_per_chain = p.nb - k - 1;
+    int b, i;
+    if ((int)blockIdx.x < p.nchains) {
+        b = blockIdx.x;
+        i = k + 1;
+    } else {
+        const int r = blockIdx.x - p.nchains;
+        b = r / (rows_per_chain - 1);
+        i = k + 2 + r % (rows_per_chain - 1);
+    }
+    if (p.status[b] != 0) return;
+    if (p.active && !p.active[b]) return;
+    CholFlow f = {};
+    chol_task<false>(p, f, k, b, i, smem);
+}
+
+// The whole batched factorisation as ONE cooperative launch: persistent CTAs pull tasks from a queue ordered
+// so that every dependency has a lower index (group-major; inside a group step-major with the look-ahead
+// diagonals first), and wait on per-row progress counters instead of kernel boundaries.  No launch tails,
+// the diagonal critical path starts as early as its operands exist, and a group's matrices stay L2-resident.
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_dataflow(CholParams p, CholFlow f) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_task;
+    const int nb = p.nb, G = f.group;
+    const int per_group = G * (1 + nb * (nb - 1) / 2);
+    for (;;) {
+        if (threadIdx.x == 0) s_task = atomicAdd(f.counter, 1);
+        __syncthreads();
+        const int t = s_task;
+        __syncthreads();
+        if (t >= f.total_tasks) return;
+        const int grp = t / per_group;
+        int r = t - grp * per_group;
+        int k, b, i;
+        if (r < G) {
+            k = -1; i = 0; b = grp * G + r;
+        } else {
+            r -= G;
+            k = 0;
+            while (r >= G * (nb - k - 1)) { r -= G * (nb - k - 1); k++; }
+            if (r < G) {
+                b = grp * G + r; i = k + 1;
+            } else {
+                r -= G;
+                b = grp * G + r / (nb - k - 2);
+                i = k + 2 + r % (nb - k - 2);
+            }
+        }
+        if (b >= p.nchains || f.skip[b]) continue;
+        chol_task<true>(p, f, k, b, i, smem);
+    }
+}
+
+// skip[b] = chain b must not be factorised (failed earlier, or converged in the Newton loop)
+__global__ void k_chol_skip_snapshot(const int* status, const int* active, int* skip, int n) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) skip[b] = (status[b] != 0) || (active && !active[b]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -232,7 +232,8 @@ def test_failure_statuses():
     eng = _capi.Engine(X, y, kernel='iso', epsilon=0., max_chains=2, max_nimp=2)
     u = rs.normal(size=(2, 40, 2))
     out, ops, st = eng.estimate_full(np.array([[0., 0.], [0.1, 0.2]]), u, [0, 1])
-    assert list(st) == [_capi.CHAIN_CHOL_K] * 2 and np.all(np.isnan(out))
+    # an exactly singular K: which factorisation trips over the O(eps) pivot is rounding-dependent (as in LAPACK)
+    assert all(v in (_capi.CHAIN_CHOL_K, _capi.CHAIN_CHOL_B, _capi.CHAIN_CHOL_C) for v in st) and np.all(np.isnan(out))
     with pytest.raises(_capi.ApmError):
         eng.estimate_cached([0, 1], u)                      # slots hold no valid cache
     eng.close()
