@@ -42,6 +42,7 @@ __device__ __forceinline__ void gemm_load_stage(double* smA, double* smB, const 
     }
 }
 
+template <bool NEG = false>
 __device__ __forceinline__ void gemm_nt_64x64(Acc& acc, const double* __restrict__ A, int lda,
                                               const double* __restrict__ Bm, int ldb, int kdepth, double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -74,7 +75,7 @@ __device__ __forceinline__ void gemm_nt_64x64(Acc& acc, const double* __restrict
         for (int kk = 0; kk < KC / 4; kk++) {
             double a[4], b[4];
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = a_s[mi * 8 * KCP + kk * 4];
+            for (int mi = 0; mi < 4; mi++) a[mi] = NEG ? -a_s[mi * 8 * KCP + kk * 4] : a_s[mi * 8 * KCP + kk * 4];
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) b[ni] = b_s[ni * 8 * KCP + kk * 4];
 #pragma unroll
@@ -134,6 +135,83 @@ __device__ __forceinline__ void tile_store(const double* Ts, double* __restrict_
         *reinterpret_cast<double2*>(Dm + (size_t)r * ld + lane * 2) = v;
     }
 }
+// acc <- diag(rs) * S * diag(cs) (+ I on a diagonal tile), loaded straight from global memory in the DMMA
+// accumulator layout (each lane: 16-byte pieces C[g][2t..2t+1]).  Issued BEFORE the k-loop so the DRAM
+// latency hides behind the GEMM; the k-loop then subtracts (gemm with NEG=true): acc = S - A B^T.
+__device__ __forceinline__ void acc_load_tile(Acc& acc, const double* __restrict__ S, int ld, const double* rs,
+                                              const double* cs, bool add_identity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        const int r = wm * 32 + mi * 8 + g;
+        const double rsv = rs ? rs[r] : 1.0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int c = wn * 32 + ni * 8 + 2 * t;
+            double2 v = *reinterpret_cast<const double2*>(S + (size_t)r * ld + c);
+            if (rs || cs) {
+                v.x = rsv * v.x * (cs ? cs[c] : 1.0);
+                v.y = rsv * v.y * (cs ? cs[c + 1] : 1.0);
+            }
+            if (add_identity) {
+                if (r == c) v.x += 1.0;
+                if (r == c + 1) v.y += 1.0;
+            }
+            acc.v[mi][ni][0] = v.x;
+            acc.v[mi][ni][1] = v.y;
+        }
+    }
+}
+// acc <- vec[c] broadcast along rows (F = mu + ...)
+__device__ __forceinline__ void acc_load_rowvec(Acc& acc, const double* vec) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & 3, wn = warp & 1;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+        const double2 v = vec ? *reinterpret_cast<const double2*>(vec + wn * 32 + ni * 8 + 2 * t) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            acc.v[mi][ni][0] = v.x;
+            acc.v[mi][ni][1] = v.y;
+        }
+    }
+}
+// Ts <- acc
+__device__ __forceinline__ void tile_put_acc(double* Ts, const Acc& acc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+            *reinterpret_cast<double2*>(Ts + (wm * 32 + mi * 8 + g) * TSP + wn * 32 + ni * 8 + 2 * t) =
+                make_double2(acc.v[mi][ni][0], acc.v[mi][ni][1]);
+}
+// acc -> global, directly from the fragment layout (16-byte stores, 64-byte row segments per quad)
+__device__ __forceinline__ void acc_store_tile(const Acc& acc, double* __restrict__ Dm, int ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++)
+            *reinterpret_cast<double2*>(Dm + (size_t)(wm * 32 + mi * 8 + g) * ld + wn * 32 + ni * 8 + 2 * t) =
+                make_double2(acc.v[mi][ni][0], acc.v[mi][ni][1]);
+}
+// warm L2 with a 64x64 tile that will be needed after the k-loop (2 lines of 128 B per thread)
+__device__ __forceinline__ void prefetch_tile_l2(const double* __restrict__ S, int ld) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int e = threadIdx.x + q * TILE_THREADS;      // 256 lines: row = e / 4, 128-byte piece = e % 4
+        const double* ptr = S + (size_t)(e >> 2) * ld + (e & 3) * 16;
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
+    }
+}
+
 // Ts += sign * acc (fragment layout of the DMMA accumulators)
 __device__ __forceinline__ void tile_add_acc(double* Ts, const Acc& acc, double sign) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -280,14 +358,16 @@ __device__ __forceinline__ void trsm64_smem(double* Ts, const double* Ld, const 
 // stage the diagonal block L_kk (row-major, ld) into Ld (stride TSP) with its reciprocal diagonal
 __device__ __forceinline__ void load_diag_block(double* Ld, double* invd, const double* __restrict__ Lkk, int ld) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 4
+    double2 v[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; rr++)   // all 16 loads in flight before the first use
+        v[rr] = __ldcg(reinterpret_cast<const double2*>(Lkk + (size_t)(warp * 16 + rr) * ld + lane * 2));
+#pragma unroll
     for (int rr = 0; rr < 16; rr++) {
         const int r = warp * 16 + rr;
-        const double2 v = __ldcg(reinterpret_cast<const double2*>(Lkk + (size_t)r * ld + lane * 2));
-        Ld[r * TSP + lane * 2] = v.x;
-        Ld[r * TSP + lane * 2 + 1] = v.y;
-        if (r == lane * 2) invd[r] = 1.0 / v.x;
-        if (r == lane * 2 + 1) invd[r] = 1.0 / v.y;
+        *reinterpret_cast<double2*>(Ld + r * TSP + lane * 2) = v[rr];
+        if (r == lane * 2) invd[r] = 1.0 / v[rr].x;
+        if (r == lane * 2 + 1) invd[r] = 1.0 / v[rr].y;
     }
 }
 
@@ -374,16 +454,14 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
             wait_progress(prog + k, k + 1);   // block row k complete (including L_kk)
             wait_progress(prog + i, k);       // our own row up to column block k-1
         }
-        acc.zero();
-        gemm_nt_64x64(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
-        tile_load(s.Ts, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
-                  sc ? sc + k * TB : nullptr, false);
+        acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
+                      sc ? sc + k * TB : nullptr, false);
+        prefetch_tile_l2(dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
+        gemm_nt_64x64<true>(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
+        tile_put_acc(s.Ts, acc);
         load_diag_block(s.LT, s.invd, dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
         __syncthreads();
-        tile_add_acc(s.Ts, acc, -1.0);
-        __syncthreads();
         trsm64_smem(s.Ts, s.LT, s.invd);
-        __syncthreads();
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + k * TB, p.ldd);
         if (FLOW && i != k + 1) publish_progress(prog + i, k + 1);
     }
@@ -392,16 +470,13 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
             __threadfence();
             __syncthreads();  // the panel block just written is an operand of the diagonal update
         }
-        acc.zero();
-        gemm_nt_64x64(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)i * TB * p.ldd, p.ldd, i * TB, smem);
-        tile_load(s.Ts, src + (size_t)i * TB * p.lds + i * TB, p.lds, sc ? sc + i * TB : nullptr,
-                  sc ? sc + i * TB : nullptr, p.add_identity != 0);
+        acc_load_tile(acc, src + (size_t)i * TB * p.lds + i * TB, p.lds, sc ? sc + i * TB : nullptr,
+                      sc ? sc + i * TB : nullptr, p.add_identity != 0);
+        gemm_nt_64x64<true>(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)i * TB * p.ldd, p.ldd, i * TB, smem);
+        tile_put_acc(s.Ts, acc);
         if (threadIdx.x == 0) s.potrf->fail = 0;
         __syncthreads();
-        tile_add_acc(s.Ts, acc, -1.0);
-        __syncthreads();
         potrf64_smem(s.Ts, s.potrf);
-        __syncthreads();
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + i * TB, p.ldd);
         if (FLOW) publish_progress(prog + i, i + 1);
         if (threadIdx.x < 64) {
@@ -521,15 +596,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_trsm_rows(TrsmParams p) {
     TileScratch s = carve_scratch(smem);
     Acc acc;
     for (int k = 0; k < p.nb; k++) {
-        acc.zero();
-        gemm_nt_64x64(acc, X, p.ldx, L + (size_t)k * TB * p.ldl, p.ldl, k * TB, smem);
-        tile_load(s.Ts, R + k * TB, p.ldr, nullptr, cs ? cs + k * TB : nullptr, false);
+        acc_load_tile(acc, R + k * TB, p.ldr, nullptr, cs ? cs + k * TB : nullptr, false);
+        prefetch_tile_l2(L + (size_t)k * TB * p.ldl + k * TB, p.ldl);
+        gemm_nt_64x64<true>(acc, X, p.ldx, L + (size_t)k * TB * p.ldl, p.ldl, k * TB, smem);
+        tile_put_acc(s.Ts, acc);
         load_diag_block(s.LT, s.invd, L + (size_t)k * TB * p.ldl + k * TB, p.ldl);
         __syncthreads();
-        tile_add_acc(s.Ts, acc, -1.0);
-        __syncthreads();
         trsm64_smem(s.Ts, s.LT, s.invd);
-        __syncthreads();
         tile_store(s.Ts, X + k * TB, p.ldx);
         __threadfence();
         __syncthreads();  // X_rk is an operand of the following block columns
@@ -560,15 +633,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_syrk_sub(SyrkParams p) {
     const double* S = p.S + (long long)b * p.s_bs;
     const double* Z = p.Z + (long long)b * p.z_bs;
     double* C = p.C + chain_index(p.c_idx, b) * p.c_bs;
-    TileScratch s = carve_scratch(smem);
     Acc acc;
-    acc.zero();
-    gemm_nt_64x64(acc, Z + (size_t)i * TB * p.ldz, p.ldz, Z + (size_t)j * TB * p.ldz, p.ldz, p.nb * TB, smem);
-    tile_load(s.Ts, S + (size_t)i * TB * p.lds + j * TB, p.lds, nullptr, nullptr, false);
-    __syncthreads();
-    tile_add_acc(s.Ts, acc, -1.0);
-    __syncthreads();
-    tile_store(s.Ts, C + (size_t)i * TB * p.ldc + j * TB, p.ldc);
+    acc_load_tile(acc, S + (size_t)i * TB * p.lds + j * TB, p.lds, nullptr, nullptr, false);
+    gemm_nt_64x64<true>(acc, Z + (size_t)i * TB * p.ldz, p.ldz, Z + (size_t)j * TB * p.ldz, p.ldz, p.nb * TB, smem);
+    acc_store_tile(acc, C + (size_t)i * TB * p.ldc + j * TB, p.ldc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,19 +662,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_gemm_tri(GemmTriParams p) {
     const double* UT = p.UT + (long long)b * p.u_bs + (size_t)rb * TB * p.ldu;
     const double* L = p.L + chain_index(p.l_idx, b) * p.l_bs + (size_t)k * TB * p.ldl;
     double* F = p.F + (long long)b * p.f_bs + (size_t)rb * TB * p.ldf + k * TB;
-    TileScratch s = carve_scratch(smem);
     Acc acc;
-    acc.zero();
-    gemm_nt_64x64(acc, UT, p.ldu, L, p.ldl, (k + 1) * TB, smem);
-    if (p.mu) {
-        tile_fill_rowvec(s.Ts, p.mu + chain_index(p.mu_idx, b) * p.mu_bs + k * TB);
-    } else {
-        for (int e = threadIdx.x; e < TB * TSP; e += TILE_THREADS) s.Ts[e] = 0.0;
-    }
-    __syncthreads();
-    tile_add_acc(s.Ts, acc, 1.0);
-    __syncthreads();
-    tile_store(s.Ts, F, p.ldf);
+    acc_load_rowvec(acc, p.mu ? p.mu + chain_index(p.mu_idx, b) * p.mu_bs + k * TB : nullptr);
+    gemm_nt_64x64<false>(acc, UT, p.ldu, L, p.ldl, (k + 1) * TB, smem);
+    acc_store_tile(acc, F, p.ldf);
 }
 
 }  // namespace apm
