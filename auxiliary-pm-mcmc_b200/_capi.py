@@ -14,7 +14,7 @@ EXPORTS = [
     'apm_version', 'apm_last_error', 'apm_create', 'apm_destroy', 'apm_set_stream', 'apm_synchronize',
     'apm_set_newton', 'apm_get_info', 'apm_kernel_build', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
-    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_measure_fp64_peak',
+    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
 ]
 
 KERNEL_ISO, KERNEL_ARD = 0, 1
@@ -62,6 +62,7 @@ def lib():
     L.apm_profile_read.argtypes = [vp, ct.c_int, ct.c_char_p, vp, vp, ct.c_int]
     L.apm_launch_count.argtypes = [vp, ct.c_int]
     L.apm_launch_count.restype = ct.c_int64
+    L.apm_dev_chol_bench.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, dp]
     L.apm_measure_fp64_peak.argtypes = [ct.c_int, ct.c_int, dp]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -163,6 +164,11 @@ class Engine(object):
             name = names.raw[32 * i:32 * (i + 1)].split(b'\0')[0].decode()
             out[name] = (float(ms[i]), int(cnt[i]))
         return out
+
+    def dev_chol_bench(self, B, reps=5, mode=0):
+        out = ct.c_double(0.)
+        check(self._L.apm_dev_chol_bench(self._h, int(B), int(reps), int(mode), ct.byref(out)))
+        return out.value
 
     def launch_count(self, reset=False):
         return int(self._L.apm_launch_count(self._h, 1 if reset else 0))

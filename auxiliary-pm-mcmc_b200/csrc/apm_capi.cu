@@ -61,7 +61,7 @@ struct apm_ctx {
     double* dLdB = nullptr;
     int *dFlowCounter = nullptr, *dFlowProgress = nullptr, *dFlowSkip = nullptr;
     int flow_grid = 0;        // persistent grid of k_chol_dataflow (SMs x occupancy); 0 = per-step launches
-    int flow_group = 32;      // chains per scheduling group
+    int flow_group = 1 << 20; // chains per scheduling group (default: all chains = step-major order)
     double* dInvB = nullptr;   // (L_kk^{-1})^T diagonal blocks of chol(B): [max_chains][nb][64*64]
     double* dVec[V_COUNT] = {nullptr};
     double *dUT = nullptr, *dF = nullptr, *dZf = nullptr, *dUstage = nullptr;
@@ -199,7 +199,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_dataflow, TILE_THREADS, TILE_SMEM_BYTES) == cudaSuccess &&
             occ > 0 && coop && !getenv("APM_CHOL_STEPWISE"))
             c->flow_grid = occ * sms;
-        if (getenv("APM_CHOL_GROUP")) c->flow_group = atoi(getenv("APM_CHOL_GROUP")) > 0 ? atoi(getenv("APM_CHOL_GROUP")) : 32;
+        if (getenv("APM_CHOL_GROUP")) c->flow_group = atoi(getenv("APM_CHOL_GROUP")) > 0 ? atoi(getenv("APM_CHOL_GROUP")) : (1 << 20);
     }
     const size_t B = max_chains, np = c->np;
     int rc = APM_OK;
@@ -420,6 +420,8 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
         f.group = c->flow_group < B ? c->flow_group : B;
         const int ngroups = (B + f.group - 1) / f.group;
         f.total_tasks = ngroups * f.group * (1 + c->nb * (c->nb - 1) / 2);
+        f.flags = getenv("APM_FLOW_FLAGS") ? atoi(getenv("APM_FLOW_FLAGS")) : 0;
+        f.spin_ns = getenv("APM_SPIN_NS") ? atoi(getenv("APM_SPIN_NS")) : 100;
         CU_TRY(cudaMemsetAsync(c->dFlowCounter, 0, sizeof(int), c->stream));
         CU_TRY(cudaMemsetAsync(c->dFlowProgress, 0, sizeof(int) * (size_t)B * c->nb, c->stream));
         prof_begin(c, KID_MISC);
@@ -897,6 +899,127 @@ extern "C" int apm_slot_copy(apm_ctx* c, const int* src, const int* dst, int B) 
     }
     return APM_OK;
 }
+
+// dev/tuning entry (not part of the reference-facing surface): time `reps` batched Cholesky factorisations
+// of the K matrices currently in the context (after apm_kernel_build) into slots 0..B-1.  mode 0: default
+// path, 1: force per-step launches.
+extern "C" int apm_dev_chol_bench(apm_ctx* c, int B, int reps, int mode, double* ms_out) {
+    APM_TRY(check_B(c, B));
+    if (B > c->nslots || !ms_out) return APM_ERR_INVALID;
+    APM_TRY(reset_status(c, B));
+    for (int b = 0; b < B; b++) c->hInts[b] = b;
+    CU_TRY(cudaMemcpyAsync(c->dSlotsA, c->hInts, sizeof(int) * B, cudaMemcpyHostToDevice, c->stream));
+    const int saved = c->flow_grid;
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    int rc = APM_OK;
+    const int variant = mode >> 4;   // 0: chol(K) -> slot, 1: chol(I + Ws K Ws) -> LB (Newton step), 2: as 1 with 1/8 of the chains active
+    mode &= 15;
+    if (mode == 1) c->flow_grid = 0;
+    if (variant >= 1) {
+        k_fill_double<<<(unsigned)(((size_t)B * c->np + 255) / 256), 256, 0, c->stream>>>(c->dVec[V_WS], 0.5, (long long)B * c->np);
+        k_fill_int<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dActive, 1, B);
+        if (variant == 2) {
+            std::vector<int> act(B, 0);
+            for (int b = 0; b < B; b += 8) act[b] = 1;
+            cudaMemcpyAsync(c->dActive, act.data(), sizeof(int) * B, cudaMemcpyHostToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);
+        }
+    }
+    for (int r = 0; r < reps + 1 && rc == APM_OK; r++) {
+        if (r == 1) cudaEventRecord(e0, c->stream);
+        if (variant == 0)
+            rc = run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dSlotLK, (long long)c->mat, c->dSlotsA, nullptr, 0,
+                          c->dSlotLdK, c->dSlotsA, APM_CHAIN_CHOL_K, nullptr, c->dInvB);
+        else
+            rc = run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, c->dVec[V_WS], 1,
+                          c->dLdB, nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB);
+    }
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->flow_grid = saved;
+    *ms_out = ms / reps;
+    return rc;
+}
+
+// dev: time k_syrk_sub (a pure tile GEMM, depth n) at a forced occupancy (extra dynamic smem)
+extern "C" int apm_dev_syrk_bench(apm_ctx* c, int B, int reps, int smem_bytes, double* ms_out) {
+    APM_TRY(check_B(c, B));
+    APM_TRY(reset_status(c, B));
+    CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SyrkParams s;
+    s.S = c->dK; s.s_bs = (long long)c->mat; s.lds = c->np;
+    s.Z = c->dK; s.z_bs = (long long)c->mat; s.ldz = c->np;
+    s.C = c->dLB; s.c_bs = (long long)c->mat; s.ldc = c->np; s.c_idx = nullptr;
+    s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
+    s.status = c->dStatus;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int r = 0; r < reps + 1; r++) {
+        if (r == 1) cudaEventRecord(e0, c->stream);
+        k_syrk_sub<<<B * s.ntiles, TILE_THREADS, smem_bytes, c->stream>>>(s);
+    }
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = ms / reps;
+    return cudaGetLastError() == cudaSuccess ? APM_OK : APM_ERR_CUDA;
+}
+
+// dev: DMMA TFLOP/s with `warps_per_sm` resident warps (one CTA per SM) and nacc (1, 4, 16) independent
+// accumulator chains per warp
+extern "C" int apm_dev_dmma_sweep(int device, int warps_per_sm, int nacc, double* tflops) {
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CU_TRY(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 20000 * 16 / nacc, blocks = prop.multiProcessorCount, threads = warps_per_sm * 32;
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        if (nacc == 1) k_peak_dmma_n<1><<<blocks, threads>>>(d, iters);
+        else if (nacc == 4) k_peak_dmma_n<4><<<blocks, threads>>>(d, iters);
+        else k_peak_dmma_n<16><<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = (double)blocks * warps_per_sm * iters * nacc * 512.0 / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return cudaGetLastError() == cudaSuccess ? APM_OK : APM_ERR_CUDA;
+}
+
+#ifdef APM_PHASE_TIMING
+extern "C" int apm_dev_phase_read(unsigned long long* cycles, unsigned long long* counts, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(cycles, g_phase_cycles, sizeof(unsigned long long) * 16);
+    cudaMemcpyFromSymbol(counts, g_phase_counts, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+        cudaMemcpyToSymbol(g_phase_counts, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // fp64 peak probes

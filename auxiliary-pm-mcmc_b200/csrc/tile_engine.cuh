@@ -150,7 +150,7 @@ __device__ __forceinline__ void acc_load_tile(Acc& acc, const double* __restrict
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) {
             const int c = wn * 32 + ni * 8 + 2 * t;
-            double2 v = *reinterpret_cast<const double2*>(S + (size_t)r * ld + c);
+            double2 v = __ldcg(reinterpret_cast<const double2*>(S + (size_t)r * ld + c));
             if (rs || cs) {
                 v.x = rsv * v.x * (cs ? cs[c] : 1.0);
                 v.y = rsv * v.y * (cs ? cs[c + 1] : 1.0);
@@ -317,41 +317,69 @@ __device__ __forceinline__ void potrf64_smem(double* Ts, PotrfScratch* sc) {
 }
 
 // Ts <- Ts * L^{-T} for a 64x64 tile; Ld = L (64x64 lower, row-major, stride TSP), invd[c] = 1 / L[c][c].
-// All 128 threads call this.
+// Right-looking over 8-column panels with the whole tile register-resident: every warp owns 16 rows
+// (2 m-tiles x 8 n-tiles of DMMA accumulators) and needs nothing from the other warps, so the only
+// synchronisation is __syncwarp.  Per panel: the 16x8 panel goes through shared memory to 16 lanes that solve
+// it exactly against the 8x8 diagonal sub-block (substitution, one row per lane), comes back as DMMA
+// A-fragments, and is subtracted from all panels to its right (independent accumulators, chains of length 2).
+// The caller must __syncthreads() before (Ts, Ld complete) and after (Ts readable by other warps).
 __device__ __forceinline__ void trsm64_smem(double* Ts, const double* Ld, const double* invd) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
+    double* rows = Ts + warp * 16 * TSP;
+    double acc[2][8][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const double2 v = *reinterpret_cast<const double2*>(rows + (mt * 8 + g) * TSP + nt * 8 + 2 * t);
+            acc[mt][nt][0] = v.x;
+            acc[mt][nt][1] = v.y;
+        }
+#pragma unroll
     for (int p = 0; p < 8; p++) {
         const int c0 = p * 8;
         if (p > 0) {
-            // X[:, c0:c0+8] -= X[:, 0:c0] * L[c0:c0+8, 0:c0]^T
 #pragma unroll
-            for (int mi = 0; mi < 2; mi++) {
-                const int mt = warp * 2 + mi;
-                double* dp = Ts + (mt * 8 + g) * TSP + c0 + 2 * t;
-                double d0 = dp[0], d1 = dp[1];
-                const double* ap = Ts + (mt * 8 + g) * TSP + t;
-                const double* bp = Ld + (c0 + g) * TSP + t;
-                for (int k0 = 0; k0 < c0; k0 += 4) dmma884(d0, d1, -ap[k0], bp[k0]);
-                dp[0] = d0;
-                dp[1] = d1;
-            }
-            __syncthreads();
+            for (int mt = 0; mt < 2; mt++)
+                *reinterpret_cast<double2*>(rows + (mt * 8 + g) * TSP + c0 + 2 * t) = make_double2(acc[mt][p][0], acc[mt][p][1]);
+            __syncwarp();
         }
-        if (tid < 64) {
-            double* row = Ts + tid * TSP + c0;
+        if (lane < 16) {
+            double* row = rows + lane * TSP + c0;
+            double l8[8][8];
+#pragma unroll
+            for (int j = 1; j < 8; j++)
+#pragma unroll
+                for (int k = 0; k < j; k++) l8[j][k] = Ld[(c0 + j) * TSP + c0 + k];
             double x[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 double v = row[j];
 #pragma unroll
-                for (int k = 0; k < j; k++) v = fma(-x[k], Ld[(c0 + j) * TSP + c0 + k], v);
+                for (int k = 0; k < j; k++) v = fma(-x[k], l8[j][k], v);
                 x[j] = v * invd[c0 + j];
             }
 #pragma unroll
             for (int j = 0; j < 8; j++) row[j] = x[j];
         }
-        __syncthreads();
+        __syncwarp();
+        if (p < 7) {
+            double a[2][2];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) a[mt][kk] = -rows[(mt * 8 + g) * TSP + c0 + kk * 4 + t];
+#pragma unroll
+            for (int q = p + 1; q < 8; q++) {
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+                    const double bq = Ld[(q * 8 + g) * TSP + c0 + kk * 4 + t];
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) dmma884(acc[mt][q][0], acc[mt][q][1], a[mt][kk], bq);
+                }
+            }
+        }
     }
 }
 
@@ -416,20 +444,26 @@ struct CholFlow {
     const int* skip;     // [nchains] snapshot taken before the launch: non-zero -> chain is not factorised
     int group;           // chains per scheduling group (group-major, step-major inside a group)
     int total_tasks;
+    int flags;           // tuning switches (dev): 1 = load the source tile before waiting, 2 = no L2 prefetch
+    int spin_ns;
 };
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+// relaxed polling load (no L1 invalidation per poll); the acquire fence is issued once after the spin
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 // all threads call; returns when *p >= need
-__device__ __forceinline__ void wait_progress(const int* p, int need) {
+__device__ __forceinline__ void wait_progress(const int* p, int need, int spin_ns = 100) {
     if (threadIdx.x == 0) {
-        while (ld_acquire_gpu(p) < need) __nanosleep(40);
+        if (ld_relaxed_gpu(p) < need) {
+            do { __nanosleep(spin_ns); } while (ld_relaxed_gpu(p) < need);
+        }
+        __threadfence();
     }
     __syncthreads();
 }
@@ -440,6 +474,23 @@ __device__ __forceinline__ void publish_progress(int* p, int v) {
     if (threadIdx.x == 0) st_release_gpu(p, v);
 }
 
+#ifdef APM_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_phase_counts[16];
+#define PHASE_MARK(id)                                                          \
+    do {                                                                        \
+        __syncthreads();                                                        \
+        if (threadIdx.x == 0) {                                                 \
+            const long long now__ = clock64();                                  \
+            atomicAdd(&g_phase_cycles[id], (unsigned long long)(now__ - t_phase)); \
+            atomicAdd(&g_phase_counts[id], 1ull);                               \
+            t_phase = now__;                                                    \
+        }                                                                       \
+    } while (0)
+#else
+#define PHASE_MARK(id) do {} while (0)
+#endif
+
 // One task of the blocked Cholesky: block L_ik of chain b (k >= 0), plus the diagonal block L_ii if i == k+1.
 template <bool FLOW>
 __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f, int k, int b, int i, double* smem) {
@@ -449,21 +500,34 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
     int* prog = FLOW ? f.progress + (size_t)b * p.nb : nullptr;
     TileScratch s = carve_scratch(smem);
     Acc acc;
+#ifdef APM_PHASE_TIMING
+    long long t_phase = clock64();
+#endif
     if (k >= 0) {
+        const bool early = FLOW && (f.flags & 1);
+        // the source tile never depends on other tasks (in-place: nobody has written tile (i,k) yet)
+        if (early) acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
+                                 sc ? sc + k * TB : nullptr, false);
         if (FLOW) {
-            wait_progress(prog + k, k + 1);   // block row k complete (including L_kk)
-            wait_progress(prog + i, k);       // our own row up to column block k-1
+            wait_progress(prog + k, k + 1, f.spin_ns);   // block row k complete (including L_kk)
+            wait_progress(prog + i, k, f.spin_ns);       // our own row up to column block k-1
         }
-        acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
-                      sc ? sc + k * TB : nullptr, false);
-        prefetch_tile_l2(dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
+        if (!early) acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
+                                  sc ? sc + k * TB : nullptr, false);
+        PHASE_MARK(0);  // waits + source tile load issue
+        if (!(FLOW && (f.flags & 2))) prefetch_tile_l2(dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
         gemm_nt_64x64<true>(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
+        PHASE_MARK(1);  // panel GEMM
         tile_put_acc(s.Ts, acc);
         load_diag_block(s.LT, s.invd, dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
         __syncthreads();
+        PHASE_MARK(2);  // stage T and L_kk
         trsm64_smem(s.Ts, s.LT, s.invd);
+        __syncthreads();
+        PHASE_MARK(3);  // triangular solve
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + k * TB, p.ldd);
         if (FLOW && i != k + 1) publish_progress(prog + i, k + 1);
+        PHASE_MARK(4);  // store + publish
     }
     if (i == k + 1) {
         if (k >= 0) {
@@ -473,12 +537,15 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
         acc_load_tile(acc, src + (size_t)i * TB * p.lds + i * TB, p.lds, sc ? sc + i * TB : nullptr,
                       sc ? sc + i * TB : nullptr, p.add_identity != 0);
         gemm_nt_64x64<true>(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)i * TB * p.ldd, p.ldd, i * TB, smem);
+        PHASE_MARK(5);  // diagonal GEMM
         tile_put_acc(s.Ts, acc);
         if (threadIdx.x == 0) s.potrf->fail = 0;
         __syncthreads();
         potrf64_smem(s.Ts, s.potrf);
+        PHASE_MARK(6);  // 64x64 Cholesky
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + i * TB, p.ldd);
         if (FLOW) publish_progress(prog + i, i + 1);
+        PHASE_MARK(7);  // store + publish
         if (threadIdx.x < 64) {
             double lg = log(s.Ts[threadIdx.x * TSP + threadIdx.x]);
             lg = warp_sum(lg);
@@ -501,8 +568,10 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
             if (threadIdx.x < 64) s.invd[threadIdx.x] = 1.0 / s.Ts[threadIdx.x * TSP + threadIdx.x];
             __syncthreads();
             trsm64_smem(s.LT, s.Ts, s.invd);
+            __syncthreads();
             tile_store(s.LT, p.inv_out + (long long)b * p.inv_bs + (size_t)i * TB * TB, TB);
         }
+        PHASE_MARK(8);  // log-det + inverse of the diagonal block
     }
     __syncthreads();  // scratch is re-used by the next task of a persistent CTA
 }
@@ -603,6 +672,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_trsm_rows(TrsmParams p) {
         load_diag_block(s.LT, s.invd, L + (size_t)k * TB * p.ldl + k * TB, p.ldl);
         __syncthreads();
         trsm64_smem(s.Ts, s.LT, s.invd);
+        __syncthreads();
         tile_store(s.Ts, X + k * TB, p.ldx);
         __threadfence();
         __syncthreads();  // X_rk is an operand of the following block columns

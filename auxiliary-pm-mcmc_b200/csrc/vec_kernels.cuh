@@ -498,6 +498,22 @@ __global__ void k_peak_dmma(double* out, int iters) {
     for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
     if (s == 123.456) out[0] = s;
 }
+// DMMA throughput as a function of resident warps: NACC independent accumulators per warp
+template <int NACC>
+__global__ void k_peak_dmma_n(double* out, int iters) {
+    double c[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) c[i][0] = c[i][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, bb = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < NACC; i++) dmma884(c[i][0], c[i][1], a, bb);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
 __global__ void k_peak_dfma(double* out, int iters) {
     double c[16];
 #pragma unroll

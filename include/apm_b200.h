@@ -175,6 +175,10 @@ int apm_profile_read(apm_ctx* ctx, int max_entries, char* names, double* ms, int
  * it as gpu_launches). */
 int64_t apm_launch_count(apm_ctx* ctx, int reset);
 
+/* Tuning aid: average milliseconds of one batched Cholesky of the context's current K matrices (B chains,
+ * after apm_kernel_build) into slots 0..B-1.  mode 0 = default path, 1 = per-step launches. */
+int apm_dev_chol_bench(apm_ctx* ctx, int B, int reps, int mode, double* ms_out);
+
 /* Micro-benchmarks used by bench.py to measure the fp64 roofline denominators on the box:
  * kind 0: DMMA m8n8k4 issue peak, 1: DFMA peak.  Returns TFLOP/s in *tflops. */
 int apm_measure_fp64_peak(int device, int kind, double* tflops);

@@ -1,0 +1,16 @@
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from apm_b200 import _capi, synth
+n, D, B = 768, 8, int(os.environ.get('B', 256))
+X, y, th = synth.make_dataset(n, D, seed=0)
+thetas = synth.bulk_thetas(B, D)
+eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=B, max_nimp=1)
+import torch
+K = torch.empty(B, n, n, dtype=torch.float64, device='cuda')
+eng.kernel_build(thetas, out=K)
+flop = B * n**3 / 3.
+for mode in [int(v) for v in os.environ.get('MODES', '0,1').split(',')]:
+    ms = eng.dev_chol_bench(B, reps=5, mode=mode)
+    print('%s mode=%d  %.3f ms  %.2f TF/s' % (os.environ.get('TAG', ''), mode, ms, flop / ms / 1e9), flush=True)
