@@ -1,0 +1,294 @@
+"""Lock-step batched drivers for the auxiliary pseudo-marginal samplers: B independent chains advance
+together so that every log-ML estimate they need becomes one batched C-ABI call.
+
+The reference runs chains one after another (notebook cell 14: `for c in range(n_chain)`) and each chain
+is scalar Python control flow around `log_f_estimator` (auxpm/samplers.py, auxpm/mcmc_updates.py).  Here
+every chain is a generator that *yields* its next estimate request -- ('full', theta) or ('cached', u) --
+and is resumed with the value; the scheduler gathers the requests of all live chains, issues one
+`apm_estimate_full` and one `apm_estimate_cached` call per round, and hands the results back.  Slice /
+elliptical-slice shrink loops therefore stay data dependent per chain (no masking tricks): a chain that
+needs three shrink steps simply takes part in three rounds.
+
+Per chain the arithmetic, the order of random draws and the cache hand-over
+(current / proposed slot, swapped on acceptance: smp.py:413-417, 1079-1086) are those of the single-chain
+classes in `apm_b200.samplers`, so with `rng='parity'` (one `numpy.random.RandomState(seed)` per chain, u
+drawn on the host) chain c reproduces the single-chain / reference trace for the same seed, independently of
+how many chains share the batch or how they are sharded over GPUs.  `rng='device'` keeps u in HBM
+(torch CUDA generator, not stream-identical to numpy) for throughput runs.
+"""
+import numpy as np
+
+from . import utils
+
+TWO_PI = 2. * np.pi
+
+
+class ChainFailure(Exception):
+    """A chain hit one of the reference's exceptions (status code of the C ABI)."""
+
+    def __init__(self, status):
+        Exception.__init__(self, 'chain failed with status %d' % status)
+        self.status = status
+
+
+class EngineBackend(object):
+    """Batched estimate calls on an apm_b200._capi.Engine.  `u` arguments are lists of per-chain arrays
+    (numpy (n, N) on the host in parity mode, torch CUDA tensors in device mode)."""
+
+    def __init__(self, engine):
+        self.engine = engine
+
+    def _stack(self, us):
+        if isinstance(us[0], np.ndarray):
+            return np.ascontiguousarray(np.stack(us))
+        import torch
+        return torch.stack(us).contiguous()
+
+    def full(self, thetas, us, slots):
+        return self.engine.estimate_full(np.asarray(thetas), self._stack(us), slots)
+
+    def cached(self, slots, us):
+        return self.engine.estimate_cached(slots, self._stack(us))
+
+    def laplace_lml(self, thetas):
+        return self.engine.laplace_lml(np.asarray(thetas))
+
+
+class _Chain(object):
+    """State of one chain + its generator."""
+
+    def __init__(self, index, seed, theta_init):
+        self.index = index
+        self.prng = np.random.RandomState(seed)
+        self.theta = np.array(theta_init, dtype=np.float64)
+        self.u = None
+        self.log_f = None
+        self.cur_slot = 2 * index
+        self.prop_slot = 2 * index + 1
+        self.n_reject = [0, 0]
+        self.n_cubic_ops = 0
+        self.n_full = 0
+        self.n_cached = 0
+        self.failed = None
+
+
+class BatchedAPMSampler(object):
+    """B chains of one of the composite samplers in lock-step.
+
+    method: 'mi+mh', 'ess+mh', 'mi+rdss', 'ess+rdss' (u-update + theta-update) or 'pmmh' (fresh u inside every
+    estimate, smp.py:159-262 with the notebooks' main-phase closure).
+    log_prior(theta) -> float is added to every estimate (the notebooks' closure, nb cell 12).
+    prop_scales: random-walk scales of the MH theta-update (copied per chain; see SURVEY App. B on the
+    reference's aliasing quirk).  slice_width: w of the random-direction slice update (max_steps_out = 0).
+    """
+
+    def __init__(self, backend, n_data, n_imp, n_theta, method, log_prior, seeds, prop_scales=None, slice_width=1.,
+                 max_slice_iters=1000, rng='parity', device=None):
+        if method not in ('mi+mh', 'ess+mh', 'mi+rdss', 'ess+rdss', 'pmmh'):
+            raise ValueError('unknown method %r' % method)
+        if rng not in ('parity', 'device'):
+            raise ValueError("rng must be 'parity' or 'device'")
+        self.backend = backend
+        self.n, self.N, self.P = int(n_data), int(n_imp), int(n_theta)
+        self.method = method
+        self.log_prior = log_prior
+        self.seeds = list(seeds)
+        self.B = len(self.seeds)
+        self.prop_scales = None if prop_scales is None else np.array(prop_scales, dtype=np.float64)
+        self.slice_width = float(slice_width)
+        self.max_slice_iters = int(max_slice_iters)
+        self.rng = rng
+        self.device = device
+        self._gen = None
+        if rng == 'device':
+            import torch
+            self._torch = torch
+            self._gen = torch.Generator(device=device)
+            self._gen.manual_seed(int(self.seeds[0]) * 7919 + 17)
+
+    # ---- random draws -----------------------------------------------------------------------------
+    def _draw_u(self, ch):
+        """u_sampler(): n*N standard normals, row-major (nb cell 12: prng.normal(size=(n, N)))."""
+        if self.rng == 'parity':
+            return ch.prng.normal(size=(self.n, self.N))
+        return self._torch.randn(self.n, self.N, dtype=self._torch.float64, device=self.device, generator=self._gen)
+
+    def _ellipse(self, u, v, phi):
+        if self.rng == 'parity':
+            return u * np.cos(phi) + v * np.sin(phi)              # mu.py:382
+        return u * float(np.cos(phi)) + v * float(np.sin(phi))
+
+    # ---- one chain as a generator of estimate requests -------------------------------------------------
+    def _u_update_mi(self, ch):
+        u_prop = self._draw_u(ch)                                   # mu.py:284-288
+        log_f_prop = yield ('cached', u_prop)
+        if ch.prng.uniform() < np.exp(log_f_prop - ch.log_f):       # mu.py:299-303
+            ch.u, ch.log_f = u_prop, log_f_prop
+        else:
+            ch.n_reject[0] += 1
+
+    def _u_update_ess(self, ch):
+        v = self._draw_u(ch)                                        # smp.py:786
+        log_y = ch.log_f + np.log(ch.prng.uniform())                # mu.py:373
+        phi = ch.prng.uniform() * TWO_PI                            # mu.py:375
+        lo, hi = phi - TWO_PI, phi
+        for _ in range(self.max_slice_iters):
+            u_prop = self._ellipse(ch.u, v, phi)
+            log_f_prop = yield ('cached', u_prop)
+            if log_f_prop > log_y:
+                ch.u, ch.log_f = u_prop, log_f_prop
+                return
+            if phi < 0:
+                lo = phi
+            elif phi > 0:
+                hi = phi
+            else:
+                return                                              # slice collapsed (mu.py:391-393)
+            phi = lo + ch.prng.uniform() * (hi - lo)
+        raise ChainFailure(2)
+
+    def _theta_update_mh(self, ch):
+        s = self.prop_scales
+        theta_prop = ch.theta + s * np.array([ch.prng.normal() for _ in range(self.P)])   # nb cell 12 prop_sampler
+        log_f_prop = yield ('full', theta_prop)
+        # symmetric Gaussian random walk: forward and backward proposal densities cancel (mu.py:149-152)
+        fwd = -0.5 * np.sum(((theta_prop - ch.theta) / s)**2)
+        bwd = -0.5 * np.sum(((ch.theta - theta_prop) / s)**2)
+        if ch.prng.uniform() < np.exp(log_f_prop + bwd - ch.log_f - fwd):
+            ch.theta, ch.log_f = theta_prop, log_f_prop
+            ch.cur_slot, ch.prop_slot = ch.prop_slot, ch.cur_slot   # smp.py:413-417
+        else:
+            ch.n_reject[1] += 1
+
+    def _theta_update_rdss(self, ch):
+        d = ch.prng.normal(size=self.P)                             # nb-rdss cell 12 dir_and_w_sampler
+        d /= d.dot(d)**0.5
+        w = self.slice_width
+        log_y = np.log(ch.prng.uniform()) + ch.log_f                # mu.py:481
+        lo = 0. - w * ch.prng.uniform()                             # mu.py:483-484
+        hi = lo + w
+        base = ch.theta.copy()
+        for _ in range(self.max_slice_iters):
+            x = lo + (hi - lo) * ch.prng.uniform()                  # mu.py:503
+            log_f_prop = yield ('full', base + x * d)
+            # every evaluation overwrites the current cache (smp.py:1083-1085)
+            ch.cur_slot, ch.prop_slot = ch.prop_slot, ch.cur_slot
+            if log_f_prop > log_y:
+                ch.theta, ch.log_f = base + x * d, log_f_prop
+                return
+            if x < 0.:
+                lo = x
+            elif x > 0.:
+                hi = x
+            else:
+                return
+        raise ChainFailure(2)
+
+    def _pmmh_update(self, ch):
+        s = self.prop_scales
+        theta_prop = ch.theta + s * np.array([ch.prng.normal() for _ in range(self.P)])
+        ch.u = self._draw_u(ch)                                     # fresh normals inside the estimate closure
+        log_f_prop = yield ('full', theta_prop)
+        fwd = -0.5 * np.sum(((theta_prop - ch.theta) / s)**2)
+        bwd = -0.5 * np.sum(((ch.theta - theta_prop) / s)**2)
+        if ch.prng.uniform() < np.exp(log_f_prop + bwd - ch.log_f - fwd):
+            ch.theta, ch.log_f = theta_prop, log_f_prop
+        else:
+            ch.n_reject[1] += 1
+
+    def _run_chain(self, ch, n_sample, trace):
+        trace[0] = ch.theta
+        if self.method == 'pmmh':
+            ch.u = self._draw_u(ch)
+            ch.log_f = yield ('full', ch.theta)
+            for s in range(1, n_sample):
+                yield from self._pmmh_update(ch)
+                trace[s] = ch.theta
+            return
+        ch.u = self._draw_u(ch)                                      # smp.py:377 / 546 / 689 / 825
+        ch.log_f = yield ('full', ch.theta)
+        ch.cur_slot, ch.prop_slot = ch.prop_slot, ch.cur_slot        # the first estimate's cache is current
+        u_step = self._u_update_mi if self.method.startswith('mi') else self._u_update_ess
+        th_step = self._theta_update_mh if self.method.endswith('mh') else self._theta_update_rdss
+        for s in range(1, n_sample):
+            yield from u_step(ch)
+            yield from th_step(ch)
+            trace[s] = ch.theta
+
+    # ---- the lock-step scheduler ----------------------------------------------------------------------
+    def get_samples(self, theta_init, n_sample, theta_init_sampler=None):
+        """theta_init: (B, n_theta), or None with theta_init_sampler(prng) -> theta drawing each chain's start
+        from its own stream right after seeding (as the notebooks do, nb cell 14).  Returns dict(thetas
+        (B, n_sample, P), n_reject (B, 2), n_cubic_ops (B,), n_full (B,), n_cached (B,), failed (B,) status
+        codes, rounds)."""
+        B = self.B
+        if theta_init is None:
+            chains = [_Chain(c, self.seeds[c], np.zeros(self.P)) for c in range(B)]
+            for ch in chains:
+                ch.theta = np.array(theta_init_sampler(ch.prng), dtype=np.float64)
+        else:
+            theta_init = np.asarray(theta_init, dtype=np.float64)
+            chains = [_Chain(c, self.seeds[c], theta_init[c]) for c in range(B)]
+        traces = np.full((B, n_sample, self.P), np.nan)
+        gens = [self._run_chain(ch, n_sample, traces[c]) for c, ch in enumerate(chains)]
+        pending = {}
+        for c, g in enumerate(gens):
+            pending[c] = next(g)
+        rounds = 0
+        while pending:
+            rounds += 1
+            full = [c for c, r in pending.items() if r[0] == 'full']
+            cached = [c for c, r in pending.items() if r[0] == 'cached']
+            results = {}
+            if full:
+                thetas = np.stack([pending[c][1] for c in full])
+                us = [chains[c].u for c in full]
+                slots = [chains[c].prop_slot for c in full]      # written into the proposal slot
+                vals, ops, st = self.backend.full(thetas, us, slots)
+                for j, c in enumerate(full):
+                    ch = chains[c]
+                    ch.n_full += 1
+                    if st[j] != 0:
+                        results[c] = ChainFailure(int(st[j]))
+                    else:
+                        ch.n_cubic_ops += int(ops[j])
+                        results[c] = float(vals[j]) + self.log_prior(pending[c][1])
+            if cached:
+                us = [pending[c][1] for c in cached]
+                slots = [chains[c].cur_slot for c in cached]
+                vals, st = self.backend.cached(slots, us)
+                for j, c in enumerate(cached):
+                    ch = chains[c]
+                    ch.n_cached += 1
+                    if st[j] != 0:
+                        results[c] = ChainFailure(int(st[j]))
+                    else:
+                        results[c] = float(vals[j]) + self.log_prior(ch.theta)
+            new_pending = {}
+            for c, res in results.items():
+                try:
+                    if isinstance(res, ChainFailure):
+                        raise res
+                    new_pending[c] = gens[c].send(res)
+                except StopIteration:
+                    pass
+                except ChainFailure as e:           # the notebooks skip a failing chain (nb cell 14)
+                    chains[c].failed = e.status
+            pending = new_pending
+        return dict(thetas=traces, n_reject=np.array([ch.n_reject for ch in chains]),
+                    n_cubic_ops=np.array([ch.n_cubic_ops for ch in chains]),
+                    n_full=np.array([ch.n_full for ch in chains]), n_cached=np.array([ch.n_cached for ch in chains]),
+                    failed=np.array([0 if ch.failed is None else ch.failed for ch in chains]), rounds=rounds)
+
+
+def make_log_prior(D, ard):
+    """The notebooks' log-Gamma prior (nb cell 8 + cell 12), same tau prior for every ARD length-scale."""
+    from . import synth
+    p = synth.prior_params(D)
+
+    def log_prior(theta):
+        v = utils.log_gamma_log_pdf(theta[0], p['a_sigma'], p['b_sigma'])
+        for t in theta[1:]:
+            v = v + utils.log_gamma_log_pdf(t, p['a_tau'], p['b_tau'])
+        return v
+    return log_prior

@@ -288,6 +288,21 @@ def run_gpu_arm(args):
     # ---- the O(n^2 N) cached estimate (u-updates), for context
     ms_cached, _ = timed(step_cached, max(args.steps, 3))
 
+    # ---- APM-MCMC iterations/s: ESS-u + RD-SS-theta in lock-step over the same chains (device-resident u)
+    from apm_b200 import batched
+    drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, 'ess+rdss', batched.make_log_prior(D, True),
+                                    [1000 + rank * B + c for c in range(B)], rng='device', device=dev)
+    apm_iters = args.apm_iters
+    barrier()
+    t_apm = time.perf_counter()
+    apm_out = drv.get_samples(thetas[0], apm_iters + 1)
+    barrier()
+    t_apm = time.perf_counter() - t_apm
+    t_apm_t = torch.tensor([t_apm], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_apm_t, op=dist.ReduceOp.MAX)
+    t_apm = float(t_apm_t.item())
+
     # ---- diagnostics gather over NCCL (per-chain log-ML of the last step): the only collective of the path
     last = torch.from_numpy(outs[-1][0]).to(dev)
     if world > 1:
@@ -359,6 +374,11 @@ def run_gpu_arm(args):
             'roofline': roofline,
             'cpu_baseline': cpu,
             'cached_estimates_per_s': world * B * max(args.steps, 3) / (ms_cached * 1e-3),
+            'apm_iters_per_s': {'value': world * B * apm_iters / t_apm, 'unit': 'chain-iterations/s',
+                                'method': 'E-SS u + RD-SS theta, lock-step, %d chains/GPU, %d iterations, device RNG' % (B, apm_iters),
+                                'full_estimates_per_iter': float(apm_out['n_full'].mean() - 1) / apm_iters,
+                                'cached_estimates_per_iter': float(apm_out['n_cached'].mean()) / apm_iters,
+                                'failed_chains': int((apm_out['failed'] != 0).sum()), 'timing': 'host wall clock incl. Python scheduler'},
             'diagnostics_gather': {'collective': 'nccl all_gather' if world > 1 else 'none (1 GPU)',
                                    'chains': int(all_logml.shape[0]), 'mean_logml': float(np.nanmean(all_logml))},
         }
@@ -378,6 +398,7 @@ def main():
     ap.add_argument('--impl', default='apm_b200', choices=['apm_b200', 'reference'])
     ap.add_argument('--chains', type=int, default=0, help='chains per GPU (default 256)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--apm-iters', type=int, default=5, help='iterations of the batched ESS+RDSS sampler leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
