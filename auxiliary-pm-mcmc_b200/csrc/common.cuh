@@ -7,9 +7,19 @@
 namespace apm {
 
 constexpr int TB = 64;          // tile edge of every blocked kernel; matrices are padded to a multiple
-constexpr int KC = 16;          // k-chunk (doubles) staged per pipeline stage
-constexpr int KCP = 20;         // padded smem row stride of a k-chunk: 160 B == 32 (mod 128) -> conflict-free DMMA fragment loads
-constexpr int STAGES = 3;       // cp.async pipeline depth
+#ifndef APM_KC
+#define APM_KC 16
+#endif
+#ifndef APM_STAGES
+#define APM_STAGES 3
+#endif
+#ifndef APM_MIN_CTAS
+#define APM_MIN_CTAS 3
+#endif
+constexpr int KC = APM_KC;      // k-chunk (doubles) staged per pipeline stage
+constexpr int KCP = KC + 4;     // padded smem row stride of a k-chunk: (KC+4)*8 B == 32 (mod 128) -> conflict-free DMMA fragment loads
+constexpr int STAGES = APM_STAGES;   // cp.async pipeline depth
+constexpr int MIN_CTAS = APM_MIN_CTAS;
 constexpr int TILE_THREADS = 128;
 constexpr int TSP = 68;         // row stride of the 64x64 fp64 work tile: 68 == 4 (mod 16) -> conflict-free DMMA fragment loads
 constexpr int VSP = 65;         // row stride of tiles accessed one row / one column per thread (vec kernels)

@@ -33,10 +33,12 @@ struct Acc {
 
 __device__ __forceinline__ void gemm_load_stage(double* smA, double* smB, const double* __restrict__ A, int lda,
                                                 const double* __restrict__ Bm, int ldb, int k0, int tid) {
+    constexpr int SEG_PER_ROW = KC / 2;                     // 16-byte segments per row of a k-chunk
+    constexpr int NSEG = TB * SEG_PER_ROW;                  // per operand per stage
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int seg = tid + q * TILE_THREADS;  // 512 16-byte segments per operand per stage
-        const int row = seg >> 3, cs = (seg & 7) * 2;
+    for (int q = 0; q < NSEG / TILE_THREADS; q++) {
+        const int seg = tid + q * TILE_THREADS;
+        const int row = seg / SEG_PER_ROW, cs = (seg % SEG_PER_ROW) * 2;
         cp_async16(smA + row * KCP + cs, A + (size_t)row * lda + k0 + cs);
         cp_async16(smB + row * KCP + cs, Bm + (size_t)row * ldb + k0 + cs);
     }
@@ -86,6 +88,28 @@ __device__ __forceinline__ void gemm_nt_64x64(Acc& acc, const double* __restrict
     }
     cp_async_wait<0>();
     __syncthreads();  // all warps done with the stage buffers: they may be re-used by the caller
+}
+
+// acc -= X X^T with X = the 64x64 tile in shared memory (stride TSP, conflict-free fragment loads): the
+// contribution of a freshly solved panel block L_ik to its own diagonal block.
+__device__ __forceinline__ void syrk_from_tile(Acc& acc, const double* Ts) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const double* a_s = Ts + (wm * 32 + g) * TSP + t;
+    const double* b_s = Ts + (wn * 32 + g) * TSP + t;
+#pragma unroll 4
+    for (int kk = 0; kk < TB / 4; kk++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) a[mi] = -a_s[mi * 8 * TSP + kk * 4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) b[ni] = b_s[ni * 8 * TSP + kk * 4];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) dmma884(acc.v[mi][ni][0], acc.v[mi][ni][1], a[mi], b[ni]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -259,32 +283,23 @@ __device__ __forceinline__ void chol8_regs(const double (&d)[8][8], double (&l)[
     }
 }
 
-// Ts (64x64, stride TSP) <- chol(Ts) in place; strict upper triangle zeroed.  All 128 threads call this.
-__device__ __forceinline__ void potrf64_smem(double* Ts, PotrfScratch* sc) {
+// Ts (64x64, stride TSP) <- chol(Ts) in place; strict upper triangle zeroed.  All 128 threads call this, after
+// a __syncthreads() that made Ts complete.  Right-looking over 8-column panels with the tile register-resident
+// (warp w owns rows 16w..16w+15 as 2 x 8 DMMA accumulator tiles): per panel the 8 columns go through shared
+// memory, every row's lane re-derives the 8x8 diagonal factor from a broadcast read and solves its row
+// (chol8_regs), the solved panel is published in Lp (64 x 8, stride 12: conflict-free fragment loads) and
+// subtracted from all panels to its right by DMMA (independent accumulators, chains of length 2).
+// Two block barriers per panel.  Lp: scratch of 64*12 doubles.
+constexpr int LPS = 12;
+__device__ __forceinline__ void potrf64_smem(double* Ts, double* Lp, PotrfScratch* sc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
+    const int r = warp * 16 + lane;  // row owned by lanes 0..15 in the solve step
     for (int p = 0; p < 8; p++) {
         const int c0 = p * 8;
-        if (p > 0) {
-            // panel(64x8) -= L[:, 0:c0] * L[c0:c0+8, 0:c0]^T   (rows >= c0 only)
-#pragma unroll
-            for (int mi = 0; mi < 2; mi++) {
-                const int mt = warp + 4 * mi;
-                if (mt >= p) {
-                    double* dp = Ts + (mt * 8 + g) * TSP + c0 + 2 * t;
-                    double d0 = dp[0], d1 = dp[1];
-                    const double* ap = Ts + (mt * 8 + g) * TSP + t;
-                    const double* bp = Ts + (c0 + g) * TSP + t;
-                    for (int k0 = 0; k0 < c0; k0 += 4) dmma884(d0, d1, -ap[k0], bp[k0]);
-                    dp[0] = d0;
-                    dp[1] = d1;
-                }
-            }
-            __syncthreads();
-        }
         double x[8];
         bool bad = false;
-        const bool mine = tid < 64 && tid >= c0;
+        const bool mine = lane < 16 && r >= c0;
         if (mine) {
             double d[8][8], l[8][8], inv[8];
 #pragma unroll
@@ -292,7 +307,7 @@ __device__ __forceinline__ void potrf64_smem(double* Ts, PotrfScratch* sc) {
 #pragma unroll
                 for (int j = 0; j <= i; j++) d[i][j] = Ts[(c0 + i) * TSP + c0 + j];
             chol8_regs(d, l, inv, bad);
-            const double* row = Ts + tid * TSP + c0;
+            const double* row = Ts + r * TSP + c0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 double v = row[j];
@@ -300,17 +315,31 @@ __device__ __forceinline__ void potrf64_smem(double* Ts, PotrfScratch* sc) {
                 for (int k = 0; k < j; k++) v = fma(-x[k], l[j][k], v);
                 x[j] = v * inv[j];
             }
+#pragma unroll
+            for (int j = 0; j < 8; j++) Lp[r * LPS + j] = x[j];
+            if (bad && r == c0) sc->fail = 1;
         }
-        __syncthreads();  // every reader of the 8x8 block is done before its rows are overwritten
-        if (mine) {
-            double* row = Ts + tid * TSP + c0;
+        __syncthreads();   // Lp published; every reader of the 8x8 block is done
+        if (lane < 16) {
+            double* row = Ts + r * TSP + c0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) row[j] = (c0 + j <= tid) ? x[j] : 0.0;
-            if (bad && tid == c0) sc->fail = 1;
-        } else if (tid < c0 && tid < 64) {
-            double* row = Ts + tid * TSP + c0;  // strictly above the diagonal block: zeros
+            for (int j = 0; j < 8; j++) row[j] = (mine && c0 + j <= r) ? x[j] : 0.0;
+        }
+        // trailing update of the lower-triangular tiles to the right: T[mt rows][q cols] -= Lp[mt rows] Lp[q rows]^T
+        // (shared-memory resident: 2 DMMAs per 8x8 tile, all tiles independent)
+        if (p < 7) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) row[j] = 0.0;
+            for (int mt = 0; mt < 2; mt++) {
+                const int r0 = warp * 16 + mt * 8;
+                const double a0 = -Lp[(r0 + g) * LPS + t], a1 = -Lp[(r0 + g) * LPS + 4 + t];
+                for (int q = p + 1; q * 8 <= r0; q++) {
+                    double* dp = Ts + (r0 + g) * TSP + q * 8 + 2 * t;
+                    double2 v = *reinterpret_cast<double2*>(dp);
+                    dmma884(v.x, v.y, a0, Lp[(q * 8 + g) * LPS + t]);
+                    dmma884(v.x, v.y, a1, Lp[(q * 8 + g) * LPS + 4 + t]);
+                    *reinterpret_cast<double2*>(dp) = v;
+                }
+            }
         }
         __syncthreads();
     }
@@ -503,19 +532,24 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
 #ifdef APM_PHASE_TIMING
     long long t_phase = clock64();
 #endif
+    // The running diagonal block D_ii = A_ii - sum_{j<=k} L_ij L_ij^T lives in dst(i,i): every panel task adds
+    // its own contribution right after solving L_ik, so the task that finishes a row (i == k+1) only has the
+    // 64x64 factorisation left (no long diagonal GEMM on the critical path).
+    const double* sci = sc ? sc + i * TB : nullptr;
+    double* dii = dst + (size_t)i * TB * p.ldd + i * TB;
     if (k >= 0) {
         const bool early = FLOW && (f.flags & 1);
         // the source tile never depends on other tasks (in-place: nobody has written tile (i,k) yet)
-        if (early) acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
-                                 sc ? sc + k * TB : nullptr, false);
+        if (early) acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sci, sc ? sc + k * TB : nullptr, false);
         if (FLOW) {
             wait_progress(prog + k, k + 1, f.spin_ns);   // block row k complete (including L_kk)
-            wait_progress(prog + i, k, f.spin_ns);       // our own row up to column block k-1
+            wait_progress(prog + i, k, f.spin_ns);       // our own row up to column block k-1 (and its D_ii updates)
         }
-        if (!early) acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr,
-                                  sc ? sc + k * TB : nullptr, false);
+        if (!early) acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sci, sc ? sc + k * TB : nullptr, false);
         PHASE_MARK(0);  // waits + source tile load issue
-        if (!(FLOW && (f.flags & 2))) prefetch_tile_l2(dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
+        prefetch_tile_l2(dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
+        if (k == 0) prefetch_tile_l2(src + (size_t)i * TB * p.lds + i * TB, p.lds);
+        else prefetch_tile_l2(dii, p.ldd);
         gemm_nt_64x64<true>(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
         PHASE_MARK(1);  // panel GEMM
         tile_put_acc(s.Ts, acc);
@@ -525,25 +559,27 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
         trsm64_smem(s.Ts, s.LT, s.invd);
         __syncthreads();
         PHASE_MARK(3);  // triangular solve
+        if (k == 0) acc_load_tile(acc, src + (size_t)i * TB * p.lds + i * TB, p.lds, sci, sci, p.add_identity != 0);
+        else acc_load_tile(acc, dii, p.ldd, nullptr, nullptr, false);
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + k * TB, p.ldd);
-        if (FLOW && i != k + 1) publish_progress(prog + i, k + 1);
-        PHASE_MARK(4);  // store + publish
+        syrk_from_tile(acc, s.Ts);
+        PHASE_MARK(4);  // store L_ik + diagonal contribution
+        if (i != k + 1) {
+            acc_store_tile(acc, dii, p.ldd);
+            if (FLOW) publish_progress(prog + i, k + 1);
+            PHASE_MARK(5);
+        }
+    } else {
+        acc_load_tile(acc, src + (size_t)i * TB * p.lds + i * TB, p.lds, sci, sci, p.add_identity != 0);
     }
     if (i == k + 1) {
-        if (k >= 0) {
-            __threadfence();
-            __syncthreads();  // the panel block just written is an operand of the diagonal update
-        }
-        acc_load_tile(acc, src + (size_t)i * TB * p.lds + i * TB, p.lds, sc ? sc + i * TB : nullptr,
-                      sc ? sc + i * TB : nullptr, p.add_identity != 0);
-        gemm_nt_64x64<true>(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)i * TB * p.ldd, p.ldd, i * TB, smem);
-        PHASE_MARK(5);  // diagonal GEMM
+        __syncthreads();   // every warp is done reading Ts as the SYRK operand
         tile_put_acc(s.Ts, acc);
         if (threadIdx.x == 0) s.potrf->fail = 0;
         __syncthreads();
-        potrf64_smem(s.Ts, s.potrf);
+        potrf64_smem(s.Ts, s.LT, s.potrf);
         PHASE_MARK(6);  // 64x64 Cholesky
-        tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + i * TB, p.ldd);
+        tile_store(s.Ts, dii, p.ldd);
         if (FLOW) publish_progress(prog + i, i + 1);
         PHASE_MARK(7);  // store + publish
         if (threadIdx.x < 64) {
@@ -577,7 +613,7 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
 }
 
 // one launch per block column (k = -1 .. nb-2); the heavy CTAs (look-ahead diagonal) come first in launch order
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_step(CholParams p, int k) {
+__global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_chol_step(CholParams p, int k) {
     extern __shared__ __align__(16) double smem[];
     const int rows_per_chain = p.nb - k - 1;
     int b, i;
@@ -599,7 +635,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_step(CholParams p, int
 // so that every dependency has a lower index (group-major; inside a group step-major with the look-ahead
 // diagonals first), and wait on per-row progress counters instead of kernel boundaries.  No launch tails,
 // the diagonal critical path starts as early as its operands exist, and a group's matrices stay L2-resident.
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_chol_dataflow(CholParams p, CholFlow f) {
+__global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_chol_dataflow(CholParams p, CholFlow f) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_task;
     const int nb = p.nb, G = f.group;
@@ -653,7 +689,7 @@ struct TrsmParams {
     const int* status; const int* active;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_trsm_rows(TrsmParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_trsm_rows(TrsmParams p) {
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.x / p.row_blocks, rb = blockIdx.x % p.row_blocks;
     if (p.status[b] != 0) return;
@@ -690,7 +726,7 @@ struct SyrkParams {
     const int* status;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_syrk_sub(SyrkParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_syrk_sub(SyrkParams p) {
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.x / p.ntiles;
     int tix = blockIdx.x % p.ntiles;
@@ -722,7 +758,7 @@ struct GemmTriParams {
     const int* status;
 };
 
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_gemm_tri(GemmTriParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_gemm_tri(GemmTriParams p) {
     extern __shared__ __align__(16) double smem[];
     const int per_chain = p.nb * p.row_blocks;
     const int b = blockIdx.x / per_chain;
