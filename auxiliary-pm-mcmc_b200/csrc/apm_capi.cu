@@ -49,6 +49,9 @@ static const char* const KID_NAMES[KID_COUNT] = {"k_build_K", "k_chol_step", "k_
 struct apm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D of the auxiliary normals overlaps the O(n^3) front of a FULL estimate
+    cudaEvent_t copy_done = nullptr;
+    bool u_staged = false;
     int n = 0, D = 0, np = 0, nb = 0, P = 0, kind = 0;
     double eps = 1e-8;
     int maxB = 0, nslots = 0, maxN = 0, maxNpad = 0;
@@ -246,6 +249,12 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         apm_destroy(c);
         return APM_ERR_NOMEM;
     }
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
+        set_err("apm_create: stream/event creation failed");
+        apm_destroy(c);
+        return APM_ERR_CUDA;
+    }
     // data set: X padded with zero rows, y padded with +1
     std::vector<double> Xp(np * D, 0.0), yp(np, 1.0);
     memcpy(Xp.data(), X, sizeof(double) * (size_t)n * D);
@@ -274,6 +283,8 @@ extern "C" int apm_destroy(apm_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     prof_resolve(c);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->copy_done) cudaEventDestroy(c->copy_done);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (void* p : c->allocs) cudaFree(p);
     if (c->hKp) cudaFreeHost(c->hKp);
@@ -538,7 +549,12 @@ static int stage_u(apm_ctx* c, const double* u, int u_on_device, int N, int B) {
     }
     const double* du = u;
     if (!u_on_device) {
-        CU_TRY(cudaMemcpyAsync(c->dUstage, u, sizeof(double) * (size_t)B * c->n * N, cudaMemcpyHostToDevice, c->stream));
+        if (c->u_staged) {   // upload was started on the copy stream by prefetch_u
+            CU_TRY(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+            c->u_staged = false;
+        } else {
+            CU_TRY(cudaMemcpyAsync(c->dUstage, u, sizeof(double) * (size_t)B * c->n * N, cudaMemcpyHostToDevice, c->stream));
+        }
         du = c->dUstage;
     }
     const int Npad = (N + TB - 1) / TB * TB;
@@ -547,6 +563,23 @@ static int stage_u(apm_ctx* c, const double* u, int u_on_device, int N, int B) {
     k_transpose_u<<<grid, block, 0, c->stream>>>(du, (long long)c->n * N, c->n, N, c->dUT, (long long)Npad * c->np, c->np,
                                                  Npad);
     return check_launch(c, "k_transpose_u");
+}
+
+// drop a pending prefetch (a previous call returned early): the staging buffer must be quiescent before re-use
+static void cancel_prefetch(apm_ctx* c) {
+    if (c->u_staged) {
+        cudaStreamSynchronize(c->copy_stream);
+        c->u_staged = false;
+    }
+}
+
+// start the host->device copy of u on the copy stream so that it overlaps the factorisations; stage_u waits
+static int prefetch_u(apm_ctx* c, const double* u, int u_on_device, int N, int B) {
+    if (u_on_device || N <= 0 || N > c->maxN) return APM_OK;
+    CU_TRY(cudaMemcpyAsync(c->dUstage, u, sizeof(double) * (size_t)B * c->n * N, cudaMemcpyHostToDevice, c->copy_stream));
+    CU_TRY(cudaEventRecord(c->copy_done, c->copy_stream));
+    c->u_staged = true;
+    return APM_OK;
 }
 
 // the O(n^2 N) tail (estimators.py:221-241) for chains whose caches sit in slots dSlots[b]
@@ -709,6 +742,8 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
                                  const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status) {
     APM_TRY(check_B(c, B));
     if (!theta || !u || !slots || !logml_out) return APM_ERR_INVALID;
+    cancel_prefetch(c);
+    APM_TRY(prefetch_u(c, u, u_on_device, N, B));
     APM_TRY(full_front(c, theta, B, slots));
     APM_TRY(stage_u(c, u, u_on_device, N, B));
     APM_TRY(run_newton(c, B));                                                  // estimators.py:207 -> lpa.py:81-102
@@ -734,6 +769,7 @@ static int cached_common(apm_ctx* c, const int* slots, const double* u, int u_on
                          double* logw_out, int* chain_status) {
     APM_TRY(check_B(c, B));
     if (!slots || !u) return APM_ERR_INVALID;
+    cancel_prefetch(c);
     APM_TRY(reset_status(c, B));
     APM_TRY(upload_slots(c, slots, B, c->dSlotsA, true));
     APM_TRY(stage_u(c, u, u_on_device, N, B));
@@ -774,6 +810,7 @@ extern "C" int apm_estimate_prior_mc(apm_ctx* c, const double* theta, const int*
                                      int N, int B, double* logml_out, int* chain_status) {
     APM_TRY(check_B(c, B));
     if (!slots || !u || !logml_out) return APM_ERR_INVALID;
+    cancel_prefetch(c);
     if (theta) {
         APM_TRY(full_front(c, theta, B, slots));
     } else {

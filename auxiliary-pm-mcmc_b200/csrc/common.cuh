@@ -24,7 +24,7 @@ constexpr int TILE_THREADS = 128;
 constexpr int TSP = 68;         // row stride of the 64x64 fp64 work tile: 68 == 4 (mod 16) -> conflict-free DMMA fragment loads
 constexpr int VSP = 65;         // row stride of tiles accessed one row / one column per thread (vec kernels)
 constexpr int GEMM_SMEM_DOUBLES = 2 * STAGES * TB * KCP;             // A and B stages
-constexpr int TILE_SCRATCH_DOUBLES = 2 * TB * TSP + TB + 8;          // work tile + diagonal block + reciprocals + flags
+constexpr int TILE_SCRATCH_DOUBLES = TB * TSP + 36 * 64 + TB + 8;      // work tile + packed diagonal block + reciprocals + flags
 constexpr int TILE_SMEM_BYTES = (GEMM_SMEM_DOUBLES > TILE_SCRATCH_DOUBLES ? GEMM_SMEM_DOUBLES : TILE_SCRATCH_DOUBLES) * 8;  // 70208 B -> 3 CTAs / SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

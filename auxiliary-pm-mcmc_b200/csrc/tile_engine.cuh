@@ -352,7 +352,12 @@ __device__ __forceinline__ void potrf64_smem(double* Ts, double* Lp, PotrfScratc
 // it exactly against the 8x8 diagonal sub-block (substitution, one row per lane), comes back as DMMA
 // A-fragments, and is subtracted from all panels to its right (independent accumulators, chains of length 2).
 // The caller must __syncthreads() before (Ts, Ld complete) and after (Ts readable by other warps).
-__device__ __forceinline__ void trsm64_smem(double* Ts, const double* Ld, const double* invd) {
+// The 64x64 lower-triangular operand L is held PACKED in shared memory: its 36 lower 8x8 blocks, block (q,p)
+// (q >= p) at index q(q+1)/2 + p, 64 doubles each, row-major (18 KB instead of a padded 34 KB tile).
+__device__ __forceinline__ int lpk_block(int q, int p) { return (q * (q + 1) / 2 + p) * 64; }
+constexpr int LPK_DOUBLES = 36 * 64;
+
+__device__ __forceinline__ void trsm64_smem(double* Ts, const double* Lpk, const double* invd) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     double* rows = Ts + warp * 16 * TSP;
@@ -376,17 +381,13 @@ __device__ __forceinline__ void trsm64_smem(double* Ts, const double* Ld, const 
         }
         if (lane < 16) {
             double* row = rows + lane * TSP + c0;
-            double l8[8][8];
-#pragma unroll
-            for (int j = 1; j < 8; j++)
-#pragma unroll
-                for (int k = 0; k < j; k++) l8[j][k] = Ld[(c0 + j) * TSP + c0 + k];
+            const double* l8 = Lpk + lpk_block(p, p);   // broadcast reads
             double x[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 double v = row[j];
 #pragma unroll
-                for (int k = 0; k < j; k++) v = fma(-x[k], l8[j][k], v);
+                for (int k = 0; k < j; k++) v = fma(-x[k], l8[j * 8 + k], v);
                 x[j] = v * invd[c0 + j];
             }
 #pragma unroll
@@ -401,9 +402,10 @@ __device__ __forceinline__ void trsm64_smem(double* Ts, const double* Ld, const 
                 for (int kk = 0; kk < 2; kk++) a[mt][kk] = -rows[(mt * 8 + g) * TSP + c0 + kk * 4 + t];
 #pragma unroll
             for (int q = p + 1; q < 8; q++) {
+                const double* blk = Lpk + lpk_block(q, p) + g * 8 + t;
 #pragma unroll
                 for (int kk = 0; kk < 2; kk++) {
-                    const double bq = Ld[(q * 8 + g) * TSP + c0 + kk * 4 + t];
+                    const double bq = blk[kk * 4];
 #pragma unroll
                     for (int mt = 0; mt < 2; mt++) dmma884(acc[mt][q][0], acc[mt][q][1], a[mt][kk], bq);
                 }
@@ -412,20 +414,32 @@ __device__ __forceinline__ void trsm64_smem(double* Ts, const double* Ld, const 
     }
 }
 
-// stage the diagonal block L_kk (row-major, ld) into Ld (stride TSP) with its reciprocal diagonal
-__device__ __forceinline__ void load_diag_block(double* Ld, double* invd, const double* __restrict__ Lkk, int ld) {
+// stage the diagonal block L_kk (row-major in global memory, ld) into the packed layout + reciprocal diagonal
+__device__ __forceinline__ void load_diag_block(double* Lpk, double* invd, const double* __restrict__ Lkk, int ld) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pb = lane >> 2, cc = (lane & 3) * 2;          // 8-column block and column inside it
     double2 v[16];
 #pragma unroll
     for (int rr = 0; rr < 16; rr++)   // all 16 loads in flight before the first use
         v[rr] = __ldcg(reinterpret_cast<const double2*>(Lkk + (size_t)(warp * 16 + rr) * ld + lane * 2));
 #pragma unroll
     for (int rr = 0; rr < 16; rr++) {
-        const int r = warp * 16 + rr;
-        *reinterpret_cast<double2*>(Ld + r * TSP + lane * 2) = v[rr];
+        const int r = warp * 16 + rr, qb = r >> 3;
+        if (pb <= qb) *reinterpret_cast<double2*>(Lpk + lpk_block(qb, pb) + (r & 7) * 8 + cc) = v[rr];
         if (r == lane * 2) invd[r] = 1.0 / v[rr].x;
         if (r == lane * 2 + 1) invd[r] = 1.0 / v[rr].y;
     }
+}
+// pack a lower-triangular tile held in shared memory (stride TSP) + reciprocal diagonal
+__device__ __forceinline__ void pack_tile(double* Lpk, double* invd, const double* Ts) {
+    for (int e = threadIdx.x; e < TB * TB / 2; e += TILE_THREADS) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        const int qb = r >> 3, pb = c >> 3;
+        if (pb <= qb)
+            *reinterpret_cast<double2*>(Lpk + lpk_block(qb, pb) + (r & 7) * 8 + (c & 7)) =
+                *reinterpret_cast<const double2*>(Ts + r * TSP + c);
+    }
+    if (threadIdx.x < TB) invd[threadIdx.x] = 1.0 / Ts[threadIdx.x * TSP + threadIdx.x];
 }
 
 // carve the epilogue scratch out of the (finished) GEMM stage buffers
@@ -437,13 +451,13 @@ struct TileScratch {
 };
 __device__ __forceinline__ TileScratch carve_scratch(double* smem) {
     TileScratch s;
-    s.Ts = smem;                          // 64 x TSP
-    s.LT = smem + TB * TSP;               // diagonal block L_kk, 64 x TSP
-    s.invd = s.LT + TB * TSP;
+    s.Ts = smem;                          // 64 x TSP work tile
+    s.LT = smem + TB * TSP;               // packed diagonal block L_kk (LPK_DOUBLES); potrf panel scratch
+    s.invd = s.LT + LPK_DOUBLES;
     s.potrf = reinterpret_cast<PotrfScratch*>(s.invd + TB);
     return s;
 }
-static_assert((2 * TB * TSP + TB) * 8 + sizeof(PotrfScratch) <= TILE_SMEM_BYTES, "tile scratch exceeds GEMM smem");
+static_assert((TB * TSP + LPK_DOUBLES + TB) * 8 + sizeof(PotrfScratch) <= TILE_SMEM_BYTES, "tile scratch exceeds GEMM smem");
 
 // ------------------------------------------------------------------------------------------------
 // Blocked left-looking Cholesky, launch `k` of nb (k = -1 .. nb-2):
@@ -597,15 +611,16 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
             // (L_ii^{-1})^T = I * L_ii^{-T}: lets the single right-hand-side solves of the Newton step
             // (k_trsv2) replace 64-step substitutions on the diagonal blocks by parallel 64x64 mat-vecs
             __syncthreads();
+            pack_tile(s.LT, s.invd, s.Ts);
+            __syncthreads();
             for (int e = threadIdx.x; e < TB * TB; e += TILE_THREADS) {
                 const int r = e >> 6, c = e & 63;
-                s.LT[r * TSP + c] = (r == c) ? 1.0 : 0.0;
+                s.Ts[r * TSP + c] = (r == c) ? 1.0 : 0.0;
             }
-            if (threadIdx.x < 64) s.invd[threadIdx.x] = 1.0 / s.Ts[threadIdx.x * TSP + threadIdx.x];
             __syncthreads();
-            trsm64_smem(s.LT, s.Ts, s.invd);
+            trsm64_smem(s.Ts, s.LT, s.invd);
             __syncthreads();
-            tile_store(s.LT, p.inv_out + (long long)b * p.inv_bs + (size_t)i * TB * TB, TB);
+            tile_store(s.Ts, p.inv_out + (long long)b * p.inv_bs + (size_t)i * TB * TB, TB);
         }
         PHASE_MARK(8);  // log-det + inverse of the diagonal block
     }

@@ -13,7 +13,7 @@ import torch
 K = torch.empty(B, n, n, dtype=torch.float64, device='cuda')
 eng.kernel_build(thetas, out=K)
 L = _capi.lib()
-names = ['wait+srcload', 'panel GEMM', 'stage T,Lkk', 'trsm64', 'store+publish', 'diag GEMM', 'potrf64', 'store+publish(d)', 'logdet+inverse']
+names = ['wait+srcload', 'panel GEMM', 'stage T,Lkk', 'trsm64', 'store+diag syrk', 'store D+publish', 'potrf64', 'store+publish(d)', 'logdet+inverse']
 for mode in (0, 1):
     cyc = (ct.c_ulonglong * 16)(); cnt = (ct.c_ulonglong * 16)()
     L.apm_dev_phase_read(cyc, cnt, 1)

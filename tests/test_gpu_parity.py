@@ -257,6 +257,27 @@ def test_failure_statuses():
     eng.close()
 
 
+def test_many_blocks_n2048():
+    """32 block columns (n = 2048): the blocked kernels far from the n = 768 tuning point, against the oracle."""
+    n, D, N, B = 2048, 6, 16, 2
+    X, y, th = synth.make_dataset(n, D, seed=12)
+    thetas = np.stack([th, th + 0.15])
+    rs = np.random.RandomState(4)
+    u = rs.normal(size=(B, n, N))
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, max_nimp=N)
+    full, ops, st = eng.estimate_full(thetas, u, [0, 1])
+    cached, _ = eng.estimate_cached([0, 1], u)
+    assert np.all(st == 0) and np.array_equal(full, cached)
+    est = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, oracle_kernel('ard', 1e-8), orc.laplace_approximation)
+    ref, cache = est(u[0], thetas[0])
+    K0 = np.empty((n, n))
+    oracle_kernel('ard', 1e-8)(K0, X, thetas[0])
+    tol = max(REL, 2e-15 * np.linalg.cond(K0))
+    assert abs(full[0] - ref) < tol * abs(ref), (full[0], ref)
+    assert ops[0] == est.n_cubic_ops
+    eng.close()
+
+
 # ---------------------------------------------------------------------------------------------- full size
 def test_full_size_properties_pima_batch():
     """BASELINE size (n=768, D=8, N=64), a batch of chains: properties that need no oracle run --
