@@ -17,7 +17,13 @@ constexpr int TB = 64;          // tile edge of every blocked kernel; matrices a
 #define APM_MIN_CTAS 3
 #endif
 constexpr int KC = APM_KC;      // k-chunk (doubles) staged per pipeline stage
-constexpr int KCP = KC + 4;     // padded smem row stride of a k-chunk: (KC+4)*8 B == 32 (mod 128) -> conflict-free DMMA fragment loads
+#ifndef APM_SWIZZLE
+#define APM_SWIZZLE 1
+#endif
+// smem row stride of a k-chunk: padded by 4 doubles ((KC+4)*8 B == 32 mod 128), or unpadded with the 16-byte
+// segments of a row XOR-swizzled by ((row & 3) << 1) -- both give conflict-free DMMA fragment loads
+constexpr bool SWIZZLE = APM_SWIZZLE != 0;
+constexpr int KCP = SWIZZLE ? KC : KC + 4;
 constexpr int STAGES = APM_STAGES;   // cp.async pipeline depth
 constexpr int MIN_CTAS = APM_MIN_CTAS;
 constexpr int TILE_THREADS = 128;

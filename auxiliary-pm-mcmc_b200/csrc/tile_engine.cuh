@@ -38,9 +38,10 @@ __device__ __forceinline__ void gemm_load_stage(double* smA, double* smB, const 
 #pragma unroll
     for (int q = 0; q < NSEG / TILE_THREADS; q++) {
         const int seg = tid + q * TILE_THREADS;
-        const int row = seg / SEG_PER_ROW, cs = (seg % SEG_PER_ROW) * 2;
-        cp_async16(smA + row * KCP + cs, A + (size_t)row * lda + k0 + cs);
-        cp_async16(smB + row * KCP + cs, Bm + (size_t)row * ldb + k0 + cs);
+        const int row = seg / SEG_PER_ROW, sg = seg % SEG_PER_ROW, cs = sg * 2;
+        const int ds = SWIZZLE ? ((sg ^ ((row & 3) << 1)) * 2) : cs;
+        cp_async16(smA + row * KCP + ds, A + (size_t)row * lda + k0 + cs);
+        cp_async16(smB + row * KCP + ds, Bm + (size_t)row * ldb + k0 + cs);
     }
 }
 
@@ -71,15 +72,17 @@ __device__ __forceinline__ void gemm_nt_64x64(Acc& acc, const double* __restrict
             cp_async_commit();
         }
         const int st = kc % STAGES;
-        const double* a_s = smA + st * TB * KCP + (wm * 32 + g) * KCP + t;
-        const double* b_s = smB + st * TB * KCP + (wn * 32 + g) * KCP + t;
+        const double* a_s = smA + st * TB * KCP + (wm * 32 + g) * KCP + (SWIZZLE ? (t & 1) : t);
+        const double* b_s = smB + st * TB * KCP + (wn * 32 + g) * KCP + (SWIZZLE ? (t & 1) : t);
+        const int swz = (g & 3) << 1, th = t >> 1;
 #pragma unroll
         for (int kk = 0; kk < KC / 4; kk++) {
             double a[4], b[4];
+            const int ko = SWIZZLE ? (((kk * 2 + th) ^ swz) * 2) : kk * 4;
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = NEG ? -a_s[mi * 8 * KCP + kk * 4] : a_s[mi * 8 * KCP + kk * 4];
+            for (int mi = 0; mi < 4; mi++) a[mi] = NEG ? -a_s[mi * 8 * KCP + ko] : a_s[mi * 8 * KCP + ko];
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) b[ni] = b_s[ni * 8 * KCP + kk * 4];
+            for (int ni = 0; ni < 4; ni++) b[ni] = b_s[ni * 8 * KCP + ko];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++)
 #pragma unroll
