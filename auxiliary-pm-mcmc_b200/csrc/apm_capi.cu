@@ -52,6 +52,12 @@ struct apm_ctx {
     cudaStream_t copy_stream = nullptr;   // H2D of the auxiliary normals overlaps the O(n^3) front of a FULL estimate
     cudaEvent_t copy_done = nullptr;
     bool u_staged = false;
+    // chol(K) is only needed by the importance-sampling tail: it runs on aux_stream (per-step launches) as filler
+    // work beside the Newton rounds, whose latency-bound kernels leave SM slots idle
+    cudaStream_t aux_stream = nullptr;
+    cudaStream_t launch_stream = nullptr;   // stream the launch helpers (run_chol, profiling events) currently target
+    cudaEvent_t ev_k_ready = nullptr, ev_lk_done = nullptr;
+    bool overlap_chol_k = true;
     int n = 0, D = 0, np = 0, nb = 0, P = 0, kind = 0;
     double eps = 1e-8;
     int maxB = 0, nslots = 0, maxN = 0, maxNpad = 0;
@@ -114,7 +120,7 @@ static void prof_begin(apm_ctx* c, int kid) {
     p.kid = kid;
     p.a = prof_event(c);
     p.b = prof_event(c);
-    cudaEventRecord(p.a, c->stream);
+    cudaEventRecord(p.a, c->launch_stream ? c->launch_stream : c->stream);
     c->pending.push_back(p);
 }
 // fold finished launches into the per-kernel totals (call only after a stream synchronisation)
@@ -134,7 +140,7 @@ static void prof_resolve(apm_ctx* c) {
 }
 static int check_launch(apm_ctx* c, const char* what) {
     c->launches++;
-    if (c->prof && !c->pending.empty()) cudaEventRecord(c->pending.back().b, c->stream);
+    if (c->prof && !c->pending.empty()) cudaEventRecord(c->pending.back().b, c->launch_stream ? c->launch_stream : c->stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_err(std::string("launch ") + what + ": " + cudaGetErrorString(e));
@@ -249,7 +255,11 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         apm_destroy(c);
         return APM_ERR_NOMEM;
     }
+    c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_k_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_lk_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
         set_err("apm_create: stream/event creation failed");
         apm_destroy(c);
@@ -284,6 +294,9 @@ extern "C" int apm_destroy(apm_ctx* c) {
     cudaDeviceSynchronize();
     prof_resolve(c);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_k_ready) cudaEventDestroy(c->ev_k_ready);
+    if (c->ev_lk_done) cudaEventDestroy(c->ev_lk_done);
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (void* p : c->allocs) cudaFree(p);
@@ -424,7 +437,8 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     p.status = c->dStatus; p.fail_code = fail_code;
     p.active = active;
     p.nchains = B;
-    if (c->flow_grid > 0) {
+    cudaStream_t st = c->launch_stream ? c->launch_stream : c->stream;
+    if (c->flow_grid > 0 && st == c->stream) {
         // single cooperative launch (all CTAs co-resident: tasks wait on each other through progress counters)
         CholFlow f;
         f.counter = c->dFlowCounter; f.progress = c->dFlowProgress; f.skip = c->dFlowSkip;
@@ -452,7 +466,7 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     for (int k = -1; k <= c->nb - 2; k++) {
         const int grid = (k < 0) ? B : B * (c->nb - k - 1);
         prof_begin(c, KID_CHOL);
-        k_chol_step<<<grid, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(p, k);
+        k_chol_step<<<grid, TILE_THREADS, TILE_SMEM_BYTES, st>>>(p, k);
         APM_TRY(check_launch(c, "k_chol_step"));
     }
     return APM_OK;
@@ -727,15 +741,26 @@ extern "C" int apm_laplace(apm_ctx* c, const double* K, int K_on_device, int B, 
 // ------------------------------------------------------------------------------------------------
 // C ABI: estimators
 // ------------------------------------------------------------------------------------------------
-static int full_front(apm_ctx* c, const double* theta, int B, const int* slots) {
+// K(theta) and chol(K) -> slot L_K (estimators.py:205-206).  With overlap = true the factorisation is queued on the
+// aux stream (the caller must make the main stream wait on ev_lk_done before it reads the slot's L_K).
+static int full_front(apm_ctx* c, const double* theta, int B, const int* slots, bool overlap = false) {
     APM_TRY(reset_status(c, B));
     APM_TRY(upload_slots(c, slots, B, c->dSlotsA, false));
     for (int b = 0; b < B; b++) c->slot_valid[slots[b]] = 0;
     APM_TRY(upload_kernel_params(c, theta, B, c->kind));
     APM_TRY(build_K(c, B, c->kind, c->eps));
-    // chol(K) -> slot L_K                                                         (estimators.py:206)
-    return run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dSlotLK, (long long)c->mat, c->dSlotsA, nullptr, 0,
-                    c->dSlotLdK, c->dSlotsA, APM_CHAIN_CHOL_K, nullptr);
+    if (overlap) {
+        CU_TRY(cudaEventRecord(c->ev_k_ready, c->stream));
+        CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_k_ready, 0));
+        c->launch_stream = c->aux_stream;
+    }
+    int rc = run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dSlotLK, (long long)c->mat, c->dSlotsA, nullptr, 0,
+                      c->dSlotLdK, c->dSlotsA, APM_CHAIN_CHOL_K, nullptr);
+    if (overlap) {
+        c->launch_stream = nullptr;
+        if (rc == APM_OK) CU_TRY(cudaEventRecord(c->ev_lk_done, c->aux_stream));
+    }
+    return rc;
 }
 
 extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
@@ -744,7 +769,8 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
     if (!theta || !u || !slots || !logml_out) return APM_ERR_INVALID;
     cancel_prefetch(c);
     APM_TRY(prefetch_u(c, u, u_on_device, N, B));
-    APM_TRY(full_front(c, theta, B, slots));
+    const bool overlap = c->overlap_chol_k;
+    APM_TRY(full_front(c, theta, B, slots, overlap));
     APM_TRY(stage_u(c, u, u_on_device, N, B));
     APM_TRY(run_newton(c, B));                                                  // estimators.py:207 -> lpa.py:81-102
     APM_TRY(run_covariance(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA));    // lpa.py:111-112
@@ -755,6 +781,7 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
     prof_begin(c, KID_MISC);
     k_copy_vec<<<cg, 256, 0, c->stream>>>(c->dVec[V_F], c->np, nullptr, c->dSlotMu, c->np, c->dSlotsA, c->np, c->dStatus);
     APM_TRY(check_launch(c, "k_copy_vec"));
+    if (overlap) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
     APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, nullptr, 0));
     std::vector<int> st(B);
     APM_TRY(fetch_results(c, B, c->dOut, 1, logml_out, cubic_ops_out, 3, st.data()));  // iters + 1 + 2 (est.py:217)
