@@ -346,7 +346,12 @@ def run_gpu_arm(args):
         d = kern[dom]
         roofline = {
             'bound': 'tensor', 'kernel': dom, 'achieved': d['achieved'], 'peak': peak_dmma, 'unit': 'TFLOP/s',
-            'frac': d['frac'], 'traffic': None,
+            'frac': d['frac'],
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_chol_dataflow launch (256 chains, n = 768) from the
+            # `ncu --set full` capture summarised in profiles/r1_final_ncu_k_chol_dataflow_full.md: 4.21 GB + 1.20 GB
+            'traffic': 5.41e9 if (dom == 'k_chol_step' and n == 768 and B == 256) else None,
+            'traffic_note': 'bytes per launch from ncu (profiles/r1_final_ncu_k_chol_dataflow_full.md); minimum (read K, write L) '
+                            'is 1.28 GB, the blocked left-looking operand traffic with a working set > L2 is 4.7 GB',
             'achieved_per_launch_gflop': flops[dom] / d['launches'] / 1e9,
             'avg_launch_ms': d['ms_total'] / d['launches'],
             'peak_source': 'fp64 DMMA (mma.sync m8n8k4.f64) issue peak measured in this run by apm_measure_fp64_peak; '
