@@ -196,6 +196,62 @@ class BatchedAPMSampler(object):
         else:
             ch.n_reject[1] += 1
 
+    # ---- device-RNG mode: u, v and the proposals live in [B, n, N] tensors; the generators only yield symbolic
+    # requests and the scheduler does the tensor work for all chains of a round at once
+    def _dev_u_update_mi(self, ch):
+        log_f_prop = yield ('cached_new',)
+        if ch.prng.uniform() < np.exp(log_f_prop - ch.log_f):
+            ch.log_f = log_f_prop
+            ch.accept_u = True
+        else:
+            ch.n_reject[0] += 1
+
+    def _dev_u_update_ess(self, ch):
+        log_y = ch.log_f + np.log(ch.prng.uniform())
+        phi = ch.prng.uniform() * TWO_PI
+        lo, hi = phi - TWO_PI, phi
+        new_v = True
+        for _ in range(self.max_slice_iters):
+            log_f_prop = yield ('cached_ell', phi, new_v)
+            new_v = False
+            if log_f_prop > log_y:
+                ch.log_f = log_f_prop
+                ch.accept_u = True
+                return
+            if phi < 0:
+                lo = phi
+            elif phi > 0:
+                hi = phi
+            else:
+                return
+            phi = lo + ch.prng.uniform() * (hi - lo)
+        raise ChainFailure(2)
+
+    def _dev_pmmh_update(self, ch):
+        s = self.prop_scales
+        theta_prop = ch.theta + s * ch.prng.normal(size=self.P)
+        log_f_prop = yield ('full_newu', theta_prop)
+        if ch.prng.uniform() < np.exp(log_f_prop - ch.log_f):     # symmetric random walk
+            ch.theta, ch.log_f = theta_prop, log_f_prop
+        else:
+            ch.n_reject[1] += 1
+
+    def _run_chain_device(self, ch, n_sample, trace):
+        trace[0] = ch.theta
+        ch.log_f = yield ('full_newu', ch.theta)
+        if self.method == 'pmmh':
+            for s in range(1, n_sample):
+                yield from self._dev_pmmh_update(ch)
+                trace[s] = ch.theta
+            return
+        ch.cur_slot, ch.prop_slot = ch.prop_slot, ch.cur_slot
+        u_step = self._dev_u_update_mi if self.method.startswith('mi') else self._dev_u_update_ess
+        th_step = self._theta_update_mh if self.method.endswith('mh') else self._theta_update_rdss
+        for s in range(1, n_sample):
+            yield from u_step(ch)
+            yield from th_step(ch)
+            trace[s] = ch.theta
+
     def _run_chain(self, ch, n_sample, trace):
         trace[0] = ch.theta
         if self.method == 'pmmh':
@@ -215,21 +271,15 @@ class BatchedAPMSampler(object):
             yield from th_step(ch)
             trace[s] = ch.theta
 
-    # ---- the lock-step scheduler ----------------------------------------------------------------------
-    def get_samples(self, theta_init, n_sample, theta_init_sampler=None):
-        """theta_init: (B, n_theta), or None with theta_init_sampler(prng) -> theta drawing each chain's start
-        from its own stream right after seeding (as the notebooks do, nb cell 14).  Returns dict(thetas
-        (B, n_sample, P), n_reject (B, 2), n_cubic_ops (B,), n_full (B,), n_cached (B,), failed (B,) status
-        codes, rounds)."""
-        B = self.B
-        if theta_init is None:
-            chains = [_Chain(c, self.seeds[c], np.zeros(self.P)) for c in range(B)]
-            for ch in chains:
-                ch.theta = np.array(theta_init_sampler(ch.prng), dtype=np.float64)
-        else:
-            theta_init = np.asarray(theta_init, dtype=np.float64)
-            chains = [_Chain(c, self.seeds[c], theta_init[c]) for c in range(B)]
-        traces = np.full((B, n_sample, self.P), np.nan)
+    # ---- the lock-step schedulers ----------------------------------------------------------------------
+    def _log_prior_many(self, thetas):
+        """log prior of several thetas; uses a vectorised callable when the prior provides one."""
+        vec = getattr(self.log_prior, 'many', None)
+        if vec is not None:
+            return vec(np.asarray(thetas))
+        return np.array([self.log_prior(t) for t in thetas])
+
+    def _schedule_parity(self, chains, traces, n_sample):
         gens = [self._run_chain(ch, n_sample, traces[c]) for c, ch in enumerate(chains)]
         pending = {}
         for c, g in enumerate(gens):
@@ -264,17 +314,113 @@ class BatchedAPMSampler(object):
                         results[c] = ChainFailure(int(st[j]))
                     else:
                         results[c] = float(vals[j]) + self.log_prior(ch.theta)
-            new_pending = {}
-            for c, res in results.items():
-                try:
-                    if isinstance(res, ChainFailure):
-                        raise res
-                    new_pending[c] = gens[c].send(res)
-                except StopIteration:
-                    pass
-                except ChainFailure as e:           # the notebooks skip a failing chain (nb cell 14)
-                    chains[c].failed = e.status
-            pending = new_pending
+            pending = self._resume(chains, gens, results)
+        return rounds
+
+    def _resume(self, chains, gens, results):
+        new_pending = {}
+        for c, res in results.items():
+            try:
+                if isinstance(res, ChainFailure):
+                    raise res
+                new_pending[c] = gens[c].send(res)
+            except StopIteration:
+                pass
+            except ChainFailure as e:           # the notebooks skip a failing chain (nb cell 14)
+                chains[c].failed = e.status
+        return new_pending
+
+    def _schedule_device(self, chains, traces, n_sample):
+        torch = self._torch
+        B, n, N = self.B, self.n, self.N
+        kw = dict(dtype=torch.float64, device=self.device)
+        U = torch.zeros(B, n, N, **kw)        # current auxiliary normals of every chain
+        V = torch.zeros(B, n, N, **kw)        # ESS auxiliary draw
+        Uprop = torch.zeros(B, n, N, **kw)    # proposals of the current round
+        for ch in chains:
+            ch.accept_u = False
+        gens = [self._run_chain_device(ch, n_sample, traces[c]) for c, ch in enumerate(chains)]
+        pending = {c: next(g) for c, g in enumerate(gens)}
+        rounds = 0
+
+        def idx_t(lst):
+            return torch.tensor(lst, dtype=torch.long, device=self.device)
+
+        while pending:
+            rounds += 1
+            kinds = {}
+            for c, r in pending.items():
+                kinds.setdefault(r[0], []).append(c)
+            results = {}
+            # --- FULL estimates (theta changed); 'full_newu' first draws fresh normals for those chains
+            full = kinds.get('full_newu', []) + kinds.get('full', [])
+            if full:
+                newu = kinds.get('full_newu', [])
+                if newu:
+                    U[idx_t(newu)] = torch.randn(len(newu), n, N, generator=self._gen, **kw)
+                thetas = np.stack([pending[c][1] for c in full])
+                slots = [chains[c].prop_slot for c in full]
+                u_in = U if len(full) == B and full == list(range(B)) else U.index_select(0, idx_t(full))
+                vals, ops, st = self.backend.engine.estimate_full(thetas, u_in.contiguous(), slots)
+                lp = self._log_prior_many(thetas)
+                for j, c in enumerate(full):
+                    ch = chains[c]
+                    ch.n_full += 1
+                    if st[j] != 0:
+                        results[c] = ChainFailure(int(st[j]))
+                    else:
+                        ch.n_cubic_ops += int(ops[j])
+                        results[c] = float(vals[j]) + float(lp[j])
+            # --- CACHED estimates (u proposals)
+            cached = kinds.get('cached_new', []) + kinds.get('cached_ell', [])
+            if cached:
+                mi = kinds.get('cached_new', [])
+                if mi:
+                    Uprop[idx_t(mi)] = torch.randn(len(mi), n, N, generator=self._gen, **kw)
+                ell = kinds.get('cached_ell', [])
+                if ell:
+                    fresh = [c for c in ell if pending[c][2]]
+                    if fresh:
+                        V[idx_t(fresh)] = torch.randn(len(fresh), n, N, generator=self._gen, **kw)
+                    it = idx_t(ell)
+                    phis = np.array([pending[c][1] for c in ell])
+                    cs = torch.tensor(np.cos(phis), **kw)[:, None, None]
+                    sn = torch.tensor(np.sin(phis), **kw)[:, None, None]
+                    Uprop[it] = U.index_select(0, it) * cs + V.index_select(0, it) * sn       # mu.py:382
+                slots = [chains[c].cur_slot for c in cached]
+                vals, st = self.backend.engine.estimate_cached(slots, Uprop.index_select(0, idx_t(cached)).contiguous())
+                lp = self._log_prior_many(np.stack([chains[c].theta for c in cached]))
+                for j, c in enumerate(cached):
+                    ch = chains[c]
+                    ch.n_cached += 1
+                    results[c] = ChainFailure(int(st[j])) if st[j] != 0 else float(vals[j]) + float(lp[j])
+            pending = self._resume(chains, gens, results)
+            acc = [c for c in results if chains[c].accept_u]
+            if acc:
+                ia = idx_t(acc)
+                U[ia] = Uprop.index_select(0, ia)
+                for c in acc:
+                    chains[c].accept_u = False
+        return rounds
+
+    def get_samples(self, theta_init, n_sample, theta_init_sampler=None):
+        """theta_init: (B, n_theta), or None with theta_init_sampler(prng) -> theta drawing each chain's start
+        from its own stream right after seeding (as the notebooks do, nb cell 14).  Returns dict(thetas
+        (B, n_sample, P), n_reject (B, 2), n_cubic_ops (B,), n_full (B,), n_cached (B,), failed (B,) status
+        codes, rounds)."""
+        B = self.B
+        if theta_init is None:
+            chains = [_Chain(c, self.seeds[c], np.zeros(self.P)) for c in range(B)]
+            for ch in chains:
+                ch.theta = np.array(theta_init_sampler(ch.prng), dtype=np.float64)
+        else:
+            theta_init = np.asarray(theta_init, dtype=np.float64)
+            chains = [_Chain(c, self.seeds[c], theta_init[c]) for c in range(B)]
+        traces = np.full((B, n_sample, self.P), np.nan)
+        if self.rng == 'device':
+            rounds = self._schedule_device(chains, traces, n_sample)
+        else:
+            rounds = self._schedule_parity(chains, traces, n_sample)
         return dict(thetas=traces, n_reject=np.array([ch.n_reject for ch in chains]),
                     n_cubic_ops=np.array([ch.n_cubic_ops for ch in chains]),
                     n_full=np.array([ch.n_full for ch in chains]), n_cached=np.array([ch.n_cached for ch in chains]),
@@ -291,4 +437,11 @@ def make_log_prior(D, ard):
         for t in theta[1:]:
             v = v + utils.log_gamma_log_pdf(t, p['a_tau'], p['b_tau'])
         return v
+
+    def many(thetas):            # (B, P) -> (B,), same terms summed in the same order
+        v = utils.log_gamma_log_pdf(thetas[:, 0], p['a_sigma'], p['b_sigma'])
+        for k in range(1, thetas.shape[1]):
+            v = v + utils.log_gamma_log_pdf(thetas[:, k], p['a_tau'], p['b_tau'])
+        return v
+    log_prior.many = many
     return log_prior
