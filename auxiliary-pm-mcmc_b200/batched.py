@@ -83,7 +83,7 @@ class BatchedAPMSampler(object):
     """
 
     def __init__(self, backend, n_data, n_imp, n_theta, method, log_prior, seeds, prop_scales=None, slice_width=1.,
-                 max_slice_iters=1000, rng='parity', device=None):
+                 max_slice_iters=1000, rng='parity', device=None, full_batch_frac=0.8):
         if method not in ('mi+mh', 'ess+mh', 'mi+rdss', 'ess+rdss', 'pmmh'):
             raise ValueError('unknown method %r' % method)
         if rng not in ('parity', 'device'):
@@ -99,6 +99,9 @@ class BatchedAPMSampler(object):
         self.max_slice_iters = int(max_slice_iters)
         self.rng = rng
         self.device = device
+        # scheduling policy: FULL estimates are latency-bound for small batches, so they are held back until this
+        # fraction of the live chains is waiting for one (or nobody has a cheap CACHED request left)
+        self.full_batch_frac = float(full_batch_frac)
         self._gen = None
         if rng == 'device':
             import torch
@@ -290,6 +293,8 @@ class BatchedAPMSampler(object):
             full = [c for c, r in pending.items() if r[0] == 'full']
             cached = [c for c, r in pending.items() if r[0] == 'cached']
             results = {}
+            if full and cached and len(full) < self.full_batch_frac * len(pending):
+                full = []                                        # serve the cheap requests first
             if full:
                 thetas = np.stack([pending[c][1] for c in full])
                 us = [chains[c].u for c in full]
@@ -314,7 +319,9 @@ class BatchedAPMSampler(object):
                         results[c] = ChainFailure(int(st[j]))
                     else:
                         results[c] = float(vals[j]) + self.log_prior(ch.theta)
+            held = {c: r for c, r in pending.items() if c not in results}
             pending = self._resume(chains, gens, results)
+            pending.update(held)
         return rounds
 
     def _resume(self, chains, gens, results):
@@ -354,8 +361,11 @@ class BatchedAPMSampler(object):
             results = {}
             # --- FULL estimates (theta changed); 'full_newu' first draws fresh normals for those chains
             full = kinds.get('full_newu', []) + kinds.get('full', [])
+            n_cached_req = len(kinds.get('cached_new', [])) + len(kinds.get('cached_ell', []))
+            if full and n_cached_req and len(full) < self.full_batch_frac * len(pending):
+                full = []                                        # serve the cheap requests first
             if full:
-                newu = kinds.get('full_newu', [])
+                newu = [c for c in full if pending[c][0] == 'full_newu']
                 if newu:
                     U[idx_t(newu)] = torch.randn(len(newu), n, N, generator=self._gen, **kw)
                 thetas = np.stack([pending[c][1] for c in full])
@@ -394,7 +404,9 @@ class BatchedAPMSampler(object):
                     ch = chains[c]
                     ch.n_cached += 1
                     results[c] = ChainFailure(int(st[j])) if st[j] != 0 else float(vals[j]) + float(lp[j])
+            held = {c: r for c, r in pending.items() if c not in results}
             pending = self._resume(chains, gens, results)
+            pending.update(held)
             acc = [c for c in results if chains[c].accept_u]
             if acc:
                 ia = idx_t(acc)
