@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libapm_b200.so')
 # every symbol include/apm_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     'apm_version', 'apm_last_error', 'apm_create', 'apm_destroy', 'apm_set_stream', 'apm_synchronize',
-    'apm_set_newton', 'apm_get_info', 'apm_kernel_build', 'apm_laplace', 'apm_estimate_full',
+    'apm_set_overlap', 'apm_set_newton', 'apm_get_info', 'apm_kernel_build', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
     'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
 ]
@@ -45,6 +45,7 @@ def lib():
     L.apm_destroy.argtypes = [vp]
     L.apm_set_stream.argtypes = [vp, ct.c_uint64]
     L.apm_synchronize.argtypes = [vp]
+    L.apm_set_overlap.argtypes = [vp, ct.c_int]
     L.apm_set_newton.argtypes = [vp, ct.c_double, ct.c_int]
     L.apm_get_info.argtypes = [vp] + [ip] * 7
     L.apm_kernel_build.argtypes = [vp, vp, ct.c_int, ct.c_int, ct.c_double, vp, ct.c_int]
@@ -143,6 +144,9 @@ class Engine(object):
 
     def synchronize(self):
         check(self._L.apm_synchronize(self._h))
+
+    def set_overlap(self, enable=True):
+        check(self._L.apm_set_overlap(self._h, 1 if enable else 0))
 
     def set_newton(self, diff_f_tol=1e-4, max_iters=1000):
         check(self._L.apm_set_newton(self._h, float(diff_f_tol), int(max_iters)))

@@ -42,7 +42,7 @@ enum { V_F = 0, V_W, V_WS, V_B, V_A, V_T, V_S, V_FNEW, V_COUNT };
 // kernel ids for launch accounting / profiling
 enum { KID_BUILD_K = 0, KID_CHOL, KID_TRSM, KID_SYRK, KID_GEMM_TRI, KID_MATVEC, KID_TRSV, KID_NEWTON_VEC, KID_EPILOGUE,
        KID_TRANSPOSE, KID_MISC, KID_COUNT };
-static const char* const KID_NAMES[KID_COUNT] = {"k_build_K", "k_chol_step", "k_trsm_rows", "k_syrk_sub", "k_gemm_tri",
+static const char* const KID_NAMES[KID_COUNT] = {"k_build_K", "k_chol", "k_trsm_rows", "k_syrk_sub", "k_gemm_tri",
                                                  "k_matvec", "k_trsv2", "k_newton_vec", "k_is_epilogue",
                                                  "k_transpose_u", "misc"};
 
@@ -317,6 +317,11 @@ extern "C" int apm_synchronize(apm_ctx* c) {
     if (!c) return APM_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    return APM_OK;
+}
+extern "C" int apm_set_overlap(apm_ctx* c, int enable) {
+    if (!c) return APM_ERR_INVALID;
+    c->overlap_chol_k = enable != 0;
     return APM_OK;
 }
 extern "C" int apm_set_newton(apm_ctx* c, double tol, int max_iters) {

@@ -12,7 +12,7 @@ IS tail) for all chains of the rank, with fresh theta and u every step.  metric 
   value   inputs (u) already resident in HBM; timed with CUDA events, max over ranks
   e2e     the same step through the reference-facing C-ABI call with HOST buffers (pinned u, theta):
           H2D of u and theta and D2H of the results inside the timed region
-  roofline  dominant kernel family (k_chol_step, fp64 DMMA) timed live with CUDA events around every launch
+  roofline  dominant kernel family (k_chol = k_chol_dataflow / k_chol_step, fp64 DMMA) timed live with CUDA events around every launch
             of the timed region (apm_profile); peak = fp64 DMMA issue peak measured in this run
   cpu_baseline  the oracle port (numpy/scipy/OpenBLAS + the reference's own Cython kernel module when
             oracle/_ref is present) timed on this box's host cores on a bounded sample
@@ -268,20 +268,27 @@ def run_gpu_arm(args):
     for i in range(2):
         step_host(i)
 
-    # ---- timed region (device-resident inputs), per-kernel events on, clocks sampled
+    # ---- timed region (device-resident inputs), clocks sampled
     sampler = ClockSampler(local_rank)
-    eng.profile(True)
-    eng.profile_read(reset=True)
     eng.launch_count(reset=True)
     sampler.start()
     ms_total, outs = timed(step_resident, args.steps)
     clocks = sampler.stop()
     launches = eng.launch_count(reset=True)
-    prof = eng.profile_read(reset=True)
-    eng.profile(False)
     bad = int(sum((o[2] != 0).sum() for o in outs))
     iters_total = float(sum((o[1] - 3).sum() for o in outs))          # Newton iterations over all chains & steps
     chains_done = B * args.steps
+
+    # ---- roofline pass: the same K steps again with CUDA events around every launch (apm_profile) and the
+    # stream overlap switched off, so that a kernel's event time is its own duration and not a time-share
+    eng.set_overlap(False)
+    eng.profile(True)
+    eng.profile_read(reset=True)
+    ms_prof, outs_p = timed(step_resident, args.steps)
+    prof = eng.profile_read(reset=True)
+    eng.profile(False)
+    eng.set_overlap(True)
+    iters_prof = float(sum((o[1] - 3).sum() for o in outs_p))
 
     # ---- end to end through the host-buffer C-ABI call
     ms_e2e, _ = timed(step_host, args.steps)
@@ -321,20 +328,20 @@ def run_gpu_arm(args):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
         n3 = float(n)**3
         flops = {   # algorithmic flops per kernel family over the timed region (this rank)
-            'k_chol_step': (iters_total + 2. * chains_done) * n3 / 3.,
+            'k_chol': (iters_prof + 2. * chains_done) * n3 / 3.,
             'k_trsm_rows': chains_done * (n3 + float(n)**2 * N),
             'k_syrk_sub': chains_done * n3,
             'k_gemm_tri': chains_done * float(n)**2 * N,
         }
         hbm_bytes = {  # algorithmic bytes of the bandwidth-bound families
             'k_build_K': chains_done * 8. * n * n,
-            'k_matvec': iters_total * 2. * 8. * n * n,
+            'k_matvec': iters_prof * 2. * 8. * n * n,
         }
         kern = {}
         for name, (ms, cnt) in prof.items():
             if cnt == 0:
                 continue
-            ent = {'ms_total': ms, 'launches': cnt, 'share_of_step': ms / ms_total}
+            ent = {'ms_total': ms, 'launches': cnt, 'share_of_step': ms / ms_prof}
             if name in flops:
                 ent.update(bound='tensor', achieved=flops[name] / (ms * 1e-3) / 1e12, unit='TFLOP/s')
                 ent['frac'] = ent['achieved'] / peak_dmma
@@ -349,11 +356,13 @@ def run_gpu_arm(args):
             'frac': d['frac'],
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_chol_dataflow launch (256 chains, n = 768) from the
             # `ncu --set full` capture summarised in profiles/r1_final_ncu_k_chol_dataflow_full.md: 4.21 GB + 1.20 GB
-            'traffic': 5.41e9 if (dom == 'k_chol_step' and n == 768 and B == 256) else None,
+            'traffic': 5.41e9 if (dom == 'k_chol' and n == 768 and B == 256) else None,
             'traffic_note': 'bytes per launch from ncu (profiles/r1_final_ncu_k_chol_dataflow_full.md); minimum (read K, write L) '
                             'is 1.28 GB, the blocked left-looking operand traffic with a working set > L2 is 4.7 GB',
             'achieved_per_launch_gflop': flops[dom] / d['launches'] / 1e9,
             'avg_launch_ms': d['ms_total'] / d['launches'],
+            'measured': 'CUDA events around every launch of a second pass of the same %d steps with stream overlap off '
+                        '(%.2f ms/step; the timed `value` pass runs with overlap on and no per-launch events)' % (args.steps, ms_prof / args.steps),
             'peak_source': 'fp64 DMMA (mma.sync m8n8k4.f64) issue peak measured in this run by apm_measure_fp64_peak; '
                            'MEASURED_PEAKS.json has no fp64 entry (bf16 only). DFMA peak %.1f TFLOP/s. HBM peak %.0f GB/s %s'
                            % (peak_dfma, hbm_peak, hbm_src),

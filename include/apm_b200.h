@@ -71,6 +71,10 @@ int apm_set_stream(apm_ctx* ctx, uint64_t cuda_stream);
 /* Block the host until everything queued by this context has finished. */
 int apm_synchronize(apm_ctx* ctx);
 
+/* FULL estimates overlap work that is off the critical path (chol(K) on an auxiliary stream, H2D of u on a copy
+ * stream).  enable = 0 serialises everything on the context's stream (used for unperturbed per-kernel timing). */
+int apm_set_overlap(apm_ctx* ctx, int enable);
+
 /* Laplace/Newton controls, defaults as lpa.py:22-23: diff_f_tol = 1e-4, max_iters = 1000. */
 int apm_set_newton(apm_ctx* ctx, double diff_f_tol, int max_iters);
 
