@@ -412,7 +412,7 @@ def main():
     ap.add_argument('--impl', default='apm_b200', choices=['apm_b200', 'reference'])
     ap.add_argument('--chains', type=int, default=0, help='chains per GPU (default 256)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--apm-iters', type=int, default=5, help='iterations of the batched ESS+RDSS sampler leg')
+    ap.add_argument('--apm-iters', type=int, default=10, help='iterations of the batched ESS+RDSS sampler leg')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
