@@ -207,7 +207,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_dataflow, TILE_THREADS, TILE_SMEM_BYTES) == cudaSuccess &&
             occ > 0 && coop && !getenv("APM_CHOL_STEPWISE"))
-            c->flow_grid = occ * sms;
+            c->flow_grid = occ * sms / (getenv("APM_FLOW_GRID_DIV") && atoi(getenv("APM_FLOW_GRID_DIV")) > 0 ? atoi(getenv("APM_FLOW_GRID_DIV")) : 1);
         if (getenv("APM_CHOL_GROUP")) c->flow_group = atoi(getenv("APM_CHOL_GROUP")) > 0 ? atoi(getenv("APM_CHOL_GROUP")) : (1 << 20);
     }
     const size_t B = max_chains, np = c->np;
