@@ -58,6 +58,7 @@ struct apm_ctx {
     cudaStream_t launch_stream = nullptr;   // stream the launch helpers (run_chol, profiling events) currently target
     cudaEvent_t ev_k_ready = nullptr, ev_lk_done = nullptr;
     bool overlap_chol_k = true;
+    bool factored_cov = true;   // chol(C) = L_K U^-T (n^3) instead of TRSM + SYRK + chol (7/3 n^3); APM_EXPLICIT_COV=1 -> reference formulation
     int n = 0, D = 0, np = 0, nb = 0, P = 0, kind = 0;
     double eps = 1e-8;
     int maxB = 0, nslots = 0, maxN = 0, maxNpad = 0;
@@ -156,6 +157,8 @@ static int set_kernel_attrs() {
     CU_TRY(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_syrk_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_trsm_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_gemm_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_build_K, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU_TRY(cudaFuncSetAttribute(k_trsv2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -256,6 +259,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         return APM_ERR_NOMEM;
     }
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
+    c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_k_ready, cudaEventDisableTiming) != cudaSuccess ||
@@ -560,6 +564,40 @@ static int run_covariance(apm_ctx* c, int B, double* dst, long long dst_bs, cons
     return check_launch(c, "k_syrk_sub");
 }
 
+// chol(C) without forming C (see tile_engine.cuh "Factored posterior covariance"): needs chol(K) in the slots,
+// W^1/2 of the last Newton step; writes L_C and its partial log-dets into the slots.
+static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots) {
+    dim3 yg(c->np / 32, c->np / 32, B), yb(32, 8);
+    prof_begin(c, KID_TRANSPOSE);
+    k_make_Y<<<yg, yb, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->dVec[V_WS], c->np, c->dZ,
+                                       (long long)c->mat, c->np, c->dStatus);
+    APM_TRY(check_launch(c, "k_make_Y"));
+    SyrkRevParams s;
+    s.Y = c->dZ; s.y_bs = (long long)c->mat; s.ldy = c->np;
+    s.M = c->dLB; s.m_bs = (long long)c->mat; s.ldm = c->np;
+    s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
+    s.status = c->dStatus;
+    prof_begin(c, KID_SYRK);
+    k_syrk_rev<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
+    APM_TRY(check_launch(c, "k_syrk_rev"));
+    // L' = chol(M') in place (M' has eigenvalues >= 1: cannot fail for finite input)
+    APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
+                     nullptr, APM_CHAIN_CHOL_C, nullptr));
+    TrsmRevParams t;
+    t.LK = c->dSlotLK; t.lk_bs = (long long)c->mat; t.ldk = c->np; t.lk_idx = dSlots;
+    t.Lp = c->dLB; t.lp_bs = (long long)c->mat; t.ldp = c->np;
+    t.X = c->dZ; t.x_bs = (long long)c->mat; t.ldx = c->np;
+    t.LC = c->dSlotLC; t.lc_bs = (long long)c->mat; t.ldc = c->np; t.lc_idx = dSlots;
+    t.nb = c->nb;
+    t.status = c->dStatus;
+    prof_begin(c, KID_TRSM);
+    k_trsm_rev<<<B * c->nb, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
+    APM_TRY(check_launch(c, "k_trsm_rev"));
+    prof_begin(c, KID_MISC);
+    k_logdet_combine<<<B, 256, 0, c->stream>>>(c->dSlotLdK, c->dLdB, c->dSlotLdC, dSlots, c->nb, c->dStatus);
+    return check_launch(c, "k_logdet_combine");
+}
+
 // bring u (reference layout [B][n][N]) into UT [B][Npad][np]
 static int stage_u(apm_ctx* c, const double* u, int u_on_device, int N, int B) {
     if (N <= 0 || N > c->maxN) {
@@ -778,10 +816,16 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
     APM_TRY(full_front(c, theta, B, slots, overlap));
     APM_TRY(stage_u(c, u, u_on_device, N, B));
     APM_TRY(run_newton(c, B));                                                  // estimators.py:207 -> lpa.py:81-102
-    APM_TRY(run_covariance(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA));    // lpa.py:111-112
-    // chol(C) in place in the slot                                                estimators.py:209
-    APM_TRY(run_chol(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA, c->dSlotLC, (long long)c->mat, c->dSlotsA, nullptr,
-                     0, c->dSlotLdC, c->dSlotsA, APM_CHAIN_CHOL_C, nullptr));
+    if (c->factored_cov) {
+        // chol(C) = L_K U^-T straight from chol(K) and W (lpa.py:111-112 + estimators.py:209 without forming C)
+        if (overlap) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
+        APM_TRY(run_covariance_factored(c, B, c->dSlotsA));
+    } else {
+        APM_TRY(run_covariance(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA));    // lpa.py:111-112
+        // chol(C) in place in the slot                                                estimators.py:209
+        APM_TRY(run_chol(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA, c->dSlotLC, (long long)c->mat, c->dSlotsA, nullptr,
+                         0, c->dSlotLdC, c->dSlotsA, APM_CHAIN_CHOL_C, nullptr));
+    }
     dim3 cg((c->np + 255) / 256, B);
     prof_begin(c, KID_MISC);
     k_copy_vec<<<cg, 256, 0, c->stream>>>(c->dVec[V_F], c->np, nullptr, c->dSlotMu, c->np, c->dSlotsA, c->np, c->dStatus);

@@ -764,6 +764,119 @@ __global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_syrk_sub(SyrkParams 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Factored posterior covariance (replaces lpa.py:111-112 + estimators.py:209 in the fused FULL estimate):
+//   C = (K^-1 + W)^-1 = L_K M^-1 L_K^T,   M = I + L_K^T W L_K        (Woodbury; W of the last Newton step)
+//   M = U U^T with U upper triangular  =>  chol(C) = L_C = L_K U^-T   (lower x lower, positive diagonal: unique)
+// U comes from an ordinary lower Cholesky of the index-reversed matrix M' = P M P = L' L'^T (U = P L' P), and
+//   (L_C P) L'^T = L_K P   is a right triangular solve in reversed column order.
+// Cost n^3/3 (M') + n^3/3 (chol) + n^3/3 (solve) instead of n^3 (Z) + n^3 (C) + n^3/3 (chol C); no explicit C,
+// no cancellation in K - Z Z^T, and M' has eigenvalues >= 1.
+// ------------------------------------------------------------------------------------------------
+
+// M'(i,j) = [i==j] + sum_{k >= n-1-j'} Y'[i][k] Y'[j][k]  for lower tiles (i >= j), Y'[i'][k] = L_K[k][n-1-i'] W^1/2_k
+// (k_make_Y).  Row j' of Y' is zero for k-blocks < nb-1-j, so the k-range of tile (i,j) starts at block nb-1-j.
+struct SyrkRevParams {
+    const double* Y; long long y_bs; int ldy;
+    double* M; long long m_bs; int ldm;
+    int nb; int ntiles;
+    const int* status;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_syrk_rev(SyrkRevParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / p.ntiles;
+    const int tix = p.ntiles - 1 - (int)(blockIdx.x % p.ntiles);   // deepest tiles first
+    if (p.status[b] != 0) return;
+    int i = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= tix) i++;
+    while (i * (i + 1) / 2 > tix) i--;
+    const int j = tix - i * (i + 1) / 2;
+    const double* Y = p.Y + (long long)b * p.y_bs;
+    double* M = p.M + (long long)b * p.m_bs;
+    const int kstart = (p.nb - 1 - j) * TB;
+    Acc acc;
+    acc.zero();
+    if (i == j) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int g = lane >> 2, t = lane & 3, wm = warp >> 1, wn = warp & 1;
+        if (wm == wn) {
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) {   // identity on the diagonal of the 32x32 warp block
+                if (g == 2 * t) acc.v[mi][mi][0] = 1.0;
+                if (g == 2 * t + 1) acc.v[mi][mi][1] = 1.0;
+            }
+        }
+    }
+    gemm_nt_64x64<false>(acc, Y + (size_t)i * TB * p.ldy + kstart, p.ldy, Y + (size_t)j * TB * p.ldy + kstart, p.ldy,
+                         (j + 1) * TB, smem);
+    acc_store_tile(acc, M + (size_t)i * TB * p.ldm + j * TB, p.ldm);
+}
+
+// (L_C P) L'^T = L_K P : CTA (chain b, row block rb) walks the reversed block columns k' = nb-1-rb .. nb-1.
+//   X[rb,k'] = (R[rb,k'] - sum_{j'=nb-1-rb}^{k'-1} X[rb,j'] L'[k',j']^T) L'_{k'k'}^{-T},  R[r][c'] = L_K[r][n-1-c'] (lower part)
+// X (reversed coordinates) is kept in a scratch matrix as the GEMM operand and written, columns re-reversed, to L_C.
+struct TrsmRevParams {
+    const double* LK; long long lk_bs; int ldk; const int* lk_idx;   // L_K (slot)
+    const double* Lp; long long lp_bs; int ldp;                       // L' = chol(M')
+    double* X; long long x_bs; int ldx;                               // scratch, reversed coordinates
+    double* LC; long long lc_bs; int ldc; const int* lc_idx;          // output L_C (slot)
+    int nb;
+    const int* status;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_trsm_rev(TrsmRevParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / p.nb;
+    const int rb = p.nb - 1 - (int)(blockIdx.x % p.nb);   // longest rows first
+    if (p.status[b] != 0) return;
+    const double* LK = p.LK + chain_index(p.lk_idx, b) * p.lk_bs + (size_t)rb * TB * p.ldk;
+    const double* Lp = p.Lp + (long long)b * p.lp_bs;
+    double* X = p.X + (long long)b * p.x_bs + (size_t)rb * TB * p.ldx;
+    double* LC = p.LC + chain_index(p.lc_idx, b) * p.lc_bs + (size_t)rb * TB * p.ldc;
+    TileScratch s = carve_scratch(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3, wm = warp >> 1, wn = warp & 1;
+    const int k0 = p.nb - 1 - rb;
+    Acc acc;
+    for (int k = k0; k < p.nb; k++) {
+        const int ob = p.nb - 1 - k;   // original column block of L_K / L_C
+        // R tile in accumulator layout: R[r][c'] = L_K[r][ob*64 + 63 - c'], zero above L_K's diagonal (ob == rb)
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            const int r = wm * 32 + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const int c = wn * 32 + ni * 8 + 2 * t;          // reversed columns c, c+1 <- original 63-c, 62-c
+                const double2 v = __ldcg(reinterpret_cast<const double2*>(LK + (size_t)r * p.ldk + ob * TB + 62 - c));
+                const bool diag = (ob == rb);
+                acc.v[mi][ni][0] = (!diag || 63 - c <= r) ? v.y : 0.0;
+                acc.v[mi][ni][1] = (!diag || 62 - c <= r) ? v.x : 0.0;
+            }
+        }
+        prefetch_tile_l2(Lp + (size_t)k * TB * p.ldp + k * TB, p.ldp);
+        gemm_nt_64x64<true>(acc, X + k0 * TB, p.ldx, Lp + (size_t)k * TB * p.ldp + k0 * TB, p.ldp, (k - k0) * TB, smem);
+        tile_put_acc(s.Ts, acc);
+        load_diag_block(s.LT, s.invd, Lp + (size_t)k * TB * p.ldp + k * TB, p.ldp);
+        __syncthreads();
+        trsm64_smem(s.Ts, s.LT, s.invd);
+        __syncthreads();
+        tile_store(s.Ts, X + k * TB, p.ldx);
+        {   // L_C[r][ob*64 + c] = X[r][63 - c]
+#pragma unroll 4
+            for (int rr = 0; rr < 16; rr++) {
+                const int r = warp * 16 + rr;
+                double2 v;
+                v.x = s.Ts[r * TSP + 63 - lane * 2];
+                v.y = s.Ts[r * TSP + 62 - lane * 2];
+                *reinterpret_cast<double2*>(LC + (size_t)r * p.ldc + ob * TB + lane * 2) = v;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // F[s][i] = mu[i] + sum_{j <= i} U^T[s][j] L[i][j]   (estimators.py:223, 323), tile (row block rb of
 // samples, block column k): depth clipped to the lower triangle ((k+1)*64 columns).
 // ------------------------------------------------------------------------------------------------

@@ -112,6 +112,38 @@ __global__ void k_transpose_u(const double* __restrict__ u, long long u_bs, int 
     }
 }
 
+// Y'[i'][k] = L_K[k][np-1-i'] * Ws[k]  (zero above L_K's diagonal): the transposed, row-reversed, W^1/2-scaled
+// Cholesky factor whose Gram matrix is M' - I (see k_syrk_rev).  32x32 tiles through shared memory.
+__global__ void k_make_Y(const double* __restrict__ LK, long long lk_bs, const int* lk_idx, int ld,
+                         const double* __restrict__ Ws, long long ws_bs, double* __restrict__ Y, long long y_bs, int np,
+                         const int* status) {
+    __shared__ double tile[32][33];
+    const int b = blockIdx.z;
+    if (status[b] != 0) return;
+    const int k0 = blockIdx.y * 32, i0 = blockIdx.x * 32;      // L_K rows k0.., columns i0..
+    const double* L = LK + chain_index(lk_idx, b) * lk_bs;
+    double* Yb = Y + (long long)b * y_bs;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    const bool above = (i0 > k0 + 31);             // tile entirely above the diagonal: zeros
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, i = i0 + tx;
+        tile[r][tx] = (!above && i <= k) ? L[(size_t)k * ld + i] * Ws[(long long)b * ws_bs + k] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r;                      // original column of L_K -> row np-1-i of Y'
+        Yb[(size_t)(np - 1 - i) * np + k0 + tx] = tile[tx][r];
+    }
+}
+
+// per-slot partial log-dets of L_C = L_K U^-T:  sum log diag L_C = sum log diag L_K - sum log diag L'
+__global__ void k_logdet_combine(const double* ldK, const double* ldM, double* ldC, const int* slot_idx, int nb, const int* status) {
+    const int b = blockIdx.x, k = threadIdx.x;
+    if (status[b] != 0 || k >= nb) return;
+    const long long sl = chain_index(slot_idx, b);
+    ldC[sl * nb + k] = ldK[sl * nb + k] - ldM[(long long)b * nb + k];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Newton iteration pieces (lpa.py:85-99), one CTA per chain for the O(n) parts
 // ------------------------------------------------------------------------------------------------
