@@ -72,6 +72,7 @@ struct apm_ctx {
     int *dFlowCounter = nullptr, *dFlowProgress = nullptr, *dFlowSkip = nullptr;
     int flow_grid = 0;        // persistent grid of k_chol_dataflow (SMs x occupancy); 0 = per-step launches
     int flow_group = 1 << 20; // chains per scheduling group (default: all chains = step-major order)
+    double *dSymvDirect = nullptr, *dSymvPart = nullptr;   // scratch of the symmetric mat-vec
     double* dInvB = nullptr;   // (L_kk^{-1})^T diagonal blocks of chol(B): [max_chains][nb][64*64]
     double* dVec[V_COUNT] = {nullptr};
     double *dUT = nullptr, *dF = nullptr, *dZf = nullptr, *dUstage = nullptr;
@@ -228,13 +229,15 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     A(dev_alloc(c, &c->dSlotLdC, (size_t)n_slots * c->nb));
     A(dev_alloc(c, &c->dLdB, B * c->nb));
     A(dev_alloc(c, &c->dInvB, B * (size_t)c->nb * TB * TB));
+    A(dev_alloc(c, &c->dSymvDirect, B * np));
+    A(dev_alloc(c, &c->dSymvPart, B * (size_t)c->nb * c->nb * 64));
     for (int v = 0; v < V_COUNT; v++) A(dev_alloc(c, &c->dVec[v], B * np));
     const size_t usz = B * (size_t)c->maxNpad * np;
     A(dev_alloc(c, &c->dUT, usz));
     A(dev_alloc(c, &c->dF, usz));
     A(dev_alloc(c, &c->dZf, usz));
     A(dev_alloc(c, &c->dUstage, B * (size_t)n * max_nimp));
-    A(dev_alloc(c, &c->dKp, B * (size_t)(D + 1)));
+    A(dev_alloc(c, &c->dKp, B * (size_t)(2 * D + 1)));
     A(dev_alloc(c, &c->dOut, B * 2));
     A(dev_alloc(c, &c->dLogw, B * (size_t)max_nimp));
     A(dev_alloc(c, &c->dStatus, B));
@@ -250,7 +253,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         apm_destroy(c);
         return rc;
     }
-    if (cudaMallocHost(&c->hKp, B * (D + 1) * sizeof(double)) != cudaSuccess ||
+    if (cudaMallocHost(&c->hKp, B * (2 * D + 1) * sizeof(double)) != cudaSuccess ||
         cudaMallocHost(&c->hOut, B * 2 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost(&c->hInts, B * 4 * sizeof(int)) != cudaSuccess ||
         cudaMallocHost(&c->hNActive, 4 * sizeof(int)) != cudaSuccess) {
@@ -399,16 +402,20 @@ static int reset_status(apm_ctx* c, int B) {
 // sigma = exp(theta0); ARD: tau_k = exp(theta_k); ISO: 2 tau^2 -- host libm, as the reference's libc exp
 static int upload_kernel_params(apm_ctx* c, const double* theta, int B, int kind) {
     const int P = (kind == APM_KERNEL_ARD) ? c->D + 1 : 2;
-    const int stride = c->D + 1;
+    const int stride = 2 * c->D + 1;
     for (int b = 0; b < B; b++) {
         const double* th = theta + (size_t)b * P;
         double* kp = c->hKp + (size_t)b * stride;
         kp[0] = exp(th[0]);
         if (kind == APM_KERNEL_ARD) {
-            for (int k = 0; k < c->D; k++) kp[1 + k] = exp(th[1 + k]);
+            for (int k = 0; k < c->D; k++) {
+                kp[1 + k] = exp(th[1 + k]);
+                kp[1 + c->D + k] = 1.0 / kp[1 + k];
+            }
         } else {
             const double tau = exp(th[1]);
             kp[1] = 2. * (tau * tau);
+            kp[2] = 1.0 / kp[1];
         }
     }
     CU_TRY(cudaMemcpyAsync(c->dKp, c->hKp, sizeof(double) * (size_t)B * stride, cudaMemcpyHostToDevice, c->stream));
@@ -418,11 +425,11 @@ static int upload_kernel_params(apm_ctx* c, const double* theta, int B, int kind
 static int build_K(apm_ctx* c, int B, int kind, double eps) {
     KBuildParams p;
     p.X = c->dX; p.n = c->n; p.D = c->D; p.np = c->np; p.nb = c->nb;
-    p.kp = c->dKp; p.kp_stride = c->D + 1;
+    p.kp = c->dKp; p.kp_stride = 2 * c->D + 1;
     p.ard = (kind == APM_KERNEL_ARD); p.eps = eps;
     p.K = c->dK; p.k_bs = (long long)c->mat;
     p.ntiles = c->nb * (c->nb + 1) / 2;
-    const size_t smem = (size_t)(2 * 64 * c->D + 64 * VSP + c->D + 1) * sizeof(double);
+    const size_t smem = (size_t)(2 * 64 * c->D + 64 * VSP + 2 * c->D + 1) * sizeof(double);
     if (smem > 96 * 1024) {
         set_err("build_K: feature dimension too large for the shared-memory staging of X");
         return APM_ERR_INVALID;
@@ -481,6 +488,18 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     return APM_OK;
 }
 
+// out = rs * (K x) for all active chains, reading only the lower tiles of the symmetric K (lpa.py:94-95 mat-vecs)
+static int run_symv(apm_ctx* c, int B, const double* x, const double* rs, double* out) {
+    prof_begin(c, KID_MATVEC);
+    k_symv_lower<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, c->nb, x, c->np, c->dSymvDirect,
+                                                        c->dSymvPart, c->dActive, c->dStatus);
+    APM_TRY(check_launch(c, "k_symv_lower"));
+    prof_begin(c, KID_MATVEC);
+    k_symv_reduce<<<dim3(c->nb, B), 64, 0, c->stream>>>(c->dSymvDirect, c->dSymvPart, c->nb, rs, out, c->np, c->dActive,
+                                                        c->dStatus);
+    return check_launch(c, "k_symv_reduce");
+}
+
 static NewtonVecs make_nv(apm_ctx* c) {
     NewtonVecs nv;
     nv.f = c->dVec[V_F]; nv.W = c->dVec[V_W]; nv.Ws = c->dVec[V_WS]; nv.bvec = c->dVec[V_B];
@@ -508,16 +527,12 @@ static int run_newton(apm_ctx* c, int B) {
         set_err("run_newton: n too large for the single-CTA triangular solve");
         return APM_ERR_INVALID;
     }
-    const dim3 mv_grid(c->np / 32, B);
     for (int it = 0; it < c->max_iters; it++) {
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_prep<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_prep"));
         // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b))
-        prof_begin(c, KID_MATVEC);
-        k_matvec<<<mv_grid, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, c->np, nv.bvec, nv.Ws, nv.t, c->np,
-                                                 c->dActive, c->dStatus);
-        APM_TRY(check_launch(c, "k_matvec"));
+        APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t));
         // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
         APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
                          nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB));
@@ -527,10 +542,7 @@ static int run_newton(apm_ctx* c, int B) {
                                                   (long long)c->nb * TB * TB, nv);
         APM_TRY(check_launch(c, "k_trsv2"));
         // f_new = K a                                              (lpa.py:95)
-        prof_begin(c, KID_MATVEC);
-        k_matvec<<<mv_grid, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, c->np, nv.a, nullptr, nv.fnew, c->np,
-                                                 c->dActive, c->dStatus);
-        APM_TRY(check_launch(c, "k_matvec"));
+        APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew));
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_finish<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_finish"));

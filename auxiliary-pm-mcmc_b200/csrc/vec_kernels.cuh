@@ -16,11 +16,20 @@ constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 // ------------------------------------------------------------------------------------------------
 struct KBuildParams {
     const double* X; int n, D, np, nb;          // X [np][D] (pad rows zero)
-    const double* kp; int kp_stride;            // per chain: ARD [sigma, tau_1..tau_D], ISO [sigma, 2 tau^2]
+    const double* kp; int kp_stride;            // per chain: ARD [sigma, tau_1..tau_D, 1/tau_1..1/tau_D], ISO [sigma, 2 tau^2, 1/(2 tau^2)]
     int ard; double eps;
     double* K; long long k_bs;                  // [chain][np][np]
     int ntiles;                                 // nb(nb+1)/2
 };
+
+// a / b with r = RN(1/b) from the host: q = RN(a r), exact remainder by FMA, one correction (Markstein).  Returns the
+// correctly rounded quotient (the operands here are far from over/underflow), 3 fp64 operations instead of the ~15 of
+// the IEEE division sequence.
+__device__ __forceinline__ double div_by(double a, double b, double r) {
+    const double q = __dmul_rn(a, r);
+    const double rem = fma(-q, b, a);
+    return fma(rem, r, q);
+}
 
 __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
     extern __shared__ __align__(16) double smem[];
@@ -34,7 +43,7 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
     double* Xi = smem;                    // [64][D]
     double* XjT = Xi + 64 * D;            // [D][64]
     double* Ts = XjT + 64 * D;            // [64][65] mirror staging
-    double* prm = Ts + 64 * VSP;          // [D+1]
+    double* prm = Ts + 64 * VSP;          // [2D+1]
     const int tid = threadIdx.x;
     for (int e = tid; e < 64 * D; e += 256) {
         const int r = e / D, k = e % D;
@@ -42,7 +51,7 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
         XjT[k * 64 + r] = p.X[(size_t)(tj * 64 + r) * D + k];
     }
     const double* kp = p.kp + (size_t)b * p.kp_stride;
-    for (int e = tid; e < D + 1; e += 256) prm[e] = (p.ard || e < 2) ? kp[e] : 0.0;
+    for (int e = tid; e < 2 * D + 1; e += 256) prm[e] = (p.ard || e < 3) ? kp[e] : 0.0;
     __syncthreads();
     const double sigma = prm[0];
     const int tx = tid & 31, ty = tid >> 5;
@@ -59,7 +68,7 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
             double acc = 0.0;
             if (p.ard) {
                 for (int k = 0; k < D; k++) {
-                    const double d = __ddiv_rn(__dsub_rn(Xi[r * D + k], XjT[k * 64 + c]), prm[k + 1]);
+                    const double d = div_by(__dsub_rn(Xi[r * D + k], XjT[k * 64 + c]), prm[k + 1], prm[D + 1 + k]);
                     acc = __dadd_rn(acc, __dmul_rn(d, d));
                 }
                 acc = __dmul_rn(sigma, exp(-acc * 0.5));
@@ -68,7 +77,7 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
                     const double d = __dsub_rn(Xi[r * D + k], XjT[k * 64 + c]);
                     acc = __dadd_rn(acc, __dmul_rn(d, d));
                 }
-                acc = __dmul_rn(sigma, exp(__ddiv_rn(-acc, prm[1])));
+                acc = __dmul_rn(sigma, exp(div_by(-acc, prm[1], prm[2])));
             }
             if (gi == gj) acc = sigma + p.eps;
             if (gi >= p.n || gj >= p.n) acc = (gi == gj) ? 1.0 : 0.0;
@@ -201,6 +210,67 @@ __global__ void __launch_bounds__(256) k_matvec(const double* __restrict__ M, lo
         acc = warp_sum(acc);
         if (lane == 0) out[(long long)b * vs + r] = rs ? rs[(long long)b * vs + r] * acc : acc;
     }
+}
+
+// Symmetric mat-vec that reads only the lower tiles of K (half the HBM bytes of k_matvec): CTA (row block i, chain)
+// streams the tiles (i, j <= i) once; each tile T gives the direct product T x_j for rows i and, for j < i, the
+// transposed product T^T x_i for rows j, which goes to a scratch part[chain][i][j][64] and is added in a fixed order
+// by k_symv_reduce (deterministic: no atomics).  256 threads = 8 warps x 8 tile rows.
+__global__ void __launch_bounds__(256) k_symv_lower(const double* __restrict__ M, long long m_bs, int ld, int nb,
+                                                    const double* __restrict__ x, long long vs, double* __restrict__ direct,
+                                                    double* __restrict__ part, const int* active, const int* status) {
+    __shared__ double colred[8][64];
+    const int b = blockIdx.y;
+    if ((active && !active[b]) || (status && status[b] != 0)) return;
+    const int i = nb - 1 - blockIdx.x;   // longest rows first
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* Mb = M + (long long)b * m_bs + (size_t)(i * 64 + warp * 8) * ld;
+    const double* xb = x + (long long)b * vs;
+    double xi[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) xi[rr] = xb[i * 64 + warp * 8 + rr];
+    double racc[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) racc[rr] = 0.0;
+    for (int j = 0; j <= i; j++) {
+        const double2 xj = *reinterpret_cast<const double2*>(xb + j * 64 + lane * 2);
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) {
+            const double2 m = *reinterpret_cast<const double2*>(Mb + (size_t)rr * ld + j * 64 + lane * 2);
+            racc[rr] = fma(m.x, xj.x, racc[rr]);
+            racc[rr] = fma(m.y, xj.y, racc[rr]);
+            c0 = fma(m.x, xi[rr], c0);
+            c1 = fma(m.y, xi[rr], c1);
+        }
+        if (j < i) {   // transposed contribution of this tile to rows of block j
+            colred[warp][lane * 2] = c0;
+            colred[warp][lane * 2 + 1] = c1;
+            __syncthreads();
+            if (threadIdx.x < 64) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) v += colred[w][threadIdx.x];
+                part[(((size_t)b * nb + i) * nb + j) * 64 + threadIdx.x] = v;
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) {
+        const double v = warp_sum(racc[rr]);
+        if (lane == 0) direct[(long long)b * vs + i * 64 + warp * 8 + rr] = v;
+    }
+}
+// out_j = rs_j * (direct_j + sum_{i > j} part[i][j]); grid (nb, chains), 64 threads
+__global__ void k_symv_reduce(const double* __restrict__ direct, const double* __restrict__ part, int nb,
+                              const double* __restrict__ rs, double* __restrict__ out, long long vs, const int* active,
+                              const int* status) {
+    const int b = blockIdx.y, j = blockIdx.x, r = threadIdx.x;
+    if ((active && !active[b]) || (status && status[b] != 0)) return;
+    double v = direct[(long long)b * vs + j * 64 + r];
+    for (int i = j + 1; i < nb; i++) v += part[(((size_t)b * nb + i) * nb + j) * 64 + r];
+    out[(long long)b * vs + j * 64 + r] = rs ? rs[(long long)b * vs + j * 64 + r] * v : v;
 }
 
 // s = L^{-T} L^{-1} t (lpa.py:94 cho_solve with one right-hand side), then a = b - Ws * s.

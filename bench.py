@@ -336,7 +336,7 @@ def run_gpu_arm(args):
         }
         hbm_bytes = {  # algorithmic bytes of the bandwidth-bound families
             'k_build_K': chains_done * 8. * n * n,
-            'k_matvec': iters_prof * 2. * 8. * n * n,
+            'k_matvec': iters_prof * 2. * 8. * (n * (n + 64) / 2.),   # symmetric mat-vec: lower tiles only
         }
         kern = {}
         for name, (ms, cnt) in prof.items():
