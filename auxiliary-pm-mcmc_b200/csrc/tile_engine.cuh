@@ -513,9 +513,18 @@ __device__ __forceinline__ void wait_progress(const int* p, int need, int spin_n
     }
     __syncthreads();
 }
-// all threads call after their global stores
+// two counters, one fence and one barrier
+__device__ __forceinline__ void wait_progress2(const int* p0, int need0, const int* p1, int need1, int spin_ns = 100) {
+    if (threadIdx.x == 0) {
+        while (ld_relaxed_gpu(p0) < need0) __nanosleep(spin_ns);
+        while (ld_relaxed_gpu(p1) < need1) __nanosleep(spin_ns);
+        __threadfence();
+    }
+    __syncthreads();
+}
+// all threads call after their global stores: the block barrier orders every thread's stores before thread 0's
+// gpu-scope release store (cumulativity), so one fence-carrying store publishes the whole tile
 __device__ __forceinline__ void publish_progress(int* p, int v) {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release_gpu(p, v);
 }
@@ -559,8 +568,8 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
         // the source tile never depends on other tasks (in-place: nobody has written tile (i,k) yet)
         if (early) acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sci, sc ? sc + k * TB : nullptr, false);
         if (FLOW) {
-            wait_progress(prog + k, k + 1, f.spin_ns);   // block row k complete (including L_kk)
-            wait_progress(prog + i, k, f.spin_ns);       // our own row up to column block k-1 (and its D_ii updates)
+            // block row k complete (including L_kk); our own row up to column block k-1 (and its D_ii updates)
+            wait_progress2(prog + k, k + 1, prog + i, k, f.spin_ns);
         }
         if (!early) acc_load_tile(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sci, sc ? sc + k * TB : nullptr, false);
         PHASE_MARK(0);  // waits + source tile load issue

@@ -3,6 +3,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from apm_b200 import _capi, synth
+if os.environ.get('LIB'):
+    _capi.LIB_PATH = os.path.join(ROOT, 'auxiliary-pm-mcmc_b200', os.environ['LIB'])
 n, D, B = 768, 8, int(os.environ.get('B', 256))
 X, y, th = synth.make_dataset(n, D, seed=0)
 thetas = synth.bulk_thetas(B, D)
