@@ -12,6 +12,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/apm_b200.h"
@@ -37,6 +38,7 @@ static void set_err(const std::string& s) { g_err = s; }
         if (r__ != APM_OK) return r__; \
     } while (0)
 
+constexpr int MAX_LANES = 8;
 enum { V_F = 0, V_W, V_WS, V_B, V_A, V_T, V_S, V_FNEW, V_COUNT };
 
 // kernel ids for launch accounting / profiling
@@ -82,6 +84,16 @@ struct apm_ctx {
     double *hKp = nullptr, *hOut = nullptr;
     int *hInts = nullptr, *hNActive = nullptr;
     std::vector<char> slot_valid;
+    // Lanes: a FULL estimate of many chains is split into up to n_lanes contiguous chain groups, each driven by its own
+    // host thread on its own streams (per-step Cholesky launches), so that the latency-bound Newton kernels, the
+    // host round trips and the stragglers of one group overlap the DMMA kernels of the others.  A lane is a view of
+    // the root context: the same buffers with every per-chain pointer offset to the group's first chain.
+    apm_ctx* root = nullptr;            // non-null in a lane view
+    std::vector<apm_ctx*> lanes;        // root only
+    int n_lanes = 1, lane_min_chains = 32, lane_min_batch = 128;
+    cudaEvent_t ev_fork = nullptr;
+    int lane_rc = 0;
+    std::string lane_err;
     int64_t launches = 0;
     std::vector<void*> allocs;
     // optional per-kernel CUDA-event timing (apm_profile): events bracket every launch on ctx->stream
@@ -92,6 +104,8 @@ struct apm_ctx {
     double prof_ms[KID_COUNT] = {0};
     int64_t prof_n[KID_COUNT] = {0};
 };
+
+static char* slot_flags(apm_ctx* c) { return (c->root ? c->root : c)->slot_valid.data(); }
 
 template <typename T>
 static int dev_alloc(apm_ctx* c, T** p, size_t count) {
@@ -204,7 +218,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     c->maxN = max_nimp;
     c->maxNpad = (max_nimp + TB - 1) / TB * TB;
     c->mat = (size_t)c->np * c->np;
-    c->slot_valid.assign(n_slots, 0);
+    c->slot_valid.assign(n_slots, 0);  // (lane views share the root's flags: slot_flags())
     {
         int occ = 0, sms = 0, coop = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -243,10 +257,10 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     A(dev_alloc(c, &c->dStatus, B));
     A(dev_alloc(c, &c->dActive, B));
     A(dev_alloc(c, &c->dIters, B));
-    A(dev_alloc(c, &c->dNActive, 4));
+    A(dev_alloc(c, &c->dNActive, 4 * (MAX_LANES + 1)));
     A(dev_alloc(c, &c->dSlotsA, B));
     A(dev_alloc(c, &c->dSlotsB, B));
-    A(dev_alloc(c, &c->dFlowCounter, 4));
+    A(dev_alloc(c, &c->dFlowCounter, 4 * (MAX_LANES + 1)));
     A(dev_alloc(c, &c->dFlowProgress, B * (size_t)c->nb));
     A(dev_alloc(c, &c->dFlowSkip, B));
     if (rc != APM_OK) {
@@ -256,7 +270,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     if (cudaMallocHost(&c->hKp, B * (2 * D + 1) * sizeof(double)) != cudaSuccess ||
         cudaMallocHost(&c->hOut, B * 2 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost(&c->hInts, B * 4 * sizeof(int)) != cudaSuccess ||
-        cudaMallocHost(&c->hNActive, 4 * sizeof(int)) != cudaSuccess) {
+        cudaMallocHost(&c->hNActive, 4 * (MAX_LANES + 1) * sizeof(int)) != cudaSuccess) {
         set_err("apm_create: pinned host allocation failed");
         apm_destroy(c);
         return APM_ERR_NOMEM;
@@ -291,6 +305,41 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         apm_destroy(c);
         return APM_ERR_CUDA;
     }
+    // lane views (streams and events of their own; buffers are the root's)
+    c->n_lanes = getenv("APM_LANES") ? atoi(getenv("APM_LANES")) : 8;
+    if (c->n_lanes < 1) c->n_lanes = 1;
+    if (c->n_lanes > MAX_LANES) c->n_lanes = MAX_LANES;
+    if (getenv("APM_LANE_MIN_CHAINS") && atoi(getenv("APM_LANE_MIN_CHAINS")) > 0) c->lane_min_chains = atoi(getenv("APM_LANE_MIN_CHAINS"));
+    if (getenv("APM_LANE_MIN_BATCH") && atoi(getenv("APM_LANE_MIN_BATCH")) > 0) c->lane_min_batch = atoi(getenv("APM_LANE_MIN_BATCH"));
+    if (c->n_lanes > 1) {
+        if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+            set_err("apm_create: event creation failed");
+            apm_destroy(c);
+            return APM_ERR_CUDA;
+        }
+        for (int l = 0; l < c->n_lanes; l++) {
+            apm_ctx* v = new apm_ctx(*c);
+            v->root = c;
+            v->lanes.clear(); v->allocs.clear(); v->ev_pool.clear(); v->pending.clear(); v->slot_valid.clear();
+            v->prof = false;
+            v->launches = 0;
+            v->stream = v->copy_stream = v->aux_stream = nullptr;
+            v->ev_k_ready = v->ev_lk_done = v->copy_done = v->ev_fork = nullptr;
+            v->u_staged = false;
+            if (!getenv("APM_LANE_FLOW")) v->flow_grid = 0;   // per-step Cholesky launches: no spinning CTAs beside other lanes' kernels
+            c->lanes.push_back(v);
+            if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&v->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&v->ev_k_ready, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&v->ev_lk_done, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&v->copy_done, cudaEventDisableTiming) != cudaSuccess) {
+                set_err("apm_create: lane stream/event creation failed");
+                apm_destroy(c);
+                return APM_ERR_CUDA;
+            }
+        }
+    }
     *out = c;
     return APM_OK;
 }
@@ -300,6 +349,17 @@ extern "C" int apm_destroy(apm_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     prof_resolve(c);
+    for (apm_ctx* v : c->lanes) {
+        if (v->stream) cudaStreamDestroy(v->stream);
+        if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
+        if (v->aux_stream) cudaStreamDestroy(v->aux_stream);
+        if (v->ev_k_ready) cudaEventDestroy(v->ev_k_ready);
+        if (v->ev_lk_done) cudaEventDestroy(v->ev_lk_done);
+        if (v->copy_done) cudaEventDestroy(v->copy_done);
+        delete v;
+    }
+    c->lanes.clear();
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->ev_k_ready) cudaEventDestroy(c->ev_k_ready);
@@ -329,12 +389,17 @@ extern "C" int apm_synchronize(apm_ctx* c) {
 extern "C" int apm_set_overlap(apm_ctx* c, int enable) {
     if (!c) return APM_ERR_INVALID;
     c->overlap_chol_k = enable != 0;
+    for (apm_ctx* l : c->lanes) l->overlap_chol_k = c->overlap_chol_k;
     return APM_OK;
 }
 extern "C" int apm_set_newton(apm_ctx* c, double tol, int max_iters) {
     if (!c || !(tol > 0) || max_iters <= 0) return APM_ERR_INVALID;
     c->tol = tol;
     c->max_iters = max_iters;
+    for (apm_ctx* l : c->lanes) {
+        l->tol = tol;
+        l->max_iters = max_iters;
+    }
     return APM_OK;
 }
 extern "C" int apm_get_info(apm_ctx* c, int* n, int* D, int* n_pad, int* n_theta, int* n_slots, int* max_chains,
@@ -379,6 +444,10 @@ extern "C" int64_t apm_launch_count(apm_ctx* c, int reset) {
     if (!c) return 0;
     int64_t v = c->launches;
     if (reset) c->launches = 0;
+    for (apm_ctx* l : c->lanes) {
+        v += l->launches;
+        if (reset) l->launches = 0;
+    }
     return v;
 }
 
@@ -696,7 +765,7 @@ static int upload_slots(apm_ctx* c, const int* slots, int B, int* dSlots, bool r
             set_err("slot index out of range");
             return APM_ERR_INVALID;
         }
-        if (require_valid && !c->slot_valid[slots[b]]) {
+        if (require_valid && !slot_flags(c)[slots[b]]) {
             set_err("slot " + std::to_string(slots[b]) + " holds no valid cache");
             return APM_ERR_INVALID;
         }
@@ -801,7 +870,7 @@ extern "C" int apm_laplace(apm_ctx* c, const double* K, int K_on_device, int B, 
 static int full_front(apm_ctx* c, const double* theta, int B, const int* slots, bool overlap = false) {
     APM_TRY(reset_status(c, B));
     APM_TRY(upload_slots(c, slots, B, c->dSlotsA, false));
-    for (int b = 0; b < B; b++) c->slot_valid[slots[b]] = 0;
+    for (int b = 0; b < B; b++) slot_flags(c)[slots[b]] = 0;
     APM_TRY(upload_kernel_params(c, theta, B, c->kind));
     APM_TRY(build_K(c, B, c->kind, c->eps));
     if (overlap) {
@@ -818,10 +887,83 @@ static int full_front(apm_ctx* c, const double* theta, int B, const int* slots, 
     return rc;
 }
 
+// point a lane view at chains [off, off + cnt) of the root's buffers (N: importance samples of this call)
+static void lane_bind(apm_ctx* v, int lane, int off, int cnt, int N) {
+    const apm_ctx* r = v->root;
+    const size_t o = (size_t)off, np = r->np, nb = r->nb;
+    const size_t Npad = (size_t)((N + TB - 1) / TB * TB);
+    v->maxB = cnt;
+    v->dK = r->dK + o * r->mat; v->dLB = r->dLB + o * r->mat; v->dZ = r->dZ + o * r->mat;
+    v->dLdB = r->dLdB + o * nb;
+    v->dInvB = r->dInvB + o * nb * TB * TB;
+    v->dSymvDirect = r->dSymvDirect + o * np;
+    v->dSymvPart = r->dSymvPart + o * nb * nb * 64;
+    for (int k = 0; k < V_COUNT; k++) v->dVec[k] = r->dVec[k] + o * np;
+    v->dUT = r->dUT + o * Npad * np; v->dF = r->dF + o * Npad * np; v->dZf = r->dZf + o * Npad * np;
+    v->dUstage = r->dUstage + o * (size_t)r->n * N;
+    v->dKp = r->dKp + o * (2 * r->D + 1);
+    v->dOut = r->dOut + o * 2;
+    v->dLogw = r->dLogw + o * N;
+    v->dStatus = r->dStatus + o; v->dActive = r->dActive + o; v->dIters = r->dIters + o;
+    v->dSlotsA = r->dSlotsA + o; v->dSlotsB = r->dSlotsB + o;
+    v->dFlowSkip = r->dFlowSkip + o; v->dFlowProgress = r->dFlowProgress + o * nb;
+    v->dNActive = r->dNActive + 4 * (lane + 1); v->dFlowCounter = r->dFlowCounter + 4 * (lane + 1);
+    v->hKp = r->hKp + o * (2 * r->D + 1); v->hOut = r->hOut + o * 2; v->hInts = r->hInts + o * 4;
+    v->hNActive = r->hNActive + 4 * (lane + 1);
+    v->overlap_chol_k = r->overlap_chol_k; v->factored_cov = r->factored_cov;
+    v->tol = r->tol; v->max_iters = r->max_iters;
+}
+
+static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
+                              const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status);
+
 extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
                                  const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status) {
     APM_TRY(check_B(c, B));
     if (!theta || !u || !slots || !logml_out) return APM_ERR_INVALID;
+    // small batches stay on the single-launch dataflow path (a lane needs enough chains to fill its kernels)
+    int G = (c->prof || B < c->lane_min_batch) ? 1 : (int)c->lanes.size();
+    if (G > B / c->lane_min_chains) G = B / c->lane_min_chains;
+    if (G < 2) return estimate_full_impl(c, theta, u, u_on_device, N, B, slots, logml_out, cubic_ops_out, chain_status);
+    if (N <= 0 || N > c->maxN) {
+        set_err("N (importance samples) out of range for this context");
+        return APM_ERR_INVALID;
+    }
+    cancel_prefetch(c);
+    // lanes start after everything already queued on the caller's stream (device-resident u may still be in flight)
+    CU_TRY(cudaEventRecord(c->ev_fork, c->stream));
+    const int per = (B + G - 1) / G;
+    std::vector<std::thread> workers;
+    for (int l = 0; l < G; l++) {
+        const int off = l * per, cnt = (off + per <= B) ? per : B - off;
+        if (cnt <= 0) break;
+        apm_ctx* v = c->lanes[l];
+        lane_bind(v, l, off, cnt, N);
+        v->lane_rc = APM_OK;
+        workers.emplace_back([=]() {
+            cudaSetDevice(v->device);
+            int rc = (cudaStreamWaitEvent(v->stream, c->ev_fork, 0) == cudaSuccess) ? APM_OK : APM_ERR_CUDA;
+            if (rc == APM_OK)
+                rc = estimate_full_impl(v, theta + (size_t)off * c->P, u + (size_t)off * c->n * N, u_on_device, N, cnt, slots + off,
+                                        logml_out + off, cubic_ops_out ? cubic_ops_out + off : nullptr,
+                                        chain_status ? chain_status + off : nullptr);
+            v->lane_rc = rc;
+            if (rc != APM_OK) v->lane_err = g_err;   // g_err is thread-local
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int l = 0; l < (int)workers.size(); l++) {
+        if (c->lanes[l]->lane_rc != APM_OK) {
+            set_err("lane " + std::to_string(l) + ": " + c->lanes[l]->lane_err);
+            return c->lanes[l]->lane_rc;
+        }
+    }
+    return APM_OK;
+}
+
+static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
+                              const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status) {
+    APM_TRY(check_B(c, B));
     cancel_prefetch(c);
     APM_TRY(prefetch_u(c, u, u_on_device, N, B));
     const bool overlap = c->overlap_chol_k;
@@ -847,7 +989,7 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
     std::vector<int> st(B);
     APM_TRY(fetch_results(c, B, c->dOut, 1, logml_out, cubic_ops_out, 3, st.data()));  // iters + 1 + 2 (est.py:217)
     for (int b = 0; b < B; b++) {
-        c->slot_valid[slots[b]] = (st[b] == 0);
+        slot_flags(c)[slots[b]] = (st[b] == 0);
         if (chain_status) chain_status[b] = st[b];
     }
     return APM_OK;
@@ -978,7 +1120,7 @@ extern "C" int apm_slot_import(apm_ctx* c, int slot, const double* K_chol, const
         CU_TRY(cudaMemcpyAsync(c->dSlotMu + (size_t)slot * c->np, f_post, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
     }
     CU_TRY(cudaStreamSynchronize(c->stream));
-    c->slot_valid[slot] = 1;
+    slot_flags(c)[slot] = 1;
     return APM_OK;
 }
 
@@ -986,7 +1128,7 @@ extern "C" int apm_slot_factor(apm_ctx* c, int slot, const double* K, const doub
                                int* chain_status) {
     if (!c || slot < 0 || slot >= c->nslots || !K || !C || !f_post) return APM_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->device));
-    c->slot_valid[slot] = 0;
+    slot_flags(c)[slot] = 0;
     APM_TRY(reset_status(c, 1));
     c->hInts[0] = slot;
     CU_TRY(cudaMemcpyAsync(c->dSlotsA, c->hInts, sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -1003,7 +1145,7 @@ extern "C" int apm_slot_factor(apm_ctx* c, int slot, const double* K, const doub
     CU_TRY(cudaMemcpyAsync(c->hInts, c->dStatus, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     st = c->hInts[0];
-    c->slot_valid[slot] = (st == 0);
+    slot_flags(c)[slot] = (st == 0);
     if (chain_status) chain_status[0] = st;
     return APM_OK;
 }
@@ -1020,7 +1162,7 @@ extern "C" int apm_slot_copy(apm_ctx* c, const int* src, const int* dst, int B) 
         CU_TRY(cudaMemcpyAsync(c->dSlotMu + d * c->np, c->dSlotMu + s * c->np, sizeof(double) * c->np, cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->dSlotLdK + d * c->nb, c->dSlotLdK + s * c->nb, sizeof(double) * c->nb, cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->dSlotLdC + d * c->nb, c->dSlotLdC + s * c->nb, sizeof(double) * c->nb, cudaMemcpyDeviceToDevice, c->stream));
-        c->slot_valid[d] = c->slot_valid[s];
+        slot_flags(c)[d] = slot_flags(c)[s];
     }
     return APM_OK;
 }

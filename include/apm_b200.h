@@ -114,6 +114,11 @@ int apm_laplace(apm_ctx* ctx, const double* K, int K_on_device, int B, int calc_
  *   logml_out HOST [B]; cubic_ops_out HOST [B] = newton iters + 1 + 2 (est.py:217), may be NULL;
  *   chain_status HOST [B].
  * Chains with a non-zero status get logml = NaN and leave their slot invalid.
+ * Execution: batches of >= 128 chains are split into up to 8 contiguous chain groups ("lanes"), each driven by
+ * its own host thread on its own CUDA streams, so the latency-bound Newton kernels, host round trips and H2D
+ * copies of one group overlap the tensor-pipe kernels of the others; the call returns when all lanes are done.
+ * Results do not depend on the split (bit-identical to the single-lane path).  Environment overrides:
+ * APM_LANES (1 disables), APM_LANE_MIN_CHAINS, APM_LANE_MIN_BATCH.
  */
 int apm_estimate_full(apm_ctx* ctx, const double* theta, const double* u, int u_on_device, int N,
                       int B, const int* slots, double* logml_out, int* cubic_ops_out,

@@ -183,6 +183,36 @@ def test_cached_equals_full_and_batch_independence():
     eng.close()
 
 
+def test_lanes_match_single_path():
+    """A FULL estimate of >= 128 chains is split over lane views (host threads + streams, per-step Cholesky
+    launches); smaller batches take the single-launch dataflow path.  Same chains -> bit-identical results,
+    iteration counts and caches, for host and device-resident u, including a ragged last lane."""
+    import torch
+    n, D, N, B = 130, 3, 5, 167
+    X, y, th = synth.make_dataset(n, D, seed=11)
+    rs = np.random.RandomState(2)
+    thetas = th[None] + 0.4 * rs.normal(size=(B, D + 1))
+    u = rs.normal(size=(B, n, N))
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N)
+    eng.use_torch_stream()
+    laned, ops_l, st_l = eng.estimate_full(thetas, u, np.arange(B))
+    laned_dev, _, _ = eng.estimate_full(thetas, torch.from_numpy(u).cuda(), np.arange(B))
+    single = np.empty(B)
+    ops_s = np.empty(B, dtype=np.int32)
+    for lo in range(0, B, 50):                       # < 128 chains per call: no lanes
+        hi = min(B, lo + 50)
+        single[lo:hi], ops_s[lo:hi], st = eng.estimate_full(thetas[lo:hi], u[lo:hi], np.arange(B + lo, B + hi))
+        assert np.all(st == 0)
+    assert np.all(st_l == 0)
+    assert np.array_equal(laned, single) and np.array_equal(laned_dev, single)
+    assert np.array_equal(ops_l, ops_s)
+    u2 = rs.normal(size=(B, n, N))
+    c1, _ = eng.estimate_cached(np.arange(B), u2)
+    c2, _ = eng.estimate_cached(np.arange(B, 2 * B), u2)
+    assert np.array_equal(c1, c2)
+    eng.close()
+
+
 def test_device_resident_u_and_slot_roundtrip():
     import torch
     X, y, th = synth.make_dataset(150, 4, seed=9)
