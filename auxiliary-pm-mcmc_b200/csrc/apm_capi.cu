@@ -38,7 +38,7 @@ static void set_err(const std::string& s) { g_err = s; }
         if (r__ != APM_OK) return r__; \
     } while (0)
 
-constexpr int MAX_LANES = 8;
+constexpr int MAX_LANES = 16;
 enum { V_F = 0, V_W, V_WS, V_B, V_A, V_T, V_S, V_FNEW, V_COUNT };
 
 // kernel ids for launch accounting / profiling

@@ -300,6 +300,7 @@ def run_gpu_arm(args):
     drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, 'ess+rdss', batched.make_log_prior(D, True),
                                     [1000 + rank * B + c for c in range(B)], rng='device', device=dev)
     apm_iters = args.apm_iters
+    drv.get_samples(thetas[0], 3)          # warm-up (allocations, first-use initialisation)
     barrier()
     t_apm = time.perf_counter()
     apm_out = drv.get_samples(thetas[0], apm_iters + 1)
@@ -362,8 +363,8 @@ def run_gpu_arm(args):
                             'is 1.28 GB, the blocked left-looking operand traffic with a working set > L2 is 4.7 GB',
             'achieved_per_launch_gflop': flops[dom] / d['launches'] / 1e9,
             'avg_launch_ms': d['ms_total'] / d['launches'],
-            'measured': 'CUDA events around every launch of a second pass of the same %d steps with stream overlap off '
-                        '(%.2f ms/step; the timed `value` pass runs with overlap on and no per-launch events)' % (args.steps, ms_prof / args.steps),
+            'measured': 'CUDA events around every launch of a second pass of the same %d steps, single lane, stream overlap off '
+                        '(%.2f ms/step; the timed `value` pass runs with lanes and overlap on and no per-launch events)' % (args.steps, ms_prof / args.steps),
             'peak_source': 'fp64 DMMA (mma.sync m8n8k4.f64) issue peak measured in this run by apm_measure_fp64_peak; '
                            'MEASURED_PEAKS.json has no fp64 entry (bf16 only). DFMA peak %.1f TFLOP/s. HBM peak %.0f GB/s %s'
                            % (peak_dfma, hbm_peak, hbm_src),
@@ -385,6 +386,7 @@ def run_gpu_arm(args):
             'config': {'workload': '%s; %d chains per GPU per step' % (w['name'], B), 'n': n, 'D': D, 'n_imp': N,
                        'kernel': w['kernel'], 'chains_per_gpu': B, 'parallelism': 'independent chains sharded over %d GPU(s)' % world,
                        'l2_policy': 'inputs larger than L2: u 100.7 MB/step alternating between two buffers, per-chain matrices 1.2 GB each',
+                       'execution': 'apm_estimate_full splits the batch into lanes (up to 8 chain groups on their own host threads and streams); the roofline pass runs single-lane',
                        'newton_iters_mean': iters_total / chains_done, 'failed_chains': bad},
             'e2e': {'value': e2e_val, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(B * n * N * 8 + B * (D + 1) * 8), 'd2h_bytes_per_step': int(B * (8 + 4 + 4))},
@@ -397,7 +399,7 @@ def run_gpu_arm(args):
                                 'method': 'E-SS u + RD-SS theta, lock-step, %d chains/GPU, %d iterations, device RNG' % (B, apm_iters),
                                 'full_estimates_per_iter': float(apm_out['n_full'].mean() - 1) / apm_iters,
                                 'cached_estimates_per_iter': float(apm_out['n_cached'].mean()) / apm_iters,
-                                'failed_chains': int((apm_out['failed'] != 0).sum()), 'timing': 'host wall clock incl. Python scheduler'},
+                                'failed_chains': int((apm_out['failed'] != 0).sum()), 'timing': 'host wall clock incl. the Python scheduler and the drain of the last iterations'},
             'diagnostics_gather': {'collective': 'nccl all_gather' if world > 1 else 'none (1 GPU)',
                                    'chains': int(all_logml.shape[0]), 'mean_logml': float(np.nanmean(all_logml))},
         }
@@ -417,7 +419,7 @@ def main():
     ap.add_argument('--impl', default='apm_b200', choices=['apm_b200', 'reference'])
     ap.add_argument('--chains', type=int, default=0, help='chains per GPU (default 256)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--apm-iters', type=int, default=10, help='iterations of the batched ESS+RDSS sampler leg')
+    ap.add_argument('--apm-iters', type=int, default=30, help='iterations of the batched ESS+RDSS sampler leg (chains drain at the end of a run: short runs understate the steady state)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)

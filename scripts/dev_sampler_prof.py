@@ -1,0 +1,34 @@
+"""Where does a batched ESS+RD-SS iteration spend its time (calls, batch sizes, host overhead)?"""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from apm_b200 import _capi, batched, synth
+n, D, N, B = 768, 8, 64, int(os.environ.get('B', 256))
+method = os.environ.get('METHOD', 'ess+rdss')
+iters = int(os.environ.get('ITERS', 10))
+X, y, th = synth.make_dataset(n, D, seed=0)
+eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N)
+eng.use_torch_stream()
+log = {'full': [], 'cached': []}
+of, oc = eng.estimate_full, eng.estimate_cached
+def tf(*a):
+    torch.cuda.synchronize(); t = time.perf_counter(); r = of(*a); log['full'].append((len(r[0]), time.perf_counter() - t)); return r
+def tc(*a):
+    torch.cuda.synchronize(); t = time.perf_counter(); r = oc(*a); log['cached'].append((len(r[0]), time.perf_counter() - t)); return r
+eng.estimate_full, eng.estimate_cached = tf, tc
+dev = torch.device('cuda', 0)
+drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, method, batched.make_log_prior(D, True),
+                                [1000 + c for c in range(B)], prop_scales=np.full(D + 1, 0.1), rng='device', device=dev,
+                                full_batch_frac=float(os.environ.get('FRAC', 0.8)))
+th0 = synth.bulk_thetas(B, D, seed=1000)
+for rep in range(2):
+    log['full'].clear(); log['cached'].clear()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    out = drv.get_samples(th0, iters + 1)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    tf_, tc_ = sum(t for _, t in log['full']), sum(t for _, t in log['cached'])
+    print('%s B=%d iters=%d: %.3f s -> %.0f chain-iters/s; rounds %d; FULL calls %d (%.3f s) sizes %s; CACHED calls %d (%.3f s) sizes %s; other %.3f s'
+          % (method, B, iters, dt, B * iters / dt, out['rounds'], len(log['full']), tf_, [b for b, _ in log['full']][:40],
+             len(log['cached']), tc_, [b for b, _ in log['cached']][:40], dt - tf_ - tc_), flush=True)
