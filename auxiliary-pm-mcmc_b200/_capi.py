@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libapm_b200.so')
 # every symbol include/apm_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     'apm_version', 'apm_last_error', 'apm_create', 'apm_destroy', 'apm_set_stream', 'apm_synchronize',
-    'apm_set_overlap', 'apm_set_newton', 'apm_get_info', 'apm_kernel_build', 'apm_laplace', 'apm_estimate_full',
+    'apm_set_overlap', 'apm_set_newton', 'apm_get_info', 'apm_kernel_build', 'apm_kernel_grad', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
     'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
 ]
@@ -49,6 +49,7 @@ def lib():
     L.apm_set_newton.argtypes = [vp, ct.c_double, ct.c_int]
     L.apm_get_info.argtypes = [vp] + [ip] * 7
     L.apm_kernel_build.argtypes = [vp, vp, ct.c_int, ct.c_int, ct.c_double, vp, ct.c_int]
+    L.apm_kernel_grad.argtypes = [vp, vp, ct.c_int, ct.c_int, vp, ct.c_int]
     L.apm_laplace.argtypes = [vp, vp, ct.c_int, ct.c_int, ct.c_int, ct.c_int, vp, vp, ct.c_int, vp, vp, vp]
     L.apm_estimate_full.argtypes = [vp, vp, vp, ct.c_int, ct.c_int, ct.c_int, vp, vp, vp, vp]
     L.apm_estimate_cached.argtypes = [vp, vp, vp, ct.c_int, ct.c_int, ct.c_int, vp, vp]
@@ -210,6 +211,18 @@ class Engine(object):
         p, dev, keep = self._bulk(out)
         check(self._L.apm_kernel_build(self._h, _ptr(th), B, -1 if kind is None else int(kind),
                                        -1. if epsilon is None else float(epsilon), p, dev))
+        return out
+
+    def kernel_grad(self, theta, kind=None, out=None):
+        """dK/dtheta_p, (B, n_theta, n, n) -- extension, see include/apm_b200.h:apm_kernel_grad."""
+        k = self.kind if kind is None else kind
+        P = self.D + 1 if k == KERNEL_ARD else 2
+        th = self._theta(theta, P)
+        B = th.shape[0]
+        if out is None:
+            out = np.empty((B, P, self.n, self.n))
+        p, dev, keep = self._bulk(out)
+        check(self._L.apm_kernel_grad(self._h, _ptr(th), B, -1 if kind is None else int(kind), p, dev))
         return out
 
     # -- gpdemo.latent_posterior_approximations

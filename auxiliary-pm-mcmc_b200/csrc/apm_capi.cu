@@ -8,6 +8,7 @@
 // np = n rounded up to 64; padded rows/cols carry the identity so every kernel works on whole tiles.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <sched.h>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -176,6 +177,7 @@ static int set_kernel_attrs() {
     CU_TRY(cudaFuncSetAttribute(k_trsm_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_gemm_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_build_K, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU_TRY(cudaFuncSetAttribute(k_build_dK, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU_TRY(cudaFuncSetAttribute(k_trsv2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU_TRY(cudaFuncSetAttribute(k_is_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     g_attr_done = 1;
@@ -306,7 +308,18 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         return APM_ERR_CUDA;
     }
     // lane views (streams and events of their own; buffers are the root's)
-    c->n_lanes = getenv("APM_LANES") ? atoi(getenv("APM_LANES")) : 8;
+    if (getenv("APM_LANES")) {
+        c->n_lanes = atoi(getenv("APM_LANES"));
+    } else {
+        // default: 8 lanes, but never more host threads than this process's share of the cores (lane threads wait on
+        // their streams; torchrun exports LOCAL_WORLD_SIZE = processes on this node)
+        int cores = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
+        const int procs = getenv("LOCAL_WORLD_SIZE") && atoi(getenv("LOCAL_WORLD_SIZE")) > 0 ? atoi(getenv("LOCAL_WORLD_SIZE")) : 1;
+        c->n_lanes = cores > 0 ? cores / procs : 8;
+        if (c->n_lanes > 8) c->n_lanes = 8;
+    }
     if (c->n_lanes < 1) c->n_lanes = 1;
     if (c->n_lanes > MAX_LANES) c->n_lanes = MAX_LANES;
     if (getenv("APM_LANE_MIN_CHAINS") && atoi(getenv("APM_LANE_MIN_CHAINS")) > 0) c->lane_min_chains = atoi(getenv("APM_LANE_MIN_CHAINS"));
@@ -811,6 +824,47 @@ extern "C" int apm_kernel_build(apm_ctx* c, const double* theta, int B, int kern
     }
     CU_TRY(cudaStreamSynchronize(c->stream));
     return APM_OK;
+}
+
+extern "C" int apm_kernel_grad(apm_ctx* c, const double* theta, int B, int kernel_kind, double* dK_out, int dK_on_device) {
+    APM_TRY(check_B(c, B));
+    if (!theta || !dK_out) return APM_ERR_INVALID;
+    const int kind = kernel_kind < 0 ? c->kind : kernel_kind;
+    const int P = (kind == APM_KERNEL_ARD) ? c->D + 1 : 2;
+    APM_TRY(upload_kernel_params(c, theta, B, kind));
+    const size_t count = (size_t)B * P * c->n * c->n;
+    double* dst = dK_out;
+    if (!dK_on_device) {
+        cudaError_t e = cudaMalloc(&dst, count * sizeof(double));
+        if (e != cudaSuccess) {
+            set_err(std::string("apm_kernel_grad: staging buffer: ") + cudaGetErrorString(e));
+            return APM_ERR_NOMEM;
+        }
+    }
+    KGradParams p;
+    p.X = c->dX; p.n = c->n; p.D = c->D; p.nb = c->nb;
+    p.kp = c->dKp; p.kp_stride = 2 * c->D + 1;
+    p.ard = (kind == APM_KERNEL_ARD); p.P = P;
+    p.dK = dst;
+    const size_t smem = (size_t)(2 * 64 * c->D + 2 * c->D + 1) * sizeof(double);
+    int rc = APM_OK;
+    if (smem > 96 * 1024) {
+        set_err("apm_kernel_grad: feature dimension too large for the shared-memory staging of X");
+        rc = APM_ERR_INVALID;
+    } else {
+        prof_begin(c, KID_BUILD_K);
+        k_build_dK<<<B * c->nb * c->nb, 256, smem, c->stream>>>(p);
+        rc = check_launch(c, "k_build_dK");
+    }
+    cudaError_t e = cudaSuccess;
+    if (rc == APM_OK && !dK_on_device) e = cudaMemcpyAsync(dK_out, dst, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (!dK_on_device) cudaFree(dst);
+    if (rc == APM_OK && e != cudaSuccess) {
+        set_err(std::string("apm_kernel_grad: ") + cudaGetErrorString(e));
+        rc = APM_ERR_CUDA;
+    }
+    return rc;
 }
 
 static int import_matrices(apm_ctx* c, const double* M, int on_device, int B, double* dst, long long dst_bs) {

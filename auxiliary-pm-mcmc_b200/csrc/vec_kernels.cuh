@@ -101,6 +101,66 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
     }
 }
 
+// dK/dtheta_p for p = 0..P-1 (extension named by the north-star; the reference has no gradients -- SURVEY App. D):
+//   ARD:  dK_ij/dtheta_0 = K_ij (off-diagonal), sigma (diagonal);  dK_ij/dtheta_{k+1} = K_ij ((x_ik - x_jk)/tau_k)^2
+//   ISO:  dK_ij/dtheta_0 as above;                                 dK_ij/dtheta_1 = K_ij |x_i - x_j|^2 / tau^2
+// with K_ij computed exactly as k_build_K does.  Output: dense [chain][P][n][n] (ld = n), one 64x64 tile per CTA.
+struct KGradParams {
+    const double* X; int n, D, nb;
+    const double* kp; int kp_stride;
+    int ard; int P;
+    double* dK;                                 // [chain][P][n][n]
+};
+
+__global__ void __launch_bounds__(256) k_build_dK(KGradParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int ntiles = p.nb * p.nb;
+    const int b = blockIdx.x / ntiles;
+    const int ti = (blockIdx.x % ntiles) / p.nb, tj = (blockIdx.x % ntiles) % p.nb;
+    const int D = p.D;
+    double* Xi = smem;                    // [64][D]
+    double* XjT = Xi + 64 * D;            // [D][64]
+    double* prm = XjT + 64 * D;           // [2D+1]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 64 * D; e += 256) {
+        const int r = e / D, k = e % D;
+        Xi[e] = p.X[(size_t)(ti * 64 + r) * D + k];
+        XjT[k * 64 + r] = p.X[(size_t)(tj * 64 + r) * D + k];
+    }
+    const double* kp = p.kp + (size_t)b * p.kp_stride;
+    for (int e = tid; e < 2 * D + 1; e += 256) prm[e] = (p.ard || e < 3) ? kp[e] : 0.0;
+    __syncthreads();
+    const double sigma = prm[0];
+    const int tx = tid & 31, ty = tid >> 5;
+    const size_t n = p.n;
+    double* out = p.dK + (size_t)b * p.P * n * n;
+    for (int rr = 0; rr < 8; rr++) {
+        const int r = ty * 8 + rr, gi = ti * 64 + r;
+        for (int cc = 0; cc < 2; cc++) {
+            const int c = tx * 2 + cc, gj = tj * 64 + c;
+            if (gi >= p.n || gj >= p.n) continue;
+            double acc = 0.0;
+            for (int k = 0; k < D; k++) {
+                const double diff = __dsub_rn(Xi[r * D + k], XjT[k * 64 + c]);
+                const double d = p.ard ? div_by(diff, prm[k + 1], prm[D + 1 + k]) : diff;
+                acc = __dadd_rn(acc, __dmul_rn(d, d));
+            }
+            const double kij = (gi == gj) ? sigma
+                                          : (p.ard ? __dmul_rn(sigma, exp(-acc * 0.5)) : __dmul_rn(sigma, exp(div_by(-acc, prm[1], prm[2]))));
+            out[(size_t)gi * n + gj] = kij;                                        // d/dtheta_0
+            if (p.ard) {
+                for (int k = 0; k < D; k++) {
+                    const double d = div_by(__dsub_rn(Xi[r * D + k], XjT[k * 64 + c]), prm[k + 1], prm[D + 1 + k]);
+                    out[(size_t)(k + 1) * n * n + (size_t)gi * n + gj] = (gi == gj) ? 0.0 : kij * (d * d);
+                }
+            } else {
+                // prm[1] = 2 tau^2:  |x_i - x_j|^2 / tau^2 = 2 acc / (2 tau^2)
+                out[n * n + (size_t)gi * n + gj] = (gi == gj) ? 0.0 : kij * (2.0 * acc * prm[2]);
+            }
+        }
+    }
+}
+
 // u [chain][n][N] (reference layout, estimators.py:155-160) -> uT [chain][Npad][np], zero padded
 __global__ void k_transpose_u(const double* __restrict__ u, long long u_bs, int n, int N, double* __restrict__ uT,
                               long long ut_bs, int np, int Npad) {

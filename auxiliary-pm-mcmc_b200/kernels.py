@@ -63,3 +63,30 @@ def diagonal_squared_exponential_kernel(K, X, theta, epsilon=1e-8):
     """K[i,j] = exp(theta[0]) exp(-1/2 sum_k ((x_ik-x_jk)/exp(theta[k+1]))^2) + epsilon [i==j]
     (gpdemo/kernels.pyx:52-90)."""
     return _build('ard', K, X, theta, epsilon)
+
+
+def _grad(kind, dK, X, theta):
+    theta = np.asarray(theta, dtype=np.float64)
+    X = np.asarray(X, dtype=np.float64)
+    n, D = X.shape
+    n_theta = D + 1 if kind == 'ard' else 2
+    if theta.shape != (n_theta,):
+        raise ValueError('theta must have %d elements for this kernel' % n_theta)
+    if not isinstance(dK, np.ndarray) or dK.shape != (n_theta, n, n) or dK.dtype != np.float64:
+        raise ValueError('dK must be a float64 array of shape (n_theta, n_data, n_data)')
+    eng = _engine_for(X, kind)
+    if dK.flags.c_contiguous:
+        eng.kernel_grad(theta, out=dK.reshape(1, n_theta, n, n))
+    else:
+        dK[...] = eng.kernel_grad(theta)[0]
+    return None
+
+
+def isotropic_squared_exponential_kernel_gradients(dK, X, theta):
+    """EXTENSION (no counterpart in gpdemo/kernels.pyx): dK[p] = dK/dtheta[p] of the isotropic kernel, in place."""
+    return _grad('iso', dK, X, theta)
+
+
+def diagonal_squared_exponential_kernel_gradients(dK, X, theta):
+    """EXTENSION (no counterpart in gpdemo/kernels.pyx): dK[p] = dK/dtheta[p] of the ARD kernel, in place."""
+    return _grad('ard', dK, X, theta)

@@ -92,6 +92,16 @@ int apm_kernel_build(apm_ctx* ctx, const double* theta, int B, int kernel_kind, 
                      double* K_out, int K_on_device);
 
 /*
+ * Gradients of the covariance with respect to the (log-)hyper-parameters, dK/dtheta_p for p = 0..n_theta-1.
+ * EXTENSION: named by the project brief next to the K build; the reference has no gradient code (no
+ * gradient-based update exists in auxpm), so there is no reference interface this replaces.
+ *   ARD: dK_ij/dtheta_0 = K_ij - epsilon [i==j];  dK_ij/dtheta_{k+1} = K_ij ((x_ik - x_jk) / exp(theta_{k+1}))^2
+ *   ISO: dK_ij/dtheta_0 as above;                  dK_ij/dtheta_1 = K_ij |x_i - x_j|^2 / exp(theta_1)^2
+ * theta: HOST [B][n_theta].  dK_out: [B][n_theta][n][n] dense, host (dK_on_device = 0) or device (1).
+ */
+int apm_kernel_grad(apm_ctx* ctx, const double* theta, int B, int kernel_kind, double* dK_out, int dK_on_device);
+
+/*
  * Laplace approximation for caller-supplied covariance matrices -- replaces
  * gpdemo.latent_posterior_approximations.laplace_approximation (lpa.py:22-124).
  * K: [B][n][n] host or device.  Outputs (any may be NULL): f_out HOST [B][n] posterior mode;

@@ -83,6 +83,33 @@ def diagonal_squared_exponential_kernel(K, X, theta, epsilon=1e-8):
     return None
 
 
+def kernel_gradients(X, theta, ard):
+    """dK/dtheta_p, shape (n_theta, n, n).  NO REFERENCE COUNTERPART (the reference has no gradients):
+    this is the analytic derivative of the two builders above, checked against central differences of them in
+    tests/test_oracle_vs_golden.py; it exists only to check the CUDA extension apm_kernel_grad."""
+    X = np.asarray(X, dtype=np.float64)
+    theta = np.asarray(theta, dtype=np.float64)
+    n, D = X.shape
+    sigma = np.exp(theta[0])
+    diff = X[:, None, :] - X[None, :, :]
+    off = 1. - np.eye(n)
+    if ard:
+        d2 = (diff / np.exp(theta[1:]))**2
+        K = sigma * np.exp(-0.5 * d2.sum(-1))
+        out = np.empty((D + 1, n, n))
+        out[0] = K
+        for k in range(D):
+            out[k + 1] = K * d2[:, :, k] * off
+    else:
+        r2 = (diff**2).sum(-1)
+        tau = np.exp(theta[1])
+        K = sigma * np.exp(-r2 / (2. * tau**2))
+        out = np.empty((2, n, n))
+        out[0] = K
+        out[1] = K * r2 / tau**2 * off
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # Laplace approximation  (gpdemo/latent_posterior_approximations.py:22-124)
 # ----------------------------------------------------------------------------------------------

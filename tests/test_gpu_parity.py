@@ -308,6 +308,31 @@ def test_many_blocks_n2048():
     eng.close()
 
 
+def test_kernel_gradients_vs_oracle():
+    """apm_kernel_grad (extension; the reference has no gradients): CUDA vs the numpy restatement, host and
+    device output, ragged n, both kernels, and the drop-in style in-place wrappers."""
+    import torch
+    from apm_b200 import kernels as krn
+    rs = np.random.RandomState(5)
+    for n, D, kind in ((70, 3, 'ard'), (129, 5, 'iso'), (64, 1, 'ard')):
+        X = rs.normal(size=(n, D))
+        P = D + 1 if kind == 'ard' else 2
+        thetas = 0.4 * rs.normal(size=(3, P))
+        eng = _capi.Engine(X, np.ones(n), kernel=kind, max_chains=3, max_nimp=1)
+        g = eng.kernel_grad(thetas)
+        gd = torch.empty(3, P, n, n, dtype=torch.float64, device='cuda')
+        eng.kernel_grad(thetas, out=gd)
+        assert np.array_equal(gd.cpu().numpy(), g)
+        for b in range(3):
+            ref = orc.kernel_gradients(X, thetas[b], kind == 'ard')
+            assert rel_err(g[b], ref) < 1e-14
+        eng.close()
+        dK = np.empty((P, n, n))
+        (krn.diagonal_squared_exponential_kernel_gradients if kind == 'ard'
+         else krn.isotropic_squared_exponential_kernel_gradients)(dK, X, thetas[0])
+        assert np.array_equal(dK, g[0])
+
+
 # ---------------------------------------------------------------------------------------------- full size
 def test_full_size_properties_pima_batch():
     """BASELINE size (n=768, D=8, N=64), a batch of chains: properties that need no oracle run --

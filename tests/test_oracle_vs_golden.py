@@ -87,3 +87,24 @@ def test_utils():
     assert np.array_equal(orc.log_gamma_log_pdf(g['xs'], 1.1, 0.1), g['lg_11_01'])
     assert np.array_equal(orc.log_gamma_log_pdf(g['xs'], 1., 0.3), g['lg_1_03'])
     assert np.array_equal(np.array([orc.adapt_factor_func(b, 20) for b in range(20)]), g['adapt'])
+
+
+def test_oracle_kernel_gradients_vs_central_differences():
+    """The gradient restatement has no reference counterpart (the reference has no gradients): it is pinned to
+    central differences of the golden-pinned kernel builders instead."""
+    rs = np.random.RandomState(0)
+    n, D = 23, 3
+    X = rs.normal(size=(n, D))
+    for ard, theta in ((True, np.array([0.3, 0.2, -0.1, 0.5])), (False, np.array([-0.2, 0.4]))):
+        build = orc.diagonal_squared_exponential_kernel if ard else orc.isotropic_squared_exponential_kernel
+        g = orc.kernel_gradients(X, theta, ard)
+        h = 1e-5
+        for p in range(theta.shape[0]):
+            Kp, Km = np.empty((n, n)), np.empty((n, n))
+            tp, tm = theta.copy(), theta.copy()
+            tp[p] += h
+            tm[p] -= h
+            build(Kp, X, tp, 1e-8)
+            build(Km, X, tm, 1e-8)
+            fd = (Kp - Km) / (2 * h)
+            assert np.max(np.abs(fd - g[p])) < 1e-8 * max(1., np.max(np.abs(g[p])))
