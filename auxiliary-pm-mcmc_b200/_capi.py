@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libapm_b200.so')
 # every symbol include/apm_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     'apm_version', 'apm_last_error', 'apm_create', 'apm_destroy', 'apm_set_stream', 'apm_synchronize',
-    'apm_set_overlap', 'apm_set_newton', 'apm_get_info', 'apm_kernel_build', 'apm_kernel_grad', 'apm_laplace', 'apm_estimate_full',
+    'apm_set_overlap', 'apm_set_newton', 'apm_set_approximation', 'apm_ep', 'apm_get_info', 'apm_kernel_build', 'apm_kernel_grad', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
     'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
 ]
@@ -47,6 +47,8 @@ def lib():
     L.apm_synchronize.argtypes = [vp]
     L.apm_set_overlap.argtypes = [vp, ct.c_int]
     L.apm_set_newton.argtypes = [vp, ct.c_double, ct.c_int]
+    L.apm_set_approximation.argtypes = [vp, ct.c_int, ct.c_double, ct.c_int, ct.c_double]
+    L.apm_ep.argtypes = [vp, vp, ct.c_int, ct.c_int, ct.c_int, vp, vp, ct.c_int, vp, vp, vp, vp]
     L.apm_get_info.argtypes = [vp] + [ip] * 7
     L.apm_kernel_build.argtypes = [vp, vp, ct.c_int, ct.c_int, ct.c_double, vp, ct.c_int]
     L.apm_kernel_grad.argtypes = [vp, vp, ct.c_int, ct.c_int, vp, ct.c_int]
@@ -152,6 +154,11 @@ class Engine(object):
     def set_newton(self, diff_f_tol=1e-4, max_iters=1000):
         check(self._L.apm_set_newton(self._h, float(diff_f_tol), int(max_iters)))
 
+    def set_approximation(self, kind='laplace', ep_tol=1e-6, ep_max_iters=100, ep_damping=1.0):
+        """Posterior approximation of estimate_full: 'laplace' (reference) or 'ep' (extension)."""
+        k = {'laplace': 0, 'ep': 1}[kind]
+        check(self._L.apm_set_approximation(self._h, k, float(ep_tol), int(ep_max_iters), float(ep_damping)))
+
     def profile(self, enable=True):
         check(self._L.apm_profile(self._h, 1 if enable else 0))
 
@@ -241,6 +248,20 @@ class Engine(object):
         check(self._L.apm_laplace(self._h, p, dev, B, int(calc_cov), int(calc_lml), _ptr(f), cp, cdev, _ptr(lml),
                                   _ptr(ops), _ptr(st)))
         return f, C, lml, ops, st
+
+    def ep(self, K, calc_cov=True, C_out=None):
+        """EP posterior approximation (extension): (f, C, nu, tau, ops, status) for K (B, n, n)."""
+        p, dev, keep = self._bulk(K)
+        B = 1 if keep.ndim == 2 else keep.shape[0]
+        f, nu, tau = np.empty((B, self.n)), np.empty((B, self.n)), np.empty((B, self.n))
+        ops = np.empty(B, dtype=np.int32)
+        st = np.empty(B, dtype=np.int32)
+        C, cp, cdev = None, None, 0
+        if calc_cov:
+            C = np.empty((B, self.n, self.n)) if C_out is None else C_out
+            cp, cdev, _ = self._bulk(C)
+        check(self._L.apm_ep(self._h, p, dev, B, int(calc_cov), _ptr(f), cp, cdev, _ptr(nu), _ptr(tau), _ptr(ops), _ptr(st)))
+        return f, C, nu, tau, ops, st
 
     # -- gpdemo.estimators
     def estimate_full(self, theta, u, slots):

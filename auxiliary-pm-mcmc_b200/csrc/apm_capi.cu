@@ -40,7 +40,7 @@ static void set_err(const std::string& s) { g_err = s; }
     } while (0)
 
 constexpr int MAX_LANES = 16;
-enum { V_F = 0, V_W, V_WS, V_B, V_A, V_T, V_S, V_FNEW, V_COUNT };
+enum { V_F = 0, V_W, V_WS, V_B, V_A, V_T, V_S, V_FNEW, V_S2, V_COUNT };
 
 // kernel ids for launch accounting / profiling
 enum { KID_BUILD_K = 0, KID_CHOL, KID_TRSM, KID_SYRK, KID_GEMM_TRI, KID_MATVEC, KID_TRSV, KID_NEWTON_VEC, KID_EPILOGUE,
@@ -67,6 +67,11 @@ struct apm_ctx {
     int maxB = 0, nslots = 0, maxN = 0, maxNpad = 0;
     double tol = 1e-4;
     int max_iters = 1000;
+    // posterior approximation of the FULL estimate: 0 = Laplace (the reference), 1 = EP (extension)
+    int approx = 0;
+    double ep_tol = 1e-6, ep_damping = 1.0;
+    int ep_max_iters = 100;
+    double* dEpDelta = nullptr;
     size_t mat = 0;  // np*np
     double *dX = nullptr, *dy = nullptr;
     double *dK = nullptr, *dLB = nullptr, *dZ = nullptr;
@@ -256,6 +261,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     A(dev_alloc(c, &c->dKp, B * (size_t)(2 * D + 1)));
     A(dev_alloc(c, &c->dOut, B * 2));
     A(dev_alloc(c, &c->dLogw, B * (size_t)max_nimp));
+    A(dev_alloc(c, &c->dEpDelta, B));
     A(dev_alloc(c, &c->dStatus, B));
     A(dev_alloc(c, &c->dActive, B));
     A(dev_alloc(c, &c->dIters, B));
@@ -412,6 +418,17 @@ extern "C" int apm_set_newton(apm_ctx* c, double tol, int max_iters) {
     for (apm_ctx* l : c->lanes) {
         l->tol = tol;
         l->max_iters = max_iters;
+    }
+    return APM_OK;
+}
+extern "C" int apm_set_approximation(apm_ctx* c, int kind, double ep_tol, int ep_max_iters, double ep_damping) {
+    if (!c || (kind != 0 && kind != 1)) return APM_ERR_INVALID;
+    if (kind == 1 && (!(ep_tol > 0) || ep_max_iters <= 0 || !(ep_damping > 0) || ep_damping > 1)) return APM_ERR_INVALID;
+    c->approx = kind;
+    if (kind == 1) {
+        c->ep_tol = ep_tol;
+        c->ep_max_iters = ep_max_iters;
+        c->ep_damping = ep_damping;
     }
     return APM_OK;
 }
@@ -628,6 +645,74 @@ static int run_newton(apm_ctx* c, int B) {
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_finish<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_finish"));
+        CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (c->hNActive[0] <= 0) break;
+    }
+    return APM_OK;
+}
+
+// Z L_B^T = K W^1/2 (lpa.py:111 as a right triangular solve): Z = K W^1/2 L_B^{-T} into dZ, for chains in `active`
+static int run_trsm_z(apm_ctx* c, int B, const int* active) {
+    TrsmParams t;
+    t.R = c->dK; t.r_bs = (long long)c->mat; t.ldr = c->np; t.r_idx = nullptr;
+    t.cs = c->dVec[V_WS]; t.cs_bs = c->np;
+    t.X = c->dZ; t.x_bs = (long long)c->mat; t.ldx = c->np;
+    t.L = c->dLB; t.l_bs = (long long)c->mat; t.ldl = c->np; t.l_idx = nullptr;
+    t.nb = c->nb; t.row_blocks = c->nb;
+    t.status = c->dStatus; t.active = active;
+    prof_begin(c, KID_TRSM);
+    k_trsm_rows<<<B * c->nb, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
+    return check_launch(c, "k_trsm_rows");
+}
+
+// Parallel EP (extension; the ep_approximation restatement under oracle/) for chains 0..B-1 whose K sits in c->dK.  On exit
+// f (V_F) = posterior mean, Ws = sqrt(tau~), bvec = nu~, LB / Z those of each chain's last iteration, dIters the
+// iteration counts.  Per iteration: site update (O(n)), then Sigma and mu from scratch exactly as the Newton step does
+// its solve (B = I + S^1/2 K S^1/2, a = nu~ - S^1/2 B^-1 S^1/2 K nu~, mu = K a) plus diag(Sigma) from Z.
+static int run_ep(apm_ctx* c, int B) {
+    NewtonVecs nv = make_nv(c);
+    nv.tol = c->ep_tol;
+    nv.max_iters = c->ep_max_iters;
+    EpVecs ev;
+    ev.s2 = c->dVec[V_S2]; ev.delta = c->dEpDelta; ev.damping = c->ep_damping;
+    CU_TRY(cudaMemsetAsync(nv.f, 0, sizeof(double) * (size_t)B * c->np, c->stream));
+    CU_TRY(cudaMemsetAsync(nv.W, 0, sizeof(double) * (size_t)B * c->np, c->stream));
+    CU_TRY(cudaMemsetAsync(nv.bvec, 0, sizeof(double) * (size_t)B * c->np, c->stream));
+    CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
+    prof_begin(c, KID_MISC);
+    k_fill_int<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dActive, 1, B);
+    APM_TRY(check_launch(c, "k_fill_int"));
+    prof_begin(c, KID_MISC);
+    k_fill_int<<<1, 32, 0, c->stream>>>(c->dNActive, B, 1);
+    APM_TRY(check_launch(c, "k_fill_int"));
+    prof_begin(c, KID_NEWTON_VEC);
+    k_ep_init<<<B, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, nv, ev);
+    APM_TRY(check_launch(c, "k_ep_init"));
+    const size_t trsv_smem = (size_t)(c->np + 64 + 8 * 64) * sizeof(double);
+    if (trsv_smem > 160 * 1024) {
+        set_err("run_ep: n too large for the single-CTA triangular solve");
+        return APM_ERR_INVALID;
+    }
+    for (int it = 0; it < c->ep_max_iters; it++) {
+        prof_begin(c, KID_NEWTON_VEC);
+        k_ep_sites<<<B, 256, 0, c->stream>>>(nv, ev);
+        APM_TRY(check_launch(c, "k_ep_sites"));
+        APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t));                           // t = S^1/2 K nu~
+        APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
+                         nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB));
+        prof_begin(c, KID_TRSV);
+        k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                  (long long)c->nb * TB * TB, nv);   // a = nu~ - S^1/2 B^-1 t
+        APM_TRY(check_launch(c, "k_trsv2"));
+        APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew));                         // mu = K a
+        APM_TRY(run_trsm_z(c, B, c->dActive));
+        prof_begin(c, KID_NEWTON_VEC);
+        k_ep_diag_sigma<<<dim3(c->np / 32, B), 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->dZ, (long long)c->mat, c->np, nv, ev);
+        APM_TRY(check_launch(c, "k_ep_diag_sigma"));
+        prof_begin(c, KID_NEWTON_VEC);
+        k_ep_finish<<<B, 256, 0, c->stream>>>(nv, ev);
+        APM_TRY(check_launch(c, "k_ep_finish"));
         CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
         if (c->hNActive[0] <= 0) break;
@@ -916,6 +1001,42 @@ extern "C" int apm_laplace(apm_ctx* c, const double* K, int K_on_device, int B, 
     return fetch_results(c, B, c->dOut, 1, calc_lml ? lml_out : nullptr, cubic_ops_out, calc_cov ? 1 : 0, chain_status);
 }
 
+extern "C" int apm_ep(apm_ctx* c, const double* K, int K_on_device, int B, int calc_cov, double* f_out, double* C_out,
+                      int C_on_device, double* nu_out, double* tau_out, int* cubic_ops_out, int* chain_status) {
+    APM_TRY(check_B(c, B));
+    if (!K) return APM_ERR_INVALID;
+    APM_TRY(reset_status(c, B));
+    APM_TRY(import_matrices(c, K, K_on_device, B, c->dK, (long long)c->mat));
+    APM_TRY(run_ep(c, B));
+    NewtonVecs nv = make_nv(c);
+    if (calc_cov && C_out) {
+        // Sigma = K - Z Z^T with the Z of each chain's last iteration (lower tiles -> LB buffer, dense symmetric export)
+        SyrkParams s;
+        s.S = c->dK; s.s_bs = (long long)c->mat; s.lds = c->np;
+        s.Z = c->dZ; s.z_bs = (long long)c->mat; s.ldz = c->np;
+        s.C = c->dLB; s.c_bs = (long long)c->mat; s.ldc = c->np; s.c_idx = nullptr;
+        s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
+        s.status = c->dStatus;
+        prof_begin(c, KID_SYRK);
+        k_syrk_sub<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
+        APM_TRY(check_launch(c, "k_syrk_sub"));
+        const size_t n = c->n;
+        for (int b = 0; b < B; b++) {
+            dim3 grid((c->n + 255) / 256, c->n);
+            prof_begin(c, KID_MISC);
+            k_export_lower<<<grid, 256, 0, c->stream>>>(c->dLB + (size_t)b * c->mat, c->np, c->n, c->dZ + (size_t)b * c->mat, 1);
+            APM_TRY(check_launch(c, "k_export_lower"));
+            CU_TRY(cudaMemcpyAsync(C_out + (size_t)b * n * n, c->dZ + (size_t)b * c->mat, sizeof(double) * n * n,
+                                   C_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    const size_t row = (size_t)c->n * sizeof(double), pitch = (size_t)c->np * sizeof(double);
+    if (f_out) CU_TRY(cudaMemcpy2DAsync(f_out, row, nv.f, pitch, row, B, cudaMemcpyDeviceToHost, c->stream));
+    if (nu_out) CU_TRY(cudaMemcpy2DAsync(nu_out, row, nv.bvec, pitch, row, B, cudaMemcpyDeviceToHost, c->stream));
+    if (tau_out) CU_TRY(cudaMemcpy2DAsync(tau_out, row, nv.W, pitch, row, B, cudaMemcpyDeviceToHost, c->stream));
+    return fetch_results(c, B, c->dOut, 1, nullptr, cubic_ops_out, calc_cov ? 1 : 0, chain_status);
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI: estimators
 // ------------------------------------------------------------------------------------------------
@@ -958,6 +1079,8 @@ static void lane_bind(apm_ctx* v, int lane, int off, int cnt, int N) {
     v->dKp = r->dKp + o * (2 * r->D + 1);
     v->dOut = r->dOut + o * 2;
     v->dLogw = r->dLogw + o * N;
+    v->dEpDelta = r->dEpDelta + o;
+    v->approx = r->approx; v->ep_tol = r->ep_tol; v->ep_damping = r->ep_damping; v->ep_max_iters = r->ep_max_iters;
     v->dStatus = r->dStatus + o; v->dActive = r->dActive + o; v->dIters = r->dIters + o;
     v->dSlotsA = r->dSlotsA + o; v->dSlotsB = r->dSlotsB + o;
     v->dFlowSkip = r->dFlowSkip + o; v->dFlowProgress = r->dFlowProgress + o * nb;
@@ -1023,7 +1146,8 @@ static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, 
     const bool overlap = c->overlap_chol_k;
     APM_TRY(full_front(c, theta, B, slots, overlap));
     APM_TRY(stage_u(c, u, u_on_device, N, B));
-    APM_TRY(run_newton(c, B));                                                  // estimators.py:207 -> lpa.py:81-102
+    if (c->approx == 1) APM_TRY(run_ep(c, B));                                  // extension: EP behind post_approx_func
+    else APM_TRY(run_newton(c, B));                                             // estimators.py:207 -> lpa.py:81-102
     if (c->factored_cov) {
         // chol(C) = L_K U^-T straight from chol(K) and W (lpa.py:111-112 + estimators.py:209 without forming C)
         if (overlap) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));

@@ -1,6 +1,7 @@
 // vec_kernels.cuh -- the HBM-bound part of the path: K(theta) build, Newton vector updates, matvecs,
 // single right-hand-side triangular solves, the importance-sampling epilogue, layout helpers.
 #pragma once
+#include <math_constants.h>
 #include "common.cuh"
 
 namespace apm {
@@ -478,6 +479,116 @@ __global__ void __launch_bounds__(256) k_newton_finish(NewtonVecs nv) {
         } else if (it >= nv.max_iters) {
             nv.status[b] = 2;
             still = false;
+        }
+        if (!still) {
+            nv.active[b] = 0;
+            atomicSub(nv.n_active, 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Expectation propagation for the probit likelihood (EXTENSION: the reference has no EP -- SURVEY App. D; the
+// algorithm is Rasmussen & Williams, GPML, Alg. 3.5 with all sites updated from the same (mu, diag Sigma) before the
+// posterior is recomputed -- "parallel EP" -- restated in the ep_approximation restatement under oracle/).
+// Vector roles while EP runs (NewtonVecs): f = mu, W = tau~, Ws = sqrt(tau~), bvec = nu~, fnew = mu of the new sites.
+// ------------------------------------------------------------------------------------------------
+struct EpVecs {
+    double* s2;        // diag(Sigma) [chain][np]
+    double* delta;     // max |site change| of the last update, per chain
+    double damping;
+};
+
+// s2 <- diag(K)
+__global__ void k_ep_init(const double* __restrict__ K, long long k_bs, int ld, NewtonVecs nv, EpVecs ev) {
+    const int b = blockIdx.x;
+    const long long o = (long long)b * nv.vs;
+    for (int i = threadIdx.x; i < nv.np; i += blockDim.x) ev.s2[o + i] = K[(long long)b * k_bs + (size_t)i * ld + i];
+}
+
+// cavity, probit moments, damped site update for every i at once (GPML eqs. 3.56, 3.58, 3.59)
+__global__ void __launch_bounds__(256) k_ep_sites(NewtonVecs nv, EpVecs ev) {
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    if (!nv.active[b] || nv.status[b] != 0) return;
+    const long long o = (long long)b * nv.vs;
+    double dmax = 0.0;
+    for (int i = threadIdx.x; i < nv.np; i += 256) {
+        double tau_n = 0.0, nu_n = 0.0;
+        if (i < nv.n) {
+            const double y = nv.y[i], mu = nv.f[o + i], s2 = ev.s2[o + i], tau = nv.W[o + i], nu = nv.bvec[o + i];
+            const double tau_c = 1.0 / s2 - tau, nu_c = mu / s2 - nu;
+            const double mu_c = nu_c / tau_c, s2_c = 1.0 / tau_c;
+            const double den = sqrt(1.0 + s2_c);
+            const double z = y * mu_c / den;
+            const double r = exp(-0.5 * z * z - log_ndtr(z) - HALF_LOG_2PI);
+            const double mu_h = mu_c + y * s2_c * r / den;
+            const double s2_h = s2_c - s2_c * s2_c * r * (z + r) / (1.0 + s2_c);
+            tau_n = tau + ev.damping * ((1.0 / s2_h - tau_c) - tau);
+            nu_n = nu + ev.damping * ((mu_h / s2_h - nu_c) - nu);
+            tau_n = fmax(tau_n, 0.0);
+            const double d = fmax(fabs(tau_n - tau), fabs(nu_n - nu));
+            dmax = (d == d) ? fmax(dmax, d) : CUDART_INF;   // NaN -> inf (reported as non-finite by k_ep_finish)
+        }
+        nv.W[o + i] = tau_n;
+        nv.Ws[o + i] = sqrt(tau_n);
+        nv.bvec[o + i] = nu_n;
+    }
+    dmax = warp_max(dmax);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < 8; w++) m = fmax(m, red[w]);
+        ev.delta[b] = m;
+    }
+}
+
+// s2_i = K_ii - sum_j Z_ij^2 with Z = K S^1/2 L_B^{-T} (diag of Sigma = K - Z Z^T); warp per row; grid (np/32, chains)
+__global__ void __launch_bounds__(256) k_ep_diag_sigma(const double* __restrict__ K, long long k_bs, const double* __restrict__ Z,
+                                                       long long z_bs, int ld, NewtonVecs nv, EpVecs ev) {
+    const int b = blockIdx.y;
+    if (!nv.active[b] || nv.status[b] != 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int r = blockIdx.x * 32 + warp * 4 + rr;
+        const double* row = Z + (long long)b * z_bs + (size_t)r * ld;
+        double acc = 0.0;
+        for (int j = lane * 2; j < nv.np; j += 64) {
+            const double2 m = *reinterpret_cast<const double2*>(row + j);
+            acc = fma(m.x, m.x, acc);
+            acc = fma(m.y, m.y, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) ev.s2[(long long)b * nv.vs + r] = K[(long long)b * k_bs + (size_t)r * ld + r] - acc;
+    }
+}
+
+// mu <- mu_new; iteration bookkeeping; a chain is done when the largest site change fell below tol
+__global__ void k_ep_finish(NewtonVecs nv, EpVecs ev) {
+    const int b = blockIdx.x;
+    if (!nv.active[b]) return;
+    const long long o = (long long)b * nv.vs;
+    if (nv.status[b] == 0)
+        for (int i = threadIdx.x; i < nv.np; i += blockDim.x) nv.f[o + i] = nv.fnew[o + i];
+    if (threadIdx.x == 0) {
+        bool still = true;
+        if (nv.status[b] != 0) {
+            still = false;
+        } else {
+            const double d = ev.delta[b];
+            const int it = nv.iters[b] + 1;
+            nv.iters[b] = it;
+            if (!(d == d) || isinf(d)) {
+                nv.status[b] = 4;
+                still = false;
+            } else if (d < nv.tol) {
+                still = false;
+            } else if (it >= nv.max_iters) {
+                nv.status[b] = 2;
+                still = false;
+            }
         }
         if (!still) {
             nv.active[b] = 0;

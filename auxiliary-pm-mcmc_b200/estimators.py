@@ -151,18 +151,21 @@ class LogMarginalLikelihoodApproxPosteriorISEstimator(_DeviceEstimatorBase):
         self.post_approx_func = post_approx_func
 
     def _newton_settings(self):
-        """(tol, max_iters) if post_approx_func is our Laplace approximation, else None."""
+        """('laplace', tol, max_iters) / ('ep', tol, max_iters, damping) if post_approx_func is one of our
+        approximations (possibly bound with functools.partial), else None."""
         f = self.post_approx_func
         kw = {}
         if isinstance(f, functools.partial):
             if f.args:
                 return None
             kw, f = dict(f.keywords or {}), f.func
-        if f is not _lpa.laplace_approximation:
-            return None
         if kw.get('calc_cov', True) is not True or kw.get('calc_lml', False):
             return None
-        return kw.get('diff_f_tol', 1e-4), kw.get('max_iters', 1000)
+        if f is _lpa.laplace_approximation:
+            return 'laplace', kw.get('diff_f_tol', 1e-4), kw.get('max_iters', 1000)
+        if f is _lpa.ep_approximation:
+            return 'ep', kw.get('tol', 1e-6), kw.get('max_iters', 100), kw.get('damping', 1.0)
+        return None
 
     def _full(self, ns, theta):
         N = ns.shape[1]
@@ -171,7 +174,11 @@ class LogMarginalLikelihoodApproxPosteriorISEstimator(_DeviceEstimatorBase):
         if call is not None and newton is not None:
             kind, th, eps, _ = call
             eng = self._get_engine(kind, eps, N)
-            eng.set_newton(*newton)
+            if newton[0] == 'ep':
+                eng.set_approximation('ep', *newton[1:])
+            else:
+                eng.set_approximation('laplace')
+                eng.set_newton(*newton[1:])
             slot = self._take_slot()
             try:
                 out, ops, st = eng.estimate_full(th, ns, [slot])

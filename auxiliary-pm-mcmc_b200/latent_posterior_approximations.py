@@ -60,3 +60,27 @@ def laplace_approximation(K, y, calc_cov=True, calc_lml=False, diff_f_tol=1e-4, 
         out.append(float(lml[0]))
     out.append(int(ops[0]))
     return tuple(out)
+
+
+def ep_approximation(K, y, calc_cov=True, tol=1e-6, max_iters=100, damping=1.0):
+    """EXTENSION (the reference has only laplace_approximation): expectation-propagation approximation to
+    p(f | y, theta) for the probit likelihood, usable wherever the reference takes a
+    `post_approx_func(K, y) -> (f_post, C, cubic_ops)` (estimators.py:126-139).  GPML Alg. 3.5 with all sites updated
+    per sweep, on the GPU (run_ep in csrc/apm_capi.cu; CPU restatement: the ep_approximation restatement under oracle/).
+
+    Returns (f, C, ops) or (f, ops) without calc_cov; ops = EP iterations (+1 with calc_cov).  Raises
+    MaximumIterationsExceededError like the Laplace approximation does."""
+    K = np.asarray(K, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if not np.isfinite(K).all():
+        raise ValueError('array must not contain infs or NaNs')
+    eng = _engine_for(y)
+    eng.set_approximation('ep', tol, max_iters, damping)
+    try:
+        f, C, nu, tau, ops, st = eng.ep(K, calc_cov=calc_cov)
+    finally:
+        eng.set_approximation('laplace')
+    raise_for_status(int(st[0]), int(ops[0]))
+    if calc_cov:
+        return f[0], C[0], int(ops[0])
+    return f[0], int(ops[0])

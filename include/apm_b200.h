@@ -78,6 +78,18 @@ int apm_set_overlap(apm_ctx* ctx, int enable);
 /* Laplace/Newton controls, defaults as lpa.py:22-23: diff_f_tol = 1e-4, max_iters = 1000. */
 int apm_set_newton(apm_ctx* ctx, double diff_f_tol, int max_iters);
 
+/*
+ * Posterior approximation used by apm_estimate_full: kind 0 = Laplace (the reference's
+ * gpdemo.latent_posterior_approximations.laplace_approximation, the default), kind 1 = expectation propagation.
+ * EP is an EXTENSION: the project brief names it, the reference does not contain it, so it
+ * plugs in where the reference would take it -- the post_approx_func(K, y) -> (f_post, C, cubic_ops) argument of
+ * LogMarginalLikelihoodApproxPosteriorISEstimator (gpdemo/estimators.py:126-139).  Algorithm: GPML Alg. 3.5 with
+ * all sites updated per sweep ("parallel EP"), stopped when the largest change of a site parameter is < ep_tol;
+ * ep_damping in (0, 1]; the CPU restatement it is checked against is oracle/apm_oracle.py:ep_approximation.
+ * The ep_* arguments are ignored for kind 0.
+ */
+int apm_set_approximation(apm_ctx* ctx, int kind, double ep_tol, int ep_max_iters, double ep_damping);
+
 /* Problem geometry: n, D, padded n, number of theta components, slots, max chains. */
 int apm_get_info(apm_ctx* ctx, int* n, int* D, int* n_pad, int* n_theta, int* n_slots,
                  int* max_chains, int* max_nimp);
@@ -112,6 +124,15 @@ int apm_kernel_grad(apm_ctx* ctx, const double* theta, int B, int kernel_kind, d
 int apm_laplace(apm_ctx* ctx, const double* K, int K_on_device, int B, int calc_cov, int calc_lml,
                 double* f_out, double* C_out, int C_on_device, double* lml_out, int* cubic_ops_out,
                 int* chain_status);
+
+/*
+ * EP posterior approximation for given covariance matrices (extension, see apm_set_approximation; uses the
+ * context's ep_tol / ep_max_iters / ep_damping).  K: [B][n][n]; f_out HOST [B][n] posterior mean; C_out [B][n][n]
+ * posterior covariance (if calc_cov); nu_out / tau_out HOST [B][n] site parameters (may be NULL);
+ * cubic_ops_out = EP iterations (+1 with calc_cov); chain_status as apm_laplace (2 = iteration limit).
+ */
+int apm_ep(apm_ctx* ctx, const double* K, int K_on_device, int B, int calc_cov, double* f_out, double* C_out,
+           int C_on_device, double* nu_out, double* tau_out, int* cubic_ops_out, int* chain_status);
 
 /*
  * FULL importance-sampling estimate -- replaces

@@ -83,6 +83,88 @@ def diagonal_squared_exponential_kernel(K, X, theta, epsilon=1e-8):
     return None
 
 
+# ----------------------------------------------------------------------------------------------
+# Expectation propagation -- NO REFERENCE COUNTERPART (the project brief names EP, the reference has only the Laplace
+# approximation: SURVEY.md App. D).  Two restatements of Rasmussen & Williams, GPML (2006), Alg. 3.5 for the probit
+# likelihood: the textbook sequential sweep (rank-one updates of Sigma) and the variant the CUDA path runs, in which
+# all sites are updated from the same (mu, diag Sigma) before Sigma and mu are recomputed ("parallel EP").  Both stop
+# at the same fixed point; tests/test_oracle_vs_golden.py pins the parallel one to the textbook one.
+# ----------------------------------------------------------------------------------------------
+
+def _probit_moments(y, mu_c, s2_c):
+    """Mean and variance of the tilted distribution Phi(y f) N(f | mu_c, s2_c)  (GPML eq. 3.58)."""
+    den = np.sqrt(1. + s2_c)
+    z = y * mu_c / den
+    r = np.exp(-0.5 * z * z - log_ndtr(z) - HALF_LOG_2PI)          # N(z) / Phi(z)
+    mu_h = mu_c + y * s2_c * r / den
+    s2_h = s2_c - s2_c * s2_c * r * (z + r) / (1. + s2_c)
+    return mu_h, s2_h
+
+
+def _ep_posterior(K, nu, tau):
+    """Sigma = K - K S^1/2 B^-1 S^1/2 K, mu = Sigma nu~ (GPML eqs. 3.53, 3.68) in the arithmetic the CUDA path uses:
+    a = nu~ - S^1/2 B^-1 (S^1/2 K nu~), mu = K a; Z = K S^1/2 L^-T, diag(Sigma) = diag(K) - rowsum(Z^2)."""
+    n = K.shape[0]
+    Ss = np.sqrt(tau)
+    B = np.eye(n) + (Ss[:, None] * K) * Ss[None, :]
+    L = la.cholesky(B, lower=True)
+    t = Ss * K.dot(nu)
+    a = nu - Ss * la.cho_solve((L, True), t)
+    mu = K.dot(a)
+    Z = la.solve_triangular(L, Ss[:, None] * K, lower=True).T       # Z = K S^1/2 L^-T
+    return mu, Z
+
+
+def ep_approximation(K, y, calc_cov=True, tol=1e-6, max_iters=100, damping=1.0):
+    """Parallel EP.  Returns (f_post, C, n_cubic_ops) like post_approx_func (estimators.py:126-139), or (f_post, ops)
+    without calc_cov; ops = iterations (+1 with calc_cov).  Raises after max_iters like lpa.py:100-102."""
+    n = y.shape[0]
+    nu, tau, mu, s2 = np.zeros(n), np.zeros(n), np.zeros(n), np.diag(K).copy()
+    it, done = 0, False
+    Z = None
+    while not done and it < max_iters:
+        tau_c = 1. / s2 - tau
+        nu_c = mu / s2 - nu
+        mu_h, s2_h = _probit_moments(y, nu_c / tau_c, 1. / tau_c)
+        tau_n = np.maximum(tau + damping * ((1. / s2_h - tau_c) - tau), 0.)
+        nu_n = nu + damping * ((mu_h / s2_h - nu_c) - nu)
+        delta = max(np.max(np.abs(tau_n - tau)), np.max(np.abs(nu_n - nu)))
+        tau, nu = tau_n, nu_n
+        mu, Z = _ep_posterior(K, nu, tau)
+        s2 = np.diag(K) - (Z * Z).sum(1)
+        it += 1
+        done = delta < tol
+    if not done:
+        raise MaximumIterationsExceededError('Failed to converge in {0} iterations'.format(it))
+    if calc_cov:
+        return mu, K - Z.dot(Z.T), it + 1
+    return mu, it
+
+
+def ep_sequential_textbook(K, y, tol=1e-8, max_sweeps=100):
+    """GPML Alg. 3.5 as printed: sites visited in order with rank-one updates of Sigma, Sigma and mu recomputed from
+    the Cholesky factor of B after every sweep.  O(n^3) per sweep in Python loops: small n only."""
+    n = y.shape[0]
+    nu, tau, mu, Sigma = np.zeros(n), np.zeros(n), np.zeros(n), K.copy()
+    for sweep in range(max_sweeps):
+        nu_old, tau_old = nu.copy(), tau.copy()
+        for i in range(n):
+            tau_c = 1. / Sigma[i, i] - tau[i]
+            nu_c = mu[i] / Sigma[i, i] - nu[i]
+            mu_h, s2_h = _probit_moments(y[i], nu_c / tau_c, 1. / tau_c)
+            dt = 1. / s2_h - tau_c - tau[i]
+            tau[i] += dt
+            nu[i] = mu_h / s2_h - nu_c
+            si = Sigma[:, i].copy()
+            Sigma -= (dt / (1. + dt * si[i])) * np.outer(si, si)
+            mu = Sigma.dot(nu)
+        mu, Z = _ep_posterior(K, nu, tau)
+        Sigma = K - Z.dot(Z.T)
+        if max(np.max(np.abs(tau - tau_old)), np.max(np.abs(nu - nu_old))) < tol:
+            return mu, Sigma, sweep + 1
+    raise MaximumIterationsExceededError('Failed to converge in {0} sweeps'.format(max_sweeps))
+
+
 def kernel_gradients(X, theta, ard):
     """dK/dtheta_p, shape (n_theta, n, n).  NO REFERENCE COUNTERPART (the reference has no gradients):
     this is the analytic derivative of the two builders above, checked against central differences of them in

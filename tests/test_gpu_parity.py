@@ -308,6 +308,55 @@ def test_many_blocks_n2048():
     eng.close()
 
 
+def test_ep_approximation_vs_oracle():
+    """EP (extension; the reference has no EP): the CUDA parallel-EP loop against its numpy restatement -- same
+    iteration count, posterior mean / covariance / site parameters to 1e-9 -- standalone and inside the IS estimator
+    (post_approx_func plug point, estimators.py:126-139), including a ragged n and lanes."""
+    from apm_b200 import estimators as est, kernels as krn, latent_posterior_approximations as lpa
+    for n, D in ((150, 3), (257, 4)):
+        X, y, th = synth.make_dataset(n, D, seed=21)
+        rs = np.random.RandomState(6)
+        thetas = th[None] + 0.3 * rs.normal(size=(3, D + 1))
+        eng = _capi.Engine(X, y, kernel='ard', max_chains=3, max_nimp=8)
+        K = eng.kernel_build(thetas)
+        eng.set_approximation('ep', 1e-7, 100, 1.0)
+        f, C, nu, tau, ops, st = eng.ep(K)
+        assert np.all(st == 0)
+        for b in range(3):
+            mu_r, C_r, ops_r = orc.ep_approximation(K[b], y, tol=1e-7)
+            assert ops[b] == ops_r
+            assert rel_err(f[b], mu_r) < 1e-9 and rel_err(C[b], C_r) < 1e-9
+        # fused estimate with EP, against the oracle estimator with the oracle EP plugged in
+        u = rs.normal(size=(3, n, 8))
+        full, ops_f, st = eng.estimate_full(thetas, u, [0, 1, 2])
+        cached, _ = eng.estimate_cached([0, 1, 2], u)
+        assert np.all(st == 0) and np.array_equal(full, cached)
+        import functools
+        oest = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(
+            X, y, oracle_kernel('ard', 1e-8), functools.partial(orc.ep_approximation, tol=1e-7))
+        for b in range(3):
+            ref, _ = oest(u[b], thetas[b])
+            tol = max(1e-9, 2e-15 * np.linalg.cond(K[b]))      # the oracle's own answer moves by ~cond(K) eps
+            assert abs(full[b] - ref) < tol * abs(ref), (full[b], ref, tol)
+        assert ops_f[0] + ops_f[1] + ops_f[2] == oest.n_cubic_ops
+        eng.close()
+    # drop-in layer: ep_approximation as post_approx_func of the estimator class, and standalone
+    X, y, th = synth.make_dataset(90, 2, seed=2)
+    e = est.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, krn.diagonal_squared_exponential_kernel, lpa.ep_approximation)
+    o = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, oracle_kernel('ard', 1e-8), orc.ep_approximation)
+    u = np.random.RandomState(0).normal(size=(90, 4))
+    v, cache = e(u, th)
+    r, _ = o(u, th)
+    K = np.empty((90, 90))
+    krn.diagonal_squared_exponential_kernel(K, X, th)
+    assert abs(v - r) < max(1e-9, 2e-15 * np.linalg.cond(K)) * abs(r) and e.n_cubic_ops == o.n_cubic_ops
+    f, C, ops = lpa.ep_approximation(K, y)
+    f_r, C_r, ops_r = orc.ep_approximation(K, y)
+    assert ops == ops_r and rel_err(f, f_r) < 1e-9 and rel_err(C, C_r) < 1e-9
+    with pytest.raises(lpa.MaximumIterationsExceededError):
+        lpa.ep_approximation(K, y, max_iters=2)
+
+
 def test_kernel_gradients_vs_oracle():
     """apm_kernel_grad (extension; the reference has no gradients): CUDA vs the numpy restatement, host and
     device output, ragged n, both kernels, and the drop-in style in-place wrappers."""

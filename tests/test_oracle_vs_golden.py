@@ -108,3 +108,20 @@ def test_oracle_kernel_gradients_vs_central_differences():
             build(Km, X, tm, 1e-8)
             fd = (Kp - Km) / (2 * h)
             assert np.max(np.abs(fd - g[p])) < 1e-8 * max(1., np.max(np.abs(g[p])))
+
+
+def test_oracle_parallel_ep_matches_textbook_sequential_ep():
+    """EP has no reference counterpart: the parallel-EP restatement (what the CUDA path runs) is pinned to the
+    textbook sequential sweep of GPML Alg. 3.5 -- same fixed point."""
+    from apm_b200 import synth
+    for n, D, shift in ((60, 2, 0.), (90, 3, 0.4)):
+        X, y, th = synth.make_dataset(n, D, seed=4)
+        K = np.empty((n, n))
+        orc.diagonal_squared_exponential_kernel(K, X, th + shift, 1e-8)
+        mu_p, C_p, ops = orc.ep_approximation(K, y, tol=1e-10)
+        mu_s, C_s, sweeps = orc.ep_sequential_textbook(K, y, tol=1e-10)
+        assert np.max(np.abs(mu_p - mu_s)) < 1e-8 and np.max(np.abs(C_p - C_s)) < 1e-8
+        assert 3 <= ops <= 40
+        # EP matches the first two moments better than Laplace: its mean differs from the Laplace mode
+        f_l = orc.laplace_approximation(K, y, calc_cov=False)[0]
+        assert np.max(np.abs(f_l - mu_p)) > 1e-3
