@@ -3,11 +3,12 @@
 estimates).  One JSON line per configuration; chains are independent, so the N-GPU figure of a sharded configuration
 is N x the per-GPU figure at the per-GPU chain count used here (bench.py --gpus N measures that scaling).
 
-    python scripts/bench_configs.py [breast] [nimp] [pmmh] [large]
+    python scripts/bench_configs.py [breast] [nimp] [ep] [pmmh] [large]
 
   breast  config 2: breast-shaped synthetic (n=682, D=9), Laplace IS N_imp=64, E-SS-u + RD-SS-theta, 256 lock-step chains
   nimp    config 3: pima-shaped, N_imp sweep 1..1024 with the Laplace approximation (the reference has no EP: SURVEY App. D),
           256 chains per GPU (= 1024 chains over 4 GPUs)
+  ep      config 3 as named: the same workload at N_imp=64 with the EP approximation (extension)
   pmmh    config 4: pseudo-marginal MH (fresh u inside every estimate), 512 chains per GPU (= 4096 chains over 8 GPUs)
   large   config 5: n=8192, D=16 ARD, E-SS-u + RD-SS-theta, 8 chains per GPU
 """
@@ -102,6 +103,20 @@ def run_nimp():
          'FULL log-ML estimates/s at N_imp=64', sweep['64']['full_estimates_per_s'], 'estimates/s', {'n_imp_sweep': sweep})
 
 
+def run_ep():
+    n, D, N, B = 768, 8, 64, 256
+    X, y, _ = synth.make_dataset(n, D, seed=0)
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N)
+    eng.use_torch_stream()
+    eng.set_approximation('ep', 1e-6, 100, 1.0)
+    full, cached, iters, bad = estimator_rates(eng, n, D, N, B, reps=3)
+    line('config 3 (EP extension)', 'pima-shaped synthetic (n=768, D=8), EP posterior approximation (extension: not in the reference; '
+         'checked against the parallel-EP restatement in oracle/), IS N_imp=64, 256 chains per GPU',
+         'FULL log-ML estimates/s with the EP approximation', full, 'estimates/s',
+         {'cached_estimates_per_s': cached, 'ep_iters_mean': iters, 'failed_chains': bad, 'ep_tol': 1e-6, 'ep_damping': 1.0})
+    eng.close()
+
+
 def run_pmmh():
     n, D, N, B = 768, 8, 64, 512
     X, y, _ = synth.make_dataset(n, D, seed=0)
@@ -130,6 +145,6 @@ def run_large():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['breast', 'nimp', 'pmmh', 'large']
+    which = sys.argv[1:] or ['breast', 'nimp', 'ep', 'pmmh', 'large']
     for w in which:
-        {'breast': run_breast, 'nimp': run_nimp, 'pmmh': run_pmmh, 'large': run_large}[w]()
+        {'breast': run_breast, 'nimp': run_nimp, 'ep': run_ep, 'pmmh': run_pmmh, 'large': run_large}[w]()
