@@ -15,6 +15,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef APM_SKEL
+#define APM_SKEL 0   // dev: skip phases of the Cholesky tasks to measure the skeleton (results are wrong when non-zero)
+#endif
+
 namespace apm {
 
 // ------------------------------------------------------------------------------------------------
@@ -579,16 +583,22 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
         gemm_nt_64x64<true>(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
         PHASE_MARK(1);  // panel GEMM
         tile_put_acc(s.Ts, acc);
+#if !(APM_SKEL & 8)
         load_diag_block(s.LT, s.invd, dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
+#endif
         __syncthreads();
         PHASE_MARK(2);  // stage T and L_kk
+#if !(APM_SKEL & 1)
         trsm64_smem(s.Ts, s.LT, s.invd);
+#endif
         __syncthreads();
         PHASE_MARK(3);  // triangular solve
         if (k == 0) acc_load_tile(acc, src + (size_t)i * TB * p.lds + i * TB, p.lds, sci, sci, p.add_identity != 0);
         else acc_load_tile(acc, dii, p.ldd, nullptr, nullptr, false);
         tile_store(s.Ts, dst + (size_t)i * TB * p.ldd + k * TB, p.ldd);
+#if !(APM_SKEL & 2)
         syrk_from_tile(acc, s.Ts);
+#endif
         PHASE_MARK(4);  // store L_ik + diagonal contribution
         if (i != k + 1) {
             acc_store_tile(acc, dii, p.ldd);
@@ -603,7 +613,9 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
         tile_put_acc(s.Ts, acc);
         if (threadIdx.x == 0) s.potrf->fail = 0;
         __syncthreads();
+#if !(APM_SKEL & 4)
         potrf64_smem(s.Ts, s.LT, s.potrf);
+#endif
         PHASE_MARK(6);  // 64x64 Cholesky
         tile_store(s.Ts, dii, p.ldd);
         if (FLOW) publish_progress(prog + i, i + 1);
@@ -619,7 +631,7 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
                 p.logdet_parts[(size_t)chain_index(p.logdet_idx, b) * p.logdet_stride + i] = s.invd[0] + s.invd[1];
             if (s.potrf->fail) atomicMax(&p.status[b], p.fail_code);
         }
-        if (p.inv_out) {
+        if (p.inv_out && !(APM_SKEL & 4)) {
             // (L_ii^{-1})^T = I * L_ii^{-T}: lets the single right-hand-side solves of the Newton step
             // (k_trsv2) replace 64-step substitutions on the diagonal blocks by parallel 64x64 mat-vecs
             __syncthreads();
