@@ -7,6 +7,7 @@ hdr, data = rows[0], rows[2:]
 idx = {h: i for i, h in enumerate(hdr)}
 cols = [('Kernel Name', 'kernel'), ('launch__grid_size', 'grid'), ('gpu__time_duration.sum', 'us'),
         ('launch__registers_per_thread', 'regs'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ%'),
+        ('sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active', 'dmma%'),
         ('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'fp64pipe%'),
         ('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'fp64inst%'),
         ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm%'),
