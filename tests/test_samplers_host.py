@@ -52,3 +52,35 @@ def test_utils_match_reference():
     Xn, mn, sd = utils.normalise_inputs(X)
     np.testing.assert_allclose(Xn.mean(0), 0, atol=1e-14)
     np.testing.assert_allclose(Xn.std(0), 1, atol=1e-14)
+
+
+def test_run_artefacts_have_the_reference_file_format(tmp_path):
+    """save_run / save_adaptive_run (gpdemo/utils.py:108-208): key names, perf-stat packing and sorted JSON."""
+    import json
+    thetas = np.arange(12.).reshape(6, 2)
+    res, par = utils.save_run(str(tmp_path), 'apm_test', thetas, (3, 4), 77, 1.5, {'n_imp': 4, 'a': [1, 2]})
+    z = np.load(res)
+    assert sorted(z.files) == ['n_reject_n_cubic_ops_comp_time', 'thetas']
+    assert np.array_equal(z['thetas'], thetas) and np.array_equal(z['n_reject_n_cubic_ops_comp_time'], [3, 4, 77, 1.5])
+    assert res.endswith('apm_test_results.npz') and par.endswith('apm_test_params.json')
+    assert json.load(open(par)) == {'n_imp': 4, 'a': [1, 2]} and open(par).read().index('"a"') < open(par).read().index('"n_imp"')
+    res, par = utils.save_adaptive_run(str(tmp_path), 'ad', thetas, thetas[:3], np.ones(3), thetas, 5, 9, 2.5, {})
+    z = np.load(res)
+    assert sorted(z.files) == ['adapt_accept_rates', 'adapt_prop_scales', 'adapt_thetas', 'n_reject_n_cubic_ops_comp_time', 'thetas']
+    assert np.array_equal(z['n_reject_n_cubic_ops_comp_time'], [5, 9, 2.5])
+
+
+def test_chain_diagnostics():
+    rs = np.random.RandomState(3)
+    n = 20000
+    white = rs.normal(size=n)
+    assert abs(utils.effective_sample_size(white) / n - 1.) < 0.1
+    rho = 0.9                                              # AR(1): ESS = n (1 - rho) / (1 + rho)
+    ar = np.empty(n)
+    ar[0] = white[0]
+    for t in range(1, n):
+        ar[t] = rho * ar[t - 1] + white[t]
+    assert abs(utils.effective_sample_size(ar) / (n * (1 - rho) / (1 + rho)) - 1.) < 0.2
+    same = rs.normal(size=(4, 2000))
+    assert abs(utils.gelman_rubin(same) - 1.) < 0.01
+    assert utils.gelman_rubin(same + np.arange(4)[:, None] * 3.) > 2.
