@@ -76,6 +76,11 @@ struct apm_ctx {
     double *dX = nullptr, *dy = nullptr;
     double *dK = nullptr, *dLB = nullptr, *dZ = nullptr;
     double *dSlotLK = nullptr, *dSlotLC = nullptr, *dSlotMu = nullptr, *dSlotLdK = nullptr, *dSlotLdC = nullptr;
+    // Factored cache: what a slot's "L_C" buffer holds.  0: chol(C) itself (imported / explicit covariance);
+    // 1: V = U^T with M = I + L_K^T W L_K = U U^T, so that L_C = L_K V^-1 is never formed: f_s = mu + L_K (V^-T u_s) and
+    // L_K^-1 f_s = L_K^T a + V^-T u_s (mu = K a), with dSlotMt = L_K^T a.  See run_covariance_factored / run_is_tail.
+    double* dSlotMt = nullptr;
+    std::vector<char> slot_mode;
     double* dLdB = nullptr;
     int *dFlowCounter = nullptr, *dFlowProgress = nullptr, *dFlowSkip = nullptr;
     int flow_grid = 0;        // persistent grid of k_chol_dataflow (SMs x occupancy); 0 = per-step launches
@@ -112,6 +117,7 @@ struct apm_ctx {
 };
 
 static char* slot_flags(apm_ctx* c) { return (c->root ? c->root : c)->slot_valid.data(); }
+static char* slot_modes(apm_ctx* c) { return (c->root ? c->root : c)->slot_mode.data(); }
 
 template <typename T>
 static int dev_alloc(apm_ctx* c, T** p, size_t count) {
@@ -225,6 +231,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     c->maxN = max_nimp;
     c->maxNpad = (max_nimp + TB - 1) / TB * TB;
     c->mat = (size_t)c->np * c->np;
+    c->slot_mode.assign(n_slots, 0);
     c->slot_valid.assign(n_slots, 0);  // (lane views share the root's flags: slot_flags())
     {
         int occ = 0, sms = 0, coop = 0;
@@ -246,6 +253,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     A(dev_alloc(c, &c->dSlotLK, (size_t)n_slots * c->mat));
     A(dev_alloc(c, &c->dSlotLC, (size_t)n_slots * c->mat));
     A(dev_alloc(c, &c->dSlotMu, (size_t)n_slots * np));
+    A(dev_alloc(c, &c->dSlotMt, (size_t)n_slots * np));
     A(dev_alloc(c, &c->dSlotLdK, (size_t)n_slots * c->nb));
     A(dev_alloc(c, &c->dSlotLdC, (size_t)n_slots * c->nb));
     A(dev_alloc(c, &c->dLdB, B * c->nb));
@@ -339,7 +347,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         for (int l = 0; l < c->n_lanes; l++) {
             apm_ctx* v = new apm_ctx(*c);
             v->root = c;
-            v->lanes.clear(); v->allocs.clear(); v->ev_pool.clear(); v->pending.clear(); v->slot_valid.clear();
+            v->lanes.clear(); v->allocs.clear(); v->ev_pool.clear(); v->pending.clear(); v->slot_valid.clear(); v->slot_mode.clear();
             v->prof = false;
             v->launches = 0;
             v->stream = v->copy_stream = v->aux_stream = nullptr;
@@ -743,8 +751,8 @@ static int run_covariance(apm_ctx* c, int B, double* dst, long long dst_bs, cons
     return check_launch(c, "k_syrk_sub");
 }
 
-// chol(C) without forming C (see tile_engine.cuh "Factored posterior covariance"): needs chol(K) in the slots,
-// W^1/2 of the last Newton step; writes L_C and its partial log-dets into the slots.
+// chol(C) without forming C (see tile_engine.cuh "Factored posterior covariance"): needs chol(K) in the slots, W^1/2 and
+// `a` of the last Newton / EP step; writes V (slot mode 1), mu~ and the partial log-dets of C into the slots.
 static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots) {
     dim3 yg(c->np / 32, c->np / 32, B), yb(32, 8);
     prof_begin(c, KID_TRANSPOSE);
@@ -762,19 +770,49 @@ static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots) {
     // L' = chol(M') in place (M' has eigenvalues >= 1: cannot fail for finite input)
     APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
                      nullptr, APM_CHAIN_CHOL_C, nullptr));
-    TrsmRevParams t;
-    t.LK = c->dSlotLK; t.lk_bs = (long long)c->mat; t.ldk = c->np; t.lk_idx = dSlots;
-    t.Lp = c->dLB; t.lp_bs = (long long)c->mat; t.ldp = c->np;
-    t.X = c->dZ; t.x_bs = (long long)c->mat; t.ldx = c->np;
-    t.LC = c->dSlotLC; t.lc_bs = (long long)c->mat; t.ldc = c->np; t.lc_idx = dSlots;
-    t.nb = c->nb;
-    t.status = c->dStatus;
-    prof_begin(c, KID_TRSM);
-    k_trsm_rev<<<B * c->nb, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
-    APM_TRY(check_launch(c, "k_trsm_rev"));
+    // V = anti-transpose of L' into the slot's L_C buffer; mu~ = L_K^T a.  The importance-sampling tail works with
+    // (L_K, V, mu, mu~) directly, so the n^3/3 triangular solve for the explicit L_C = L_K V^-1 is only run if somebody
+    // asks for C_chol (slot_make_explicit).
+    dim3 ag(c->np / 32, c->np / 32, B), ab(32, 8);
+    prof_begin(c, KID_TRANSPOSE);
+    k_antitranspose<<<ag, ab, 0, c->stream>>>(c->dLB, (long long)c->mat, nullptr, c->dSlotLC, (long long)c->mat, dSlots, c->np,
+                                             c->dStatus);
+    APM_TRY(check_launch(c, "k_antitranspose"));
+    prof_begin(c, KID_MATVEC);
+    k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, c->dVec[V_A], c->np,
+                                                        c->dSlotMt, c->np, dSlots, c->dStatus);
+    APM_TRY(check_launch(c, "k_lt_matvec"));
     prof_begin(c, KID_MISC);
     k_logdet_combine<<<B, 256, 0, c->stream>>>(c->dSlotLdK, c->dLdB, c->dSlotLdC, dSlots, c->nb, c->dStatus);
     return check_launch(c, "k_logdet_combine");
+}
+
+// slot mode 1 -> 0: L_C = L_K V^-1 by the reversed right triangular solve (k_trsm_rev) with L' = anti-transpose of V.
+// Uses chain 0 of the scratch matrices (the API is host-synchronous: nothing else is in flight).
+static int slot_make_explicit(apm_ctx* c, int slot) {
+    if (slot_modes(c)[slot] != 1) return APM_OK;
+    c->hInts[0] = slot;
+    CU_TRY(cudaMemcpyAsync(c->dSlotsB, c->hInts, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    dim3 ag(c->np / 32, c->np / 32, 1), ab(32, 8);
+    prof_begin(c, KID_TRANSPOSE);
+    k_antitranspose<<<ag, ab, 0, c->stream>>>(c->dSlotLC, (long long)c->mat, c->dSlotsB, c->dLB, (long long)c->mat, nullptr, c->np,
+                                             nullptr);
+    APM_TRY(check_launch(c, "k_antitranspose"));
+    CU_TRY(cudaMemsetAsync(c->dFlowSkip, 0, sizeof(int), c->stream));   // a zero status word for the single pseudo-chain
+    TrsmRevParams t;
+    t.LK = c->dSlotLK; t.lk_bs = (long long)c->mat; t.ldk = c->np; t.lk_idx = c->dSlotsB;
+    t.Lp = c->dLB; t.lp_bs = (long long)c->mat; t.ldp = c->np;
+    t.X = c->dZ; t.x_bs = (long long)c->mat; t.ldx = c->np;
+    t.LC = c->dSlotLC; t.lc_bs = (long long)c->mat; t.ldc = c->np; t.lc_idx = c->dSlotsB;
+    t.nb = c->nb;
+    t.status = c->dFlowSkip;
+    prof_begin(c, KID_TRSM);
+    k_trsm_rev<<<c->nb, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
+    APM_TRY(check_launch(c, "k_trsm_rev"));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    slot_modes(c)[slot] = 0;
+    return APM_OK;
 }
 
 // bring u (reference layout [B][n][N]) into UT [B][Npad][np]
@@ -819,13 +857,29 @@ static int prefetch_u(apm_ctx* c, const double* u, int u_on_device, int N, int B
 }
 
 // the O(n^2 N) tail (estimators.py:221-241) for chains whose caches sit in slots dSlots[b]
-static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_logml, double* d_logw, int mode) {
+// mode 0: importance sampling from the posterior approximation; 1: prior Monte Carlo.  factored (mode 0 only): the slots
+// hold V and mu~ instead of chol(C) (slot mode 1).
+static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_logml, double* d_logw, int mode, bool factored = false) {
     const int Npad = (N + TB - 1) / TB * TB;
     const int rblocks = Npad / TB;
     const long long ubs = (long long)Npad * c->np;
+    if (mode == 0 && factored) {
+        // W V^T = U^T  (w_s = V^-T u_s), rows = samples                       [same flops as estimators.py:225's solve]
+        TrsmParams t;
+        t.R = c->dUT; t.r_bs = ubs; t.ldr = c->np; t.r_idx = nullptr;
+        t.cs = nullptr; t.cs_bs = 0;
+        t.X = c->dZf; t.x_bs = ubs; t.ldx = c->np;
+        t.L = c->dSlotLC; t.l_bs = (long long)c->mat; t.ldl = c->np; t.l_idx = dSlots;
+        t.nb = c->nb; t.row_blocks = rblocks;
+        t.status = c->dStatus; t.active = nullptr;
+        prof_begin(c, KID_TRSM);
+        k_trsm_rows<<<B * rblocks, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
+        APM_TRY(check_launch(c, "k_trsm_rows"));
+    }
     GemmTriParams g;
-    g.UT = c->dUT; g.u_bs = ubs; g.ldu = c->np;
-    g.L = (mode == 0) ? c->dSlotLC : c->dSlotLK; g.l_bs = (long long)c->mat; g.ldl = c->np; g.l_idx = dSlots;
+    // F = mu + U^T L_C^T (estimators.py:223); factored: F = mu + W L_K^T; prior MC: F = U^T L_K^T (estimators.py:323)
+    g.UT = (mode == 0 && factored) ? c->dZf : c->dUT; g.u_bs = ubs; g.ldu = c->np;
+    g.L = (mode == 0 && !factored) ? c->dSlotLC : c->dSlotLK; g.l_bs = (long long)c->mat; g.ldl = c->np; g.l_idx = dSlots;
     g.mu = (mode == 0) ? c->dSlotMu : nullptr; g.mu_bs = c->np; g.mu_idx = dSlots;
     g.F = c->dF; g.f_bs = ubs; g.ldf = c->np;
     g.nb = c->nb; g.row_blocks = rblocks;
@@ -833,8 +887,8 @@ static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_lo
     prof_begin(c, KID_GEMM_TRI);
     k_gemm_tri<<<B * c->nb * rblocks, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(g);
     APM_TRY(check_launch(c, "k_gemm_tri"));
-    if (mode == 0) {
-        TrsmParams t;
+    if (mode == 0 && !factored) {
+        TrsmParams t;                                                          // Zf = L_K^-1 f_s (estimators.py:225)
         t.R = c->dF; t.r_bs = ubs; t.ldr = c->np; t.r_idx = nullptr;
         t.cs = nullptr; t.cs_bs = 0;
         t.X = c->dZf; t.x_bs = ubs; t.ldx = c->np;
@@ -852,6 +906,7 @@ static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_lo
     e.status = c->dStatus;
     e.logml = d_logml; e.logw = d_logw;
     e.mode = mode;
+    e.mt = (mode == 0 && factored) ? c->dSlotMt : nullptr; e.mt_bs = c->np;   // L_K^-1 f_s = mu~ + w_s
     prof_begin(c, KID_EPILOGUE);
     k_is_epilogue<<<B, 256, sizeof(double) * N, c->stream>>>(e);
     return check_launch(c, "k_is_epilogue");
@@ -1163,10 +1218,11 @@ static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, 
     k_copy_vec<<<cg, 256, 0, c->stream>>>(c->dVec[V_F], c->np, nullptr, c->dSlotMu, c->np, c->dSlotsA, c->np, c->dStatus);
     APM_TRY(check_launch(c, "k_copy_vec"));
     if (overlap) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
-    APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, nullptr, 0));
+    APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, nullptr, 0, c->factored_cov));
     std::vector<int> st(B);
     APM_TRY(fetch_results(c, B, c->dOut, 1, logml_out, cubic_ops_out, 3, st.data()));  // iters + 1 + 2 (est.py:217)
     for (int b = 0; b < B; b++) {
+        slot_modes(c)[slots[b]] = c->factored_cov ? 1 : 0;
         slot_flags(c)[slots[b]] = (st[b] == 0);
         if (chain_status) chain_status[b] = st[b];
     }
@@ -1180,8 +1236,16 @@ static int cached_common(apm_ctx* c, const int* slots, const double* u, int u_on
     cancel_prefetch(c);
     APM_TRY(reset_status(c, B));
     APM_TRY(upload_slots(c, slots, B, c->dSlotsA, true));
+    // all slots factored (written by apm_estimate_full) or all explicit (imported): use them as they are; a mixed batch
+    // converts its factored slots to explicit chol(C) first
+    int n_fact = 0;
+    for (int b = 0; b < B; b++) n_fact += slot_modes(c)[slots[b]] == 1;
+    if (n_fact != 0 && n_fact != B) {
+        for (int b = 0; b < B; b++) APM_TRY(slot_make_explicit(c, slots[b]));
+        n_fact = 0;
+    }
     APM_TRY(stage_u(c, u, u_on_device, N, B));
-    APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, logw_out ? c->dLogw : nullptr, 0));
+    APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, logw_out ? c->dLogw : nullptr, 0, n_fact == B));
     if (logw_out) CU_TRY(cudaMemcpyAsync(logw_out, c->dLogw, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
     return fetch_results(c, B, c->dOut, 1, logml_out, nullptr, 0, chain_status);
@@ -1258,6 +1322,7 @@ extern "C" int apm_slot_export(apm_ctx* c, int slot, double* K_chol, double* C_c
         CU_TRY(cudaStreamSynchronize(c->stream));
     }
     if (C_chol) {
+        APM_TRY(slot_make_explicit(c, slot));     // a factored slot forms chol(C) = L_K V^-1 only now
         prof_begin(c, KID_MISC);
         k_export_lower<<<grid, 256, 0, c->stream>>>(c->dSlotLC + (size_t)slot * c->mat, c->np, c->n, stage, 0);
         APM_TRY(check_launch(c, "k_export_lower"));
@@ -1298,6 +1363,7 @@ extern "C" int apm_slot_import(apm_ctx* c, int slot, const double* K_chol, const
         CU_TRY(cudaMemcpyAsync(c->dSlotMu + (size_t)slot * c->np, f_post, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
     }
     CU_TRY(cudaStreamSynchronize(c->stream));
+    slot_modes(c)[slot] = 0;
     slot_flags(c)[slot] = 1;
     return APM_OK;
 }
@@ -1323,6 +1389,7 @@ extern "C" int apm_slot_factor(apm_ctx* c, int slot, const double* K, const doub
     CU_TRY(cudaMemcpyAsync(c->hInts, c->dStatus, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     st = c->hInts[0];
+    slot_modes(c)[slot] = 0;
     slot_flags(c)[slot] = (st == 0);
     if (chain_status) chain_status[0] = st;
     return APM_OK;
@@ -1338,6 +1405,8 @@ extern "C" int apm_slot_copy(apm_ctx* c, const int* src, const int* dst, int B) 
         CU_TRY(cudaMemcpyAsync(c->dSlotLK + d * c->mat, c->dSlotLK + s * c->mat, sizeof(double) * c->mat, cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->dSlotLC + d * c->mat, c->dSlotLC + s * c->mat, sizeof(double) * c->mat, cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->dSlotMu + d * c->np, c->dSlotMu + s * c->np, sizeof(double) * c->np, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->dSlotMt + d * c->np, c->dSlotMt + s * c->np, sizeof(double) * c->np, cudaMemcpyDeviceToDevice, c->stream));
+        slot_modes(c)[d] = slot_modes(c)[s];
         CU_TRY(cudaMemcpyAsync(c->dSlotLdK + d * c->nb, c->dSlotLdK + s * c->nb, sizeof(double) * c->nb, cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->dSlotLdC + d * c->nb, c->dSlotLdC + s * c->nb, sizeof(double) * c->nb, cudaMemcpyDeviceToDevice, c->stream));
         slot_flags(c)[d] = slot_flags(c)[s];

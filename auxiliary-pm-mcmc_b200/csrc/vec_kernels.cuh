@@ -645,6 +645,7 @@ struct EpilogueParams {
     const int* status;
     double* logml; double* logw;   // logw optional [chain][N]
     int mode;
+    const double* mt; long long mt_bs;   // optional [slot][np]: L_K^{-1} f_s = mt + Zf row (factored cache, see run_is_tail)
 };
 
 __global__ void __launch_bounds__(256) k_is_epilogue(EpilogueParams p) {
@@ -670,9 +671,10 @@ __global__ void __launch_bounds__(256) k_is_epilogue(EpilogueParams p) {
         if (p.mode == 0) {
             const double* Zr = p.Zf + (long long)b * p.bs + (size_t)s * p.ld;
             const double* Ur = p.UT + (long long)b * p.bs + (size_t)s * p.ld;
+            const double* mt = p.mt ? p.mt + chain_index(p.slot_idx, b) * p.mt_bs : nullptr;
             for (int i = lane; i < p.n; i += 32) {
                 ll += log_ndtr(p.y[i] * Fr[i]);
-                const double z = Zr[i], u = Ur[i];
+                const double z = mt ? mt[i] + Zr[i] : Zr[i], u = Ur[i];
                 qk = fma(z, z, qk);
                 qu = fma(u, u, qu);
             }
@@ -712,6 +714,55 @@ __global__ void __launch_bounds__(256) k_is_epilogue(EpilogueParams p) {
 // ------------------------------------------------------------------------------------------------
 // layout helpers
 // ------------------------------------------------------------------------------------------------
+// Anti-transpose of a lower-triangular matrix: dst[i][j] = src[np-1-j][np-1-i] (i >= j), zeros above the diagonal inside
+// the 64x64 diagonal blocks.  Maps L' = chol(P M P) to V = U^T with M = U U^T (V lower triangular, V^T V... see
+// run_covariance_factored) and back (it is an involution).  32x32 tiles through shared memory; grid (np/32, np/32, chains).
+__global__ void k_antitranspose(const double* __restrict__ src, long long s_bs, const int* s_idx, double* __restrict__ dst,
+                                long long d_bs, const int* d_idx, int np, const int* status) {
+    __shared__ double tile[32][33];
+    const int b = blockIdx.z;
+    if (status && status[b] != 0) return;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    if (i0 < j0 && (i0 >> 6) != (j0 >> 6)) return;            // strictly upper, outside a diagonal block: never read
+    const double* S = src + chain_index(s_idx, b) * s_bs;
+    double* Dm = dst + chain_index(d_idx, b) * d_bs;
+    const int tx = threadIdx.x, ty = threadIdx.y;             // 32 x 8
+    const bool upper = i0 < j0;
+    if (!upper) {
+        const int r0 = np - 32 - j0, c0 = np - 32 - i0;
+        for (int r = ty; r < 32; r += 8) tile[r][tx] = S[(size_t)(r0 + r) * np + c0 + tx];
+    }
+    __syncthreads();
+    for (int a = ty; a < 32; a += 8) {
+        const int i = i0 + a, j = j0 + tx;
+        Dm[(size_t)i * np + j] = (!upper && i >= j) ? tile[31 - tx][31 - a] : 0.0;
+    }
+}
+
+// out[slot][j] = sum_{i >= j} L[i][j] x[i]   (L^T x for lower-triangular L); grid (nb, chains), 256 threads = 4 row groups
+__global__ void __launch_bounds__(256) k_lt_matvec(const double* __restrict__ L, long long l_bs, const int* l_idx, int ld, int nb,
+                                                   const double* __restrict__ x, long long x_bs, double* __restrict__ out,
+                                                   long long o_bs, const int* o_idx, const int* status) {
+    __shared__ double part[4][64];
+    const int b = blockIdx.y, jb = blockIdx.x;
+    if (status && status[b] != 0) return;
+    const double* Lb = L + chain_index(l_idx, b) * l_bs;
+    const double* xb = x + (long long)b * x_bs;
+    const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    double a0 = 0.0, a1 = 0.0;
+    const int np = nb * 64;
+    int i = jb * 64 + rg;
+    for (; i + 4 < np; i += 8) {
+        a0 = fma(Lb[(size_t)i * ld + jb * 64 + c], xb[i], a0);
+        a1 = fma(Lb[(size_t)(i + 4) * ld + jb * 64 + c], xb[i + 4], a1);
+    }
+    for (; i < np; i += 4) a0 = fma(Lb[(size_t)i * ld + jb * 64 + c], xb[i], a0);
+    part[rg][c] = a0 + a1;
+    __syncthreads();
+    if (threadIdx.x < 64)
+        out[chain_index(o_idx, b) * o_bs + jb * 64 + c] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+}
+
 // pad region of a [np][np] matrix -> identity (after importing an n x n matrix)
 __global__ void k_pad_identity(double* M, long long bs, int n, int np) {
     double* Mb = M + (long long)blockIdx.y * bs;

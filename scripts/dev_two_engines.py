@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from apm_b200 import _capi, synth
-n, D, N, B = 768, 8, 64, 256
+n, D, N = 768, 8, 64
+B = int(os.environ.get('TOTAL_CHAINS', 256))
 X, y, th = synth.make_dataset(n, D, seed=0)
 thetas = synth.bulk_thetas(B, D)
 u = torch.randn(B, n, N, dtype=torch.float64, device='cuda')
