@@ -72,6 +72,13 @@ struct apm_ctx {
     double ep_tol = 1e-6, ep_damping = 1.0;
     int ep_max_iters = 100;
     double* dEpDelta = nullptr;
+    // hybrid Newton: the iteration predicted to be a chain's last is done in M-space (M = I + L_K^T W L_K), whose
+    // Cholesky factor is exactly what the factored covariance needs, so the converged chain skips the separate
+    // SYRK + Cholesky of M' (and the chol(B) of that iteration).  APM_NO_HYBRID_NEWTON=1 disables it.
+    bool hybrid_newton = true;
+    double pred_factor = 2.0;
+    int *dMaskM = nullptr, *dMaskB = nullptr, *dDoneM = nullptr;
+    bool newton_b_finishers = true;   // set by run_newton: some chain finished in a B-space round (needs the covariance phase)
     size_t mat = 0;  // np*np
     double *dX = nullptr, *dy = nullptr;
     double *dK = nullptr, *dLB = nullptr, *dZ = nullptr;
@@ -270,6 +277,9 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     A(dev_alloc(c, &c->dOut, B * 2));
     A(dev_alloc(c, &c->dLogw, B * (size_t)max_nimp));
     A(dev_alloc(c, &c->dEpDelta, B));
+    A(dev_alloc(c, &c->dMaskM, B));
+    A(dev_alloc(c, &c->dMaskB, B));
+    A(dev_alloc(c, &c->dDoneM, B));
     A(dev_alloc(c, &c->dStatus, B));
     A(dev_alloc(c, &c->dActive, B));
     A(dev_alloc(c, &c->dIters, B));
@@ -293,6 +303,8 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     }
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
+    c->hybrid_newton = getenv("APM_NO_HYBRID_NEWTON") == nullptr;
+    if (getenv("APM_PRED_FACTOR") && atof(getenv("APM_PRED_FACTOR")) > 0) c->pred_factor = atof(getenv("APM_PRED_FACTOR"));
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_k_ready, cudaEventDisableTiming) != cudaSuccess ||
@@ -596,14 +608,14 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
 }
 
 // out = rs * (K x) for all active chains, reading only the lower tiles of the symmetric K (lpa.py:94-95 mat-vecs)
-static int run_symv(apm_ctx* c, int B, const double* x, const double* rs, double* out) {
+static int run_symv(apm_ctx* c, int B, const double* x, const double* rs, double* out, const int* mask = nullptr) {
+    if (!mask) mask = c->dActive;
     prof_begin(c, KID_MATVEC);
     k_symv_lower<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, c->nb, x, c->np, c->dSymvDirect,
-                                                        c->dSymvPart, c->dActive, c->dStatus);
+                                                        c->dSymvPart, mask, c->dStatus);
     APM_TRY(check_launch(c, "k_symv_lower"));
     prof_begin(c, KID_MATVEC);
-    k_symv_reduce<<<dim3(c->nb, B), 64, 0, c->stream>>>(c->dSymvDirect, c->dSymvPart, c->nb, rs, out, c->np, c->dActive,
-                                                        c->dStatus);
+    k_symv_reduce<<<dim3(c->nb, B), 64, 0, c->stream>>>(c->dSymvDirect, c->dSymvPart, c->nb, rs, out, c->np, mask, c->dStatus);
     return check_launch(c, "k_symv_reduce");
 }
 
@@ -614,13 +626,42 @@ static NewtonVecs make_nv(apm_ctx* c) {
     nv.vs = c->np; nv.y = c->dy; nv.n = c->n; nv.np = c->np;
     nv.active = c->dActive; nv.iters = c->dIters; nv.status = c->dStatus; nv.n_active = c->dNActive;
     nv.tol = c->tol; nv.max_iters = c->max_iters;
+    nv.done_m = nullptr; nv.round_is_m = 0; nv.pred_factor = c->pred_factor;
     return nv;
+}
+
+// M' = I + Y'Y'^T (lower tiles, reversed coordinates) -> dLB, for chains in `mask` (null: all): Y' from chol(K) in the
+// slots and W^1/2 (see tile_engine.cuh "Factored posterior covariance")
+static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mask) {
+    dim3 yg(c->np / 32, c->np / 32, B), yb(32, 8);
+    prof_begin(c, KID_TRANSPOSE);
+    k_make_Y<<<yg, yb, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->dVec[V_WS], c->np, c->dZ,
+                                       (long long)c->mat, c->np, c->dStatus, mask);
+    APM_TRY(check_launch(c, "k_make_Y"));
+    SyrkRevParams s;
+    s.Y = c->dZ; s.y_bs = (long long)c->mat; s.ldy = c->np;
+    s.M = c->dLB; s.m_bs = (long long)c->mat; s.ldm = c->np;
+    s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
+    s.status = c->dStatus; s.mask = mask;
+    prof_begin(c, KID_SYRK);
+    k_syrk_rev<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
+    return check_launch(c, "k_syrk_rev");
 }
 
 // Newton mode search (lpa.py:81-102) for chains 0..B-1 whose K sits in c->dK.  On exit f (V_F) is the
 // mode, LB / Ws / a are those of the last executed iteration of each chain, dIters the iteration counts.
-static int run_newton(apm_ctx* c, int B) {
+//
+// dSlots != null (fused FULL estimate with the factored covariance): hybrid iteration.  An iteration solves
+// (K^-1 + W) f_new = b.  The reference's form (B-space) is a = b - W^1/2 B^-1 W^1/2 K b, f_new = K a with
+// B = I + W^1/2 K W^1/2 (one Cholesky).  The M-space form is f_new = L_K M^-1 L_K^T b with M = I + L_K^T W L_K (SYRK +
+// Cholesky: twice the work) -- but chol(M) of a chain's LAST iteration is exactly what its posterior covariance needs
+// (C = L_K M^-1 L_K^T with the last W, lpa.py:107-112), so a chain whose next iteration is predicted to be the last
+// (k_newton_finish) runs it in M-space and skips both that iteration's chol(B) and the covariance phase: n^3/3 less.
+// Both forms give the same f_new up to rounding (~1e-14 relative); chains whose prediction fails simply iterate on.
+// lk_pending: chol(K) is still running on the aux stream (wait for ev_lk_done before the first M-space step).
+static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pending = false) {
     NewtonVecs nv = make_nv(c);
+    const bool hybrid = dSlots != nullptr && c->factored_cov && c->hybrid_newton;
     CU_TRY(cudaMemsetAsync(nv.f, 0, sizeof(double) * (size_t)B * c->np, c->stream));
     CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
     prof_begin(c, KID_MISC);
@@ -629,33 +670,74 @@ static int run_newton(apm_ctx* c, int B) {
     prof_begin(c, KID_MISC);
     k_fill_int<<<1, 32, 0, c->stream>>>(c->dNActive, B, 1);
     APM_TRY(check_launch(c, "k_fill_int"));
+    if (hybrid) {
+        nv.done_m = c->dDoneM;
+        CU_TRY(cudaMemsetAsync(c->dDoneM, 0, sizeof(int) * B, c->stream));
+    }
     const size_t trsv_smem = (size_t)(c->np + 64 + 8 * 64) * sizeof(double);
     if (trsv_smem > 160 * 1024) {
         set_err("run_newton: n too large for the single-CTA triangular solve");
         return APM_ERR_INVALID;
     }
+    // A round is never mixed (small extra batches would be latency-bound): it runs in M-space for ALL active chains when
+    // at least half of them are predicted to finish in it (the others just pay n^3/3 more for that one iteration).
+    bool round_m = false;
+    c->newton_b_finishers = false;
+    int n_act = B;
     for (int it = 0; it < c->max_iters; it++) {
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_prep<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_prep"));
-        // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b))
-        APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t));
-        // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
-        APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
-                         nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB));
-        // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
-        prof_begin(c, KID_TRSV);
-        k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
-                                                  (long long)c->nb * TB * TB, nv);
-        APM_TRY(check_launch(c, "k_trsv2"));
-        // f_new = K a                                              (lpa.py:95)
-        APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew));
+        if (!round_m) {
+            // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b))
+            APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t));
+            // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
+            APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
+                             nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB));
+            // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
+            prof_begin(c, KID_TRSV);
+            k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                      (long long)c->nb * TB * TB, nv);
+            APM_TRY(check_launch(c, "k_trsv2"));
+            // f_new = K a                                              (lpa.py:95)
+            APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew));
+        } else {
+            if (lk_pending) {
+                CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
+                lk_pending = false;
+            }
+            // t' = reversed L_K^T b
+            prof_begin(c, KID_MATVEC);
+            k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, nv.bvec, c->np,
+                                                                nv.t, c->np, nullptr, c->dStatus, c->dActive, 1);
+            APM_TRY(check_launch(c, "k_lt_matvec"));
+            // L' = chol(M'), M' = P (I + L_K^T W L_K) P
+            APM_TRY(run_build_mprime(c, B, dSlots, c->dActive));
+            APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
+                             nullptr, APM_CHAIN_CHOL_C, c->dActive, c->dInvB));
+            // s' = M'^-1 t'
+            prof_begin(c, KID_TRSV);
+            k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                      (long long)c->nb * TB * TB, nv);
+            APM_TRY(check_launch(c, "k_trsv2"));
+            // mu~ = reversed s' (-> slot), f_new = L_K mu~
+            prof_begin(c, KID_MATVEC);
+            k_l_matvec_rev<<<dim3(c->np / 32, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->np, nv.s,
+                                                                       c->np, nv.fnew, c->np, c->dSlotMt, c->np, dSlots, c->dStatus,
+                                                                       c->dActive);
+            APM_TRY(check_launch(c, "k_l_matvec_rev"));
+        }
+        if (hybrid) CU_TRY(cudaMemsetAsync(c->dNActive + 1, 0, sizeof(int), c->stream));
+        nv.round_is_m = round_m ? 1 : 0;
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_finish<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_finish"));
-        CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
-        if (c->hNActive[0] <= 0) break;
+        if (!round_m && c->hNActive[0] < n_act) c->newton_b_finishers = true;   // somebody finished in B-space
+        n_act = c->hNActive[0];
+        if (n_act <= 0) break;
+        round_m = hybrid && 2 * c->hNActive[1] >= n_act;
     }
     return APM_OK;
 }
@@ -753,23 +835,22 @@ static int run_covariance(apm_ctx* c, int B, double* dst, long long dst_bs, cons
 
 // chol(C) without forming C (see tile_engine.cuh "Factored posterior covariance"): needs chol(K) in the slots, W^1/2 and
 // `a` of the last Newton / EP step; writes V (slot mode 1), mu~ and the partial log-dets of C into the slots.
-static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots) {
-    dim3 yg(c->np / 32, c->np / 32, B), yb(32, 8);
-    prof_begin(c, KID_TRANSPOSE);
-    k_make_Y<<<yg, yb, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->dVec[V_WS], c->np, c->dZ,
-                                       (long long)c->mat, c->np, c->dStatus);
-    APM_TRY(check_launch(c, "k_make_Y"));
-    SyrkRevParams s;
-    s.Y = c->dZ; s.y_bs = (long long)c->mat; s.ldy = c->np;
-    s.M = c->dLB; s.m_bs = (long long)c->mat; s.ldm = c->np;
-    s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
-    s.status = c->dStatus;
-    prof_begin(c, KID_SYRK);
-    k_syrk_rev<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
-    APM_TRY(check_launch(c, "k_syrk_rev"));
-    // L' = chol(M') in place (M' has eigenvalues >= 1: cannot fail for finite input)
-    APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                     nullptr, APM_CHAIN_CHOL_C, nullptr));
+static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots, const int* done_m = nullptr) {
+    // chains whose last Newton iteration ran in M-space (done_m) already have L' = chol(M') in dLB and mu~ in the slot
+    const int* todo = nullptr;
+    const bool need_cov = !done_m || c->newton_b_finishers;
+    if (done_m && need_cov) {
+        prof_begin(c, KID_MISC);
+        k_mask_not<<<(B + 255) / 256, 256, 0, c->stream>>>(done_m, c->dMaskB, B);
+        APM_TRY(check_launch(c, "k_mask_not"));
+        todo = c->dMaskB;
+    }
+    if (need_cov) {
+        APM_TRY(run_build_mprime(c, B, dSlots, todo));
+        // L' = chol(M') in place (M' has eigenvalues >= 1: cannot fail for finite input)
+        APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
+                         nullptr, APM_CHAIN_CHOL_C, todo));
+    }
     // V = anti-transpose of L' into the slot's L_C buffer; mu~ = L_K^T a.  The importance-sampling tail works with
     // (L_K, V, mu, mu~) directly, so the n^3/3 triangular solve for the explicit L_C = L_K V^-1 is only run if somebody
     // asks for C_chol (slot_make_explicit).
@@ -778,10 +859,12 @@ static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots) {
     k_antitranspose<<<ag, ab, 0, c->stream>>>(c->dLB, (long long)c->mat, nullptr, c->dSlotLC, (long long)c->mat, dSlots, c->np,
                                              c->dStatus);
     APM_TRY(check_launch(c, "k_antitranspose"));
-    prof_begin(c, KID_MATVEC);
-    k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, c->dVec[V_A], c->np,
-                                                        c->dSlotMt, c->np, dSlots, c->dStatus);
-    APM_TRY(check_launch(c, "k_lt_matvec"));
+    if (need_cov) {
+        prof_begin(c, KID_MATVEC);
+        k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, c->dVec[V_A], c->np,
+                                                            c->dSlotMt, c->np, dSlots, c->dStatus, todo, 0);
+        APM_TRY(check_launch(c, "k_lt_matvec"));
+    }
     prof_begin(c, KID_MISC);
     k_logdet_combine<<<B, 256, 0, c->stream>>>(c->dSlotLdK, c->dLdB, c->dSlotLdC, dSlots, c->nb, c->dStatus);
     return check_launch(c, "k_logdet_combine");
@@ -1135,6 +1218,7 @@ static void lane_bind(apm_ctx* v, int lane, int off, int cnt, int N) {
     v->dOut = r->dOut + o * 2;
     v->dLogw = r->dLogw + o * N;
     v->dEpDelta = r->dEpDelta + o;
+    v->dMaskM = r->dMaskM + o; v->dMaskB = r->dMaskB + o; v->dDoneM = r->dDoneM + o;
     v->approx = r->approx; v->ep_tol = r->ep_tol; v->ep_damping = r->ep_damping; v->ep_max_iters = r->ep_max_iters;
     v->dStatus = r->dStatus + o; v->dActive = r->dActive + o; v->dIters = r->dIters + o;
     v->dSlotsA = r->dSlotsA + o; v->dSlotsB = r->dSlotsB + o;
@@ -1202,11 +1286,12 @@ static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, 
     APM_TRY(full_front(c, theta, B, slots, overlap));
     APM_TRY(stage_u(c, u, u_on_device, N, B));
     if (c->approx == 1) APM_TRY(run_ep(c, B));                                  // extension: EP behind post_approx_func
-    else APM_TRY(run_newton(c, B));                                             // estimators.py:207 -> lpa.py:81-102
+    else APM_TRY(run_newton(c, B, c->dSlotsA, overlap));                        // estimators.py:207 -> lpa.py:81-102
     if (c->factored_cov) {
         // chol(C) = L_K U^-T straight from chol(K) and W (lpa.py:111-112 + estimators.py:209 without forming C)
         if (overlap) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
-        APM_TRY(run_covariance_factored(c, B, c->dSlotsA));
+        const bool hybrid = c->approx == 0 && c->hybrid_newton;
+        APM_TRY(run_covariance_factored(c, B, c->dSlotsA, hybrid ? c->dDoneM : nullptr));
     } else {
         APM_TRY(run_covariance(c, B, c->dSlotLC, (long long)c->mat, c->dSlotsA));    // lpa.py:111-112
         // chol(C) in place in the slot                                                estimators.py:209

@@ -800,14 +800,14 @@ struct SyrkRevParams {
     const double* Y; long long y_bs; int ldy;
     double* M; long long m_bs; int ldm;
     int nb; int ntiles;
-    const int* status;
+    const int* status; const int* mask;   // mask: optional, skip chain if 0
 };
 
 __global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_syrk_rev(SyrkRevParams p) {
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.x / p.ntiles;
     const int tix = p.ntiles - 1 - (int)(blockIdx.x % p.ntiles);   // deepest tiles first
-    if (p.status[b] != 0) return;
+    if (p.status[b] != 0 || (p.mask && !p.mask[b])) return;
     int i = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
     while ((i + 1) * (i + 2) / 2 <= tix) i++;
     while (i * (i + 1) / 2 > tix) i--;

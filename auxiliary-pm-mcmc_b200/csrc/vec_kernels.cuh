@@ -186,10 +186,10 @@ __global__ void k_transpose_u(const double* __restrict__ u, long long u_bs, int 
 // Cholesky factor whose Gram matrix is M' - I (see k_syrk_rev).  32x32 tiles through shared memory.
 __global__ void k_make_Y(const double* __restrict__ LK, long long lk_bs, const int* lk_idx, int ld,
                          const double* __restrict__ Ws, long long ws_bs, double* __restrict__ Y, long long y_bs, int np,
-                         const int* status) {
+                         const int* status, const int* mask) {
     __shared__ double tile[32][33];
     const int b = blockIdx.z;
-    if (status[b] != 0) return;
+    if (status[b] != 0 || (mask && !mask[b])) return;
     const int k0 = blockIdx.y * 32, i0 = blockIdx.x * 32;      // L_K rows k0.., columns i0..
     const double* L = LK + chain_index(lk_idx, b) * lk_bs;
     double* Yb = Y + (long long)b * y_bs;
@@ -222,8 +222,12 @@ struct NewtonVecs {
     long long vs;   // stride between chains (= np)
     const double* y;
     int n, np;
-    int* active; int* iters; int* status; int* n_active;   // n_active: device counter of still-active chains
+    int* active; int* iters; int* status; int* n_active;   // n_active[0]: still-active chains, [1]: of those, predicted-last
     double tol; int max_iters;
+    // hybrid Newton (run_newton): a round runs in the reference's B-space form or, when most chains are predicted to
+    // finish in it, in "M-space"; done_m[b] = the chain's last iteration was an M-space one (null: not hybrid)
+    int* done_m;
+    int round_is_m; double pred_factor;
 };
 
 // v = exp(-f^2/2 - log_ndtr(y f) - log(2 pi)/2); grad = v y; W = v^2 + grad f; Ws = sqrt(W); b = W f + grad
@@ -484,6 +488,12 @@ __global__ void __launch_bounds__(256) k_newton_finish(NewtonVecs nv) {
             nv.active[b] = 0;
             atomicSub(nv.n_active, 1);
         }
+        if (nv.done_m) {
+            // Newton converges quadratically here (diff_{k+1} ~ 0.6-1.4 diff_k^2 on GP-probit data, profiles/): the next
+            // iteration is predicted to be the chain's last one if pred_factor * diff^2 < tol.  A wrong guess only costs time.
+            if (!still) nv.done_m[b] = nv.round_is_m;
+            else if (nv.pred_factor * diff * diff < nv.tol) atomicAdd(nv.n_active + 1, 1);
+        }
     }
 }
 
@@ -740,12 +750,14 @@ __global__ void k_antitranspose(const double* __restrict__ src, long long s_bs, 
 }
 
 // out[slot][j] = sum_{i >= j} L[i][j] x[i]   (L^T x for lower-triangular L); grid (nb, chains), 256 threads = 4 row groups
+// reverse_out: the result is written index-reversed (out[np-1-j]), the right-hand side of the reversed system M' x' = g'
 __global__ void __launch_bounds__(256) k_lt_matvec(const double* __restrict__ L, long long l_bs, const int* l_idx, int ld, int nb,
                                                    const double* __restrict__ x, long long x_bs, double* __restrict__ out,
-                                                   long long o_bs, const int* o_idx, const int* status) {
+                                                   long long o_bs, const int* o_idx, const int* status, const int* mask,
+                                                   int reverse_out) {
     __shared__ double part[4][64];
     const int b = blockIdx.y, jb = blockIdx.x;
-    if (status && status[b] != 0) return;
+    if ((status && status[b] != 0) || (mask && !mask[b])) return;
     const double* Lb = L + chain_index(l_idx, b) * l_bs;
     const double* xb = x + (long long)b * x_bs;
     const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
@@ -759,8 +771,42 @@ __global__ void __launch_bounds__(256) k_lt_matvec(const double* __restrict__ L,
     for (; i < np; i += 4) a0 = fma(Lb[(size_t)i * ld + jb * 64 + c], xb[i], a0);
     part[rg][c] = a0 + a1;
     __syncthreads();
-    if (threadIdx.x < 64)
-        out[chain_index(o_idx, b) * o_bs + jb * 64 + c] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+    if (threadIdx.x < 64) {
+        const int j = jb * 64 + c;
+        out[chain_index(o_idx, b) * o_bs + (reverse_out ? np - 1 - j : j)] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+    }
+}
+
+// M-space Newton step, last part: mu~[j] = s'[np-1-j] (solution of the reversed system), f_new = L_K mu~ (lower
+// triangular mat-vec, warp per row), mu~ stored in the slot (it is L_K^-1 f_new, what the factored cache keeps).
+// grid (np/32, chains), 256 threads = 8 warps x 4 rows
+__global__ void __launch_bounds__(256) k_l_matvec_rev(const double* __restrict__ L, long long l_bs, const int* l_idx, int ld, int np,
+                                                      const double* __restrict__ srev, long long s_bs, double* __restrict__ fnew,
+                                                      long long f_bs, double* __restrict__ mt, long long mt_bs, const int* mt_idx,
+                                                      const int* status, const int* mask) {
+    const int b = blockIdx.y;
+    if ((status && status[b] != 0) || (mask && !mask[b])) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* Lb = L + chain_index(l_idx, b) * l_bs;
+    const double* sb = srev + (long long)b * s_bs;
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int r = blockIdx.x * 32 + warp * 4 + rr;
+        const double* row = Lb + (size_t)r * ld;
+        double acc = 0.0;
+        for (int j = lane; j <= r; j += 32) acc = fma(row[j], sb[np - 1 - j], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            fnew[(long long)b * f_bs + r] = acc;
+            mt[chain_index(mt_idx, b) * mt_bs + r] = sb[np - 1 - r];
+        }
+    }
+}
+
+// dst[b] = !src[b]
+__global__ void k_mask_not(const int* src, int* dst, int n) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) dst[b] = src[b] ? 0 : 1;
 }
 
 // pad region of a [np][np] matrix -> identity (after importing an n x n matrix)
