@@ -14,7 +14,7 @@ EXPORTS = [
     'apm_version', 'apm_last_error', 'apm_create', 'apm_destroy', 'apm_set_stream', 'apm_synchronize',
     'apm_set_overlap', 'apm_set_newton', 'apm_set_approximation', 'apm_ep', 'apm_get_info', 'apm_kernel_build', 'apm_kernel_grad', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
-    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
+    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_work_count', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
 ]
 
 KERNEL_ISO, KERNEL_ARD = 0, 1
@@ -66,6 +66,7 @@ def lib():
     L.apm_profile_read.argtypes = [vp, ct.c_int, ct.c_char_p, vp, vp, ct.c_int]
     L.apm_launch_count.argtypes = [vp, ct.c_int]
     L.apm_launch_count.restype = ct.c_int64
+    L.apm_work_count.argtypes = [vp, ct.POINTER(ct.c_int64), ct.c_int]
     L.apm_dev_chol_bench.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, dp]
     L.apm_measure_fp64_peak.argtypes = [ct.c_int, ct.c_int, dp]
     for name in EXPORTS:
@@ -184,6 +185,12 @@ class Engine(object):
 
     def launch_count(self, reset=False):
         return int(self._L.apm_launch_count(self._h, 1 if reset else 0))
+
+    def work_count(self, reset=False):
+        """(chain-Choleskys, M' builds) executed since the last reset, each n^3/3 flops."""
+        out = (ct.c_int64 * 2)()
+        check(self._L.apm_work_count(self._h, out, 1 if reset else 0))
+        return int(out[0]), int(out[1])
 
     @staticmethod
     def _bulk(a):

@@ -15,6 +15,11 @@ classes in `apm_b200.samplers`, so with `rng='parity'` (one `numpy.random.Random
 drawn on the host) chain c reproduces the single-chain / reference trace for the same seed, independently of
 how many chains share the batch or how they are sharded over GPUs.  `rng='device'` keeps u in HBM
 (torch CUDA generator, not stream-identical to numpy) for throughput runs.
+
+Chain groups: given a LIST of backends (one engine context each) the chains are split into that many contiguous
+groups, each scheduled by its own host thread on its own CUDA stream.  A FULL round of one group (GPU-bound, the GIL
+is released inside the C-ABI call) then overlaps the Python scheduling, the torch tensor work and the cheap CACHED
+rounds of the others.  Per-chain results are unchanged in parity mode (every chain owns its RandomState).
 """
 import numpy as np
 
@@ -55,16 +60,18 @@ class EngineBackend(object):
 
 
 class _Chain(object):
-    """State of one chain + its generator."""
+    """State of one chain + its generator.  `local` = position inside its chain group (slot numbering of the
+    group's engine context)."""
 
-    def __init__(self, index, seed, theta_init):
+    def __init__(self, index, seed, theta_init, local=None):
         self.index = index
+        local = index if local is None else local
         self.prng = np.random.RandomState(seed)
         self.theta = np.array(theta_init, dtype=np.float64)
         self.u = None
         self.log_f = None
-        self.cur_slot = 2 * index
-        self.prop_slot = 2 * index + 1
+        self.cur_slot = 2 * local
+        self.prop_slot = 2 * local + 1
         self.n_reject = [0, 0]
         self.n_cubic_ops = 0
         self.n_full = 0
@@ -88,7 +95,8 @@ class BatchedAPMSampler(object):
             raise ValueError('unknown method %r' % method)
         if rng not in ('parity', 'device'):
             raise ValueError("rng must be 'parity' or 'device'")
-        self.backend = backend
+        self.backends = list(backend) if isinstance(backend, (list, tuple)) else [backend]
+        self.backend = self.backends[0]
         self.n, self.N, self.P = int(n_data), int(n_imp), int(n_theta)
         self.method = method
         self.log_prior = log_prior
@@ -102,12 +110,14 @@ class BatchedAPMSampler(object):
         # scheduling policy: FULL estimates are latency-bound for small batches, so they are held back until this
         # fraction of the live chains is waiting for one (or nobody has a cheap CACHED request left)
         self.full_batch_frac = float(full_batch_frac)
-        self._gen = None
+        self._gens = [None] * len(self.backends)
         if rng == 'device':
             import torch
             self._torch = torch
-            self._gen = torch.Generator(device=device)
-            self._gen.manual_seed(int(self.seeds[0]) * 7919 + 17)
+            for g in range(len(self.backends)):
+                self._gens[g] = torch.Generator(device=device)
+                self._gens[g].manual_seed(int(self.seeds[0]) * 7919 + 17 + 104729 * g)
+        self._gen = self._gens[0]
 
     # ---- random draws -----------------------------------------------------------------------------
     def _draw_u(self, ch):
@@ -282,7 +292,7 @@ class BatchedAPMSampler(object):
             return vec(np.asarray(thetas))
         return np.array([self.log_prior(t) for t in thetas])
 
-    def _schedule_parity(self, chains, traces, n_sample):
+    def _schedule_parity(self, backend, chains, traces, n_sample, gen=None):
         gens = [self._run_chain(ch, n_sample, traces[c]) for c, ch in enumerate(chains)]
         pending = {}
         for c, g in enumerate(gens):
@@ -299,7 +309,7 @@ class BatchedAPMSampler(object):
                 thetas = np.stack([pending[c][1] for c in full])
                 us = [chains[c].u for c in full]
                 slots = [chains[c].prop_slot for c in full]      # written into the proposal slot
-                vals, ops, st = self.backend.full(thetas, us, slots)
+                vals, ops, st = backend.full(thetas, us, slots)
                 for j, c in enumerate(full):
                     ch = chains[c]
                     ch.n_full += 1
@@ -311,7 +321,7 @@ class BatchedAPMSampler(object):
             if cached:
                 us = [pending[c][1] for c in cached]
                 slots = [chains[c].cur_slot for c in cached]
-                vals, st = self.backend.cached(slots, us)
+                vals, st = backend.cached(slots, us)
                 for j, c in enumerate(cached):
                     ch = chains[c]
                     ch.n_cached += 1
@@ -337,9 +347,10 @@ class BatchedAPMSampler(object):
                 chains[c].failed = e.status
         return new_pending
 
-    def _schedule_device(self, chains, traces, n_sample):
+    def _schedule_device(self, backend, chains, traces, n_sample, gen=None):
         torch = self._torch
-        B, n, N = self.B, self.n, self.N
+        B, n, N = len(chains), self.n, self.N
+        gen = self._gen if gen is None else gen
         kw = dict(dtype=torch.float64, device=self.device)
         U = torch.zeros(B, n, N, **kw)        # current auxiliary normals of every chain
         V = torch.zeros(B, n, N, **kw)        # ESS auxiliary draw
@@ -367,11 +378,11 @@ class BatchedAPMSampler(object):
             if full:
                 newu = [c for c in full if pending[c][0] == 'full_newu']
                 if newu:
-                    U[idx_t(newu)] = torch.randn(len(newu), n, N, generator=self._gen, **kw)
+                    U[idx_t(newu)] = torch.randn(len(newu), n, N, generator=gen, **kw)
                 thetas = np.stack([pending[c][1] for c in full])
                 slots = [chains[c].prop_slot for c in full]
                 u_in = U if len(full) == B and full == list(range(B)) else U.index_select(0, idx_t(full))
-                vals, ops, st = self.backend.engine.estimate_full(thetas, u_in.contiguous(), slots)
+                vals, ops, st = backend.engine.estimate_full(thetas, u_in.contiguous(), slots)
                 lp = self._log_prior_many(thetas)
                 for j, c in enumerate(full):
                     ch = chains[c]
@@ -386,19 +397,19 @@ class BatchedAPMSampler(object):
             if cached:
                 mi = kinds.get('cached_new', [])
                 if mi:
-                    Uprop[idx_t(mi)] = torch.randn(len(mi), n, N, generator=self._gen, **kw)
+                    Uprop[idx_t(mi)] = torch.randn(len(mi), n, N, generator=gen, **kw)
                 ell = kinds.get('cached_ell', [])
                 if ell:
                     fresh = [c for c in ell if pending[c][2]]
                     if fresh:
-                        V[idx_t(fresh)] = torch.randn(len(fresh), n, N, generator=self._gen, **kw)
+                        V[idx_t(fresh)] = torch.randn(len(fresh), n, N, generator=gen, **kw)
                     it = idx_t(ell)
                     phis = np.array([pending[c][1] for c in ell])
                     cs = torch.tensor(np.cos(phis), **kw)[:, None, None]
                     sn = torch.tensor(np.sin(phis), **kw)[:, None, None]
                     Uprop[it] = U.index_select(0, it) * cs + V.index_select(0, it) * sn       # mu.py:382
                 slots = [chains[c].cur_slot for c in cached]
-                vals, st = self.backend.engine.estimate_cached(slots, Uprop.index_select(0, idx_t(cached)).contiguous())
+                vals, st = backend.engine.estimate_cached(slots, Uprop.index_select(0, idx_t(cached)).contiguous())
                 lp = self._log_prior_many(np.stack([chains[c].theta for c in cached]))
                 for j, c in enumerate(cached):
                     ch = chains[c]
@@ -415,24 +426,66 @@ class BatchedAPMSampler(object):
                     chains[c].accept_u = False
         return rounds
 
+    def _run_groups(self, schedule, chains, traces, n_sample, bounds):
+        """One scheduler thread per chain group; in device mode each on its own CUDA stream (the group's engine is
+        bound to it, so the torch tensor work and the engine's kernels of a group stay ordered)."""
+        import threading
+        G = len(bounds) - 1
+        rounds, errors = [0] * G, [None] * G
+        if self.rng == 'device' and getattr(self, '_group_streams', None) is None:
+            self._group_streams = [self._torch.cuda.Stream(device=self.device) for _ in range(len(self.backends))]
+
+        def work(g):
+            lo, hi = bounds[g], bounds[g + 1]
+            try:
+                if self.rng == 'device':
+                    torch = self._torch
+                    eng = self.backends[g].engine
+                    stream = self._group_streams[g]
+                    with torch.cuda.device(self.device), torch.cuda.stream(stream):
+                        eng.use_torch_stream()        # stays bound to the group's stream (kept alive by the sampler)
+                        rounds[g] = schedule(self.backends[g], chains[lo:hi], traces[lo:hi], n_sample, self._gens[g])
+                        stream.synchronize()
+                else:
+                    rounds[g] = schedule(self.backends[g], chains[lo:hi], traces[lo:hi], n_sample, None)
+            except BaseException as e:       # re-raised in the caller's thread
+                errors[g] = e
+
+        threads = [threading.Thread(target=work, args=(g,), name='apm-group-%d' % g) for g in range(G)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errors:
+            if e is not None:
+                raise e
+        return max(rounds)
+
     def get_samples(self, theta_init, n_sample, theta_init_sampler=None):
         """theta_init: (B, n_theta), or None with theta_init_sampler(prng) -> theta drawing each chain's start
         from its own stream right after seeding (as the notebooks do, nb cell 14).  Returns dict(thetas
         (B, n_sample, P), n_reject (B, 2), n_cubic_ops (B,), n_full (B,), n_cached (B,), failed (B,) status
         codes, rounds)."""
         B = self.B
+        G = max(1, min(len(self.backends), B))
+        bounds = [(g * B) // G for g in range(G + 1)]            # contiguous chain groups, one per backend
+        local = {}
+        for g in range(G):
+            for c in range(bounds[g], bounds[g + 1]):
+                local[c] = c - bounds[g]
         if theta_init is None:
-            chains = [_Chain(c, self.seeds[c], np.zeros(self.P)) for c in range(B)]
+            chains = [_Chain(c, self.seeds[c], np.zeros(self.P), local[c]) for c in range(B)]
             for ch in chains:
                 ch.theta = np.array(theta_init_sampler(ch.prng), dtype=np.float64)
         else:
             theta_init = np.asarray(theta_init, dtype=np.float64)
-            chains = [_Chain(c, self.seeds[c], theta_init[c]) for c in range(B)]
+            chains = [_Chain(c, self.seeds[c], theta_init[c], local[c]) for c in range(B)]
         traces = np.full((B, n_sample, self.P), np.nan)
-        if self.rng == 'device':
-            rounds = self._schedule_device(chains, traces, n_sample)
+        schedule = self._schedule_device if self.rng == 'device' else self._schedule_parity
+        if G == 1:
+            rounds = schedule(self.backends[0], chains, traces, n_sample, self._gens[0])
         else:
-            rounds = self._schedule_parity(chains, traces, n_sample)
+            rounds = self._run_groups(schedule, chains, traces, n_sample, bounds)
         return dict(thetas=traces, n_reject=np.array([ch.n_reject for ch in chains]),
                     n_cubic_ops=np.array([ch.n_cubic_ops for ch in chains]),
                     n_full=np.array([ch.n_full for ch in chains]), n_cached=np.array([ch.n_cached for ch in chains]),

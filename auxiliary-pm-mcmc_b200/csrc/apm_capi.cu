@@ -60,6 +60,7 @@ struct apm_ctx {
     cudaStream_t aux_stream = nullptr;
     cudaStream_t launch_stream = nullptr;   // stream the launch helpers (run_chol, profiling events) currently target
     cudaEvent_t ev_k_ready = nullptr, ev_lk_done = nullptr;
+    cudaEvent_t ev_mix_fork = nullptr, ev_mix_join = nullptr;   // mixed Newton round: the minority form runs on aux_stream
     bool overlap_chol_k = true;
     bool factored_cov = true;   // chol(C) = L_K U^-T (n^3) instead of TRSM + SYRK + chol (7/3 n^3); APM_EXPLICIT_COV=1 -> reference formulation
     int n = 0, D = 0, np = 0, nb = 0, P = 0, kind = 0;
@@ -76,7 +77,7 @@ struct apm_ctx {
     // Cholesky factor is exactly what the factored covariance needs, so the converged chain skips the separate
     // SYRK + Cholesky of M' (and the chol(B) of that iteration).  APM_NO_HYBRID_NEWTON=1 disables it.
     bool hybrid_newton = true;
-    double pred_factor = 2.0;
+    double pred_factor = 0.15;   // measured optimum 0.1-0.2 (profiles/): a missed prediction costs a latency-bound covariance phase
     int *dMaskM = nullptr, *dMaskB = nullptr, *dDoneM = nullptr;
     bool newton_b_finishers = true;   // set by run_newton: some chain finished in a B-space round (needs the covariance phase)
     size_t mat = 0;  // np*np
@@ -113,6 +114,10 @@ struct apm_ctx {
     int lane_rc = 0;
     std::string lane_err;
     int64_t launches = 0;
+    // work actually executed by the DMMA kernel families, in units of n^3/3 flops per chain (apm_work_count): the
+    // Cholesky launches factor only the chains of their mask, the hybrid Newton skips whole factorisations
+    int64_t chol_units = 0, syrk_units = 0;
+    int newton_b_finisher_count = 0;   // set by run_newton: chains that finished in a B-space round
     std::vector<void*> allocs;
     // optional per-kernel CUDA-event timing (apm_profile): events bracket every launch on ctx->stream
     bool prof = false;
@@ -309,6 +314,8 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_k_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_lk_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_mix_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_mix_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
         set_err("apm_create: stream/event creation failed");
         apm_destroy(c);
@@ -363,7 +370,7 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
             v->prof = false;
             v->launches = 0;
             v->stream = v->copy_stream = v->aux_stream = nullptr;
-            v->ev_k_ready = v->ev_lk_done = v->copy_done = v->ev_fork = nullptr;
+            v->ev_k_ready = v->ev_lk_done = v->copy_done = v->ev_fork = v->ev_mix_fork = v->ev_mix_join = nullptr;
             v->u_staged = false;
             if (!getenv("APM_LANE_FLOW")) v->flow_grid = 0;   // per-step Cholesky launches: no spinning CTAs beside other lanes' kernels
             c->lanes.push_back(v);
@@ -372,6 +379,8 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
                 cudaStreamCreateWithFlags(&v->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&v->ev_k_ready, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&v->ev_lk_done, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&v->ev_mix_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&v->ev_mix_join, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&v->copy_done, cudaEventDisableTiming) != cudaSuccess) {
                 set_err("apm_create: lane stream/event creation failed");
                 apm_destroy(c);
@@ -394,6 +403,8 @@ extern "C" int apm_destroy(apm_ctx* c) {
         if (v->aux_stream) cudaStreamDestroy(v->aux_stream);
         if (v->ev_k_ready) cudaEventDestroy(v->ev_k_ready);
         if (v->ev_lk_done) cudaEventDestroy(v->ev_lk_done);
+        if (v->ev_mix_fork) cudaEventDestroy(v->ev_mix_fork);
+        if (v->ev_mix_join) cudaEventDestroy(v->ev_mix_join);
         if (v->copy_done) cudaEventDestroy(v->copy_done);
         delete v;
     }
@@ -403,6 +414,8 @@ extern "C" int apm_destroy(apm_ctx* c) {
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->ev_k_ready) cudaEventDestroy(c->ev_k_ready);
     if (c->ev_lk_done) cudaEventDestroy(c->ev_lk_done);
+    if (c->ev_mix_fork) cudaEventDestroy(c->ev_mix_fork);
+    if (c->ev_mix_join) cudaEventDestroy(c->ev_mix_join);
     if (c->copy_done) cudaEventDestroy(c->copy_done);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (void* p : c->allocs) cudaFree(p);
@@ -490,6 +503,18 @@ extern "C" int apm_profile_read(apm_ctx* c, int max_entries, char* names, double
     }
     return k;
 }
+extern "C" int apm_work_count(apm_ctx* c, int64_t* out, int reset) {
+    if (!c || !out) return APM_ERR_INVALID;
+    out[0] = c->chol_units;
+    out[1] = c->syrk_units;
+    if (reset) c->chol_units = c->syrk_units = 0;
+    for (apm_ctx* l : c->lanes) {
+        out[0] += l->chol_units;
+        out[1] += l->syrk_units;
+        if (reset) l->chol_units = l->syrk_units = 0;
+    }
+    return APM_OK;
+}
 extern "C" int64_t apm_launch_count(apm_ctx* c, int reset) {
     if (!c) return 0;
     int64_t v = c->launches;
@@ -560,7 +585,8 @@ static int build_K(apm_ctx* c, int B, int kind, double eps) {
 
 static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, const int* src_idx, double* dst,
                     long long dst_bs, const int* dst_idx, const double* scale, int add_identity, double* logdet_parts,
-                    const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr) {
+                    const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr, int units = -1) {
+    c->chol_units += units < 0 ? B : units;
     CholParams p;
     p.src = src; p.src_bs = src_bs; p.lds = c->np; p.src_idx = src_idx;
     p.dst = dst; p.dst_bs = dst_bs; p.ldd = c->np; p.dst_idx = dst_idx;
@@ -626,13 +652,14 @@ static NewtonVecs make_nv(apm_ctx* c) {
     nv.vs = c->np; nv.y = c->dy; nv.n = c->n; nv.np = c->np;
     nv.active = c->dActive; nv.iters = c->dIters; nv.status = c->dStatus; nv.n_active = c->dNActive;
     nv.tol = c->tol; nv.max_iters = c->max_iters;
-    nv.done_m = nullptr; nv.round_is_m = 0; nv.pred_factor = c->pred_factor;
+    nv.done_m = nullptr; nv.mask_b = nullptr; nv.mask_m = nullptr; nv.pred_factor = c->pred_factor;
     return nv;
 }
 
 // M' = I + Y'Y'^T (lower tiles, reversed coordinates) -> dLB, for chains in `mask` (null: all): Y' from chol(K) in the
 // slots and W^1/2 (see tile_engine.cuh "Factored posterior covariance")
-static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mask) {
+static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mask, int units = -1) {
+    c->syrk_units += units < 0 ? B : units;
     dim3 yg(c->np / 32, c->np / 32, B), yb(32, 8);
     prof_begin(c, KID_TRANSPOSE);
     k_make_Y<<<yg, yb, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->dVec[V_WS], c->np, c->dZ,
@@ -657,8 +684,18 @@ static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mas
 // Cholesky: twice the work) -- but chol(M) of a chain's LAST iteration is exactly what its posterior covariance needs
 // (C = L_K M^-1 L_K^T with the last W, lpa.py:107-112), so a chain whose next iteration is predicted to be the last
 // (k_newton_finish) runs it in M-space and skips both that iteration's chol(B) and the covariance phase: n^3/3 less.
-// Both forms give the same f_new up to rounding (~1e-14 relative); chains whose prediction fails simply iterate on.
+// Both forms give the same f_new up to rounding (~1e-14 relative); a chain whose prediction fails simply iterates on
+// (an unpredicted finish in B-space goes through the covariance phase as before).
 // lk_pending: chol(K) is still running on the aux stream (wait for ev_lk_done before the first M-space step).
+// restores the context's launch stream / Cholesky mode when a scope that redirected them ends (also on error returns)
+struct StreamSwap {
+    apm_ctx* c; cudaStream_t stream; int flow_grid;
+    explicit StreamSwap(apm_ctx* c_) : c(c_), stream(c_->stream), flow_grid(c_->flow_grid) {}
+    void to_aux() { c->stream = c->aux_stream; c->flow_grid = 0; }   // per-step Cholesky launches: no spinning CTAs beside the other form
+    void back() { c->stream = stream; c->flow_grid = flow_grid; }
+    ~StreamSwap() { back(); }
+};
+
 static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pending = false) {
     NewtonVecs nv = make_nv(c);
     const bool hybrid = dSlots != nullptr && c->factored_cov && c->hybrid_newton;
@@ -679,29 +716,57 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
         set_err("run_newton: n too large for the single-CTA triangular solve");
         return APM_ERR_INVALID;
     }
-    // A round is never mixed (small extra batches would be latency-bound): it runs in M-space for ALL active chains when
-    // at least half of them are predicted to finish in it (the others just pay n^3/3 more for that one iteration).
-    bool round_m = false;
+    // The form is chosen PER CHAIN (from its own diff only), so a chain's arithmetic never depends on its batch-mates:
+    // results are bit-identical whatever the batch composition, lane split or GPU count.  A round whose active chains
+    // disagree runs both forms, each under its mask (dMaskB / dMaskM, written by k_newton_finish).
     c->newton_b_finishers = false;
-    int n_act = B;
+    c->newton_b_finisher_count = 0;
+    const int* maskB = c->dActive;
+    const int* maskM = nullptr;
+    if (hybrid) {
+        nv.mask_b = c->dMaskB; nv.mask_m = c->dMaskM;
+        maskB = c->dMaskB; maskM = c->dMaskM;
+        prof_begin(c, KID_MISC);
+        k_fill_int<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dMaskB, 1, B);
+        APM_TRY(check_launch(c, "k_fill_int"));
+        CU_TRY(cudaMemsetAsync(c->dMaskM, 0, sizeof(int) * B, c->stream));
+    }
+    NewtonVecs nvB = nv, nvM = nv;     // k_trsv2 skips the chains outside nv.active
+    nvB.active = const_cast<int*>(maskB);
+    nvM.active = const_cast<int*>(maskM);
+    int n_act = B, nB = B, nM = 0;
     for (int it = 0; it < c->max_iters; it++) {
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_prep<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_prep"));
-        if (!round_m) {
+        // mixed round: the two forms touch disjoint chains, so the minority form runs beside the other on aux_stream
+        // (helpers launch on c->stream: it is swapped for the duration of that form)
+        StreamSwap swap(c);
+        cudaStream_t main_stream = c->stream;
+        const bool mixed = nB > 0 && nM > 0 && c->overlap_chol_k && c->aux_stream != nullptr;
+        const bool b_on_aux = mixed && nB <= nM, m_on_aux = mixed && !b_on_aux;
+        if (mixed) {
+            CU_TRY(cudaEventRecord(c->ev_mix_fork, main_stream));
+            CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_mix_fork, 0));
+        }
+        if (nB > 0) {
+            if (b_on_aux) swap.to_aux();
             // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b))
-            APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t));
+            APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t, maskB));
             // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
             APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB));
+                             nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB, nB));
             // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
             prof_begin(c, KID_TRSV);
             k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
-                                                      (long long)c->nb * TB * TB, nv);
+                                                      (long long)c->nb * TB * TB, nvB);
             APM_TRY(check_launch(c, "k_trsv2"));
             // f_new = K a                                              (lpa.py:95)
-            APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew));
-        } else {
+            APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew, maskB));
+            swap.back();
+        }
+        if (nM > 0) {
+            if (m_on_aux) swap.to_aux();
             if (lk_pending) {
                 CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
                 lk_pending = false;
@@ -709,36 +774,46 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
             // t' = reversed L_K^T b
             prof_begin(c, KID_MATVEC);
             k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, nv.bvec, c->np,
-                                                                nv.t, c->np, nullptr, c->dStatus, c->dActive, 1);
+                                                                nv.t, c->np, nullptr, c->dStatus, maskM, 1);
             APM_TRY(check_launch(c, "k_lt_matvec"));
             // L' = chol(M'), M' = P (I + L_K^T W L_K) P
-            APM_TRY(run_build_mprime(c, B, dSlots, c->dActive));
+            APM_TRY(run_build_mprime(c, B, dSlots, maskM, nM));
             APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_C, c->dActive, c->dInvB));
+                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, nM));
             // s' = M'^-1 t'
             prof_begin(c, KID_TRSV);
             k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
-                                                      (long long)c->nb * TB * TB, nv);
+                                                      (long long)c->nb * TB * TB, nvM);
             APM_TRY(check_launch(c, "k_trsv2"));
             // mu~ = reversed s' (-> slot), f_new = L_K mu~
             prof_begin(c, KID_MATVEC);
             k_l_matvec_rev<<<dim3(c->np / 32, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->np, nv.s,
                                                                        c->np, nv.fnew, c->np, c->dSlotMt, c->np, dSlots, c->dStatus,
-                                                                       c->dActive);
+                                                                       maskM);
             APM_TRY(check_launch(c, "k_l_matvec_rev"));
+            swap.back();
         }
-        if (hybrid) CU_TRY(cudaMemsetAsync(c->dNActive + 1, 0, sizeof(int), c->stream));
-        nv.round_is_m = round_m ? 1 : 0;
+        if (mixed) {
+            CU_TRY(cudaEventRecord(c->ev_mix_join, c->aux_stream));
+            CU_TRY(cudaStreamWaitEvent(main_stream, c->ev_mix_join, 0));
+        }
+        if (hybrid) CU_TRY(cudaMemsetAsync(c->dNActive + 1, 0, 2 * sizeof(int), c->stream));
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_finish<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_finish"));
-        CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
-        if (!round_m && c->hNActive[0] < n_act) c->newton_b_finishers = true;   // somebody finished in B-space
         n_act = c->hNActive[0];
+        if (hybrid) {
+            nM = c->hNActive[1];                                    // still active and predicted to finish next
+            c->newton_b_finisher_count += c->hNActive[2];           // finished in a B-space round: need the covariance phase
+        } else {
+            nM = 0;
+        }
+        nB = n_act - nM;
         if (n_act <= 0) break;
-        round_m = hybrid && 2 * c->hNActive[1] >= n_act;
     }
+    c->newton_b_finishers = !hybrid || c->newton_b_finisher_count > 0;
     return APM_OK;
 }
 
@@ -846,10 +921,11 @@ static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots, const i
         todo = c->dMaskB;
     }
     if (need_cov) {
-        APM_TRY(run_build_mprime(c, B, dSlots, todo));
+        const int units = todo ? c->newton_b_finisher_count : B;
+        APM_TRY(run_build_mprime(c, B, dSlots, todo, units));
         // L' = chol(M') in place (M' has eigenvalues >= 1: cannot fail for finite input)
         APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                         nullptr, APM_CHAIN_CHOL_C, todo));
+                         nullptr, APM_CHAIN_CHOL_C, todo, nullptr, units));
     }
     // V = anti-transpose of L' into the slot's L_C buffer; mu~ = L_K^T a.  The importance-sampling tail works with
     // (L_K, V, mu, mu~) directly, so the n^3/3 triangular solve for the explicit L_C = L_K V^-1 is only run if somebody

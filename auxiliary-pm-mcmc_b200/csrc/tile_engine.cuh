@@ -99,10 +99,17 @@ __device__ __forceinline__ void gemm_nt_64x64(Acc& acc, const double* __restrict
 
 // acc -= X X^T with X = the 64x64 tile in shared memory (stride TSP, conflict-free fragment loads): the
 // contribution of a freshly solved panel block L_ik to its own diagonal block.
+// Only the lower triangle of the diagonal block is ever read (potrf64_smem), so the warp that owns the upper-right
+// 32x32 quadrant does nothing and the two diagonal warps skip their strictly upper 8x8 tiles: 36 of 64 tiles.
+#ifndef APM_SYRK_LOWER
+#define APM_SYRK_LOWER 1
+#endif
 __device__ __forceinline__ void syrk_from_tile(Acc& acc, const double* Ts) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
+    if (APM_SYRK_LOWER && wm < wn) return;
+    const bool diag = APM_SYRK_LOWER && wm == wn;
     const double* a_s = Ts + (wm * 32 + g) * TSP + t;
     const double* b_s = Ts + (wn * 32 + g) * TSP + t;
 #pragma unroll 4
@@ -115,7 +122,8 @@ __device__ __forceinline__ void syrk_from_tile(Acc& acc, const double* Ts) {
 #pragma unroll
         for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) dmma884(acc.v[mi][ni][0], acc.v[mi][ni][1], a[mi], b[ni]);
+            for (int ni = 0; ni < 4; ni++)
+                if (mi >= ni || !diag) dmma884(acc.v[mi][ni][0], acc.v[mi][ni][1], a[mi], b[ni]);
     }
 }
 

@@ -191,6 +191,9 @@ __global__ void k_make_Y(const double* __restrict__ LK, long long lk_bs, const i
     const int b = blockIdx.z;
     if (status[b] != 0 || (mask && !mask[b])) return;
     const int k0 = blockIdx.y * 32, i0 = blockIdx.x * 32;      // L_K rows k0.., columns i0..
+    // k_syrk_rev starts the k-range of row block i' at the block that holds the triangle's edge: 64-blocks strictly above
+    // L_K's block diagonal are never read, so their zeros are not written either
+    if ((i0 >> 6) > (k0 >> 6)) return;
     const double* L = LK + chain_index(lk_idx, b) * lk_bs;
     double* Yb = Y + (long long)b * y_bs;
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -222,12 +225,15 @@ struct NewtonVecs {
     long long vs;   // stride between chains (= np)
     const double* y;
     int n, np;
-    int* active; int* iters; int* status; int* n_active;   // n_active[0]: still-active chains, [1]: of those, predicted-last
+    // n_active[0]: still-active chains, [1]: of those, predicted to finish in the next iteration, [2]: chains that
+    // finished in this round in the B-space form
+    int* active; int* iters; int* status; int* n_active;
     double tol; int max_iters;
-    // hybrid Newton (run_newton): a round runs in the reference's B-space form or, when most chains are predicted to
-    // finish in it, in "M-space"; done_m[b] = the chain's last iteration was an M-space one (null: not hybrid)
-    int* done_m;
-    int round_is_m; double pred_factor;
+    // hybrid Newton (run_newton): every chain runs an iteration in the reference's B-space form or, when the iteration
+    // is predicted to be its last, in "M-space"; mask_b / mask_m = the form of chain b's current (then next) iteration,
+    // done_m[b] = the chain's last iteration was an M-space one (all null: not hybrid)
+    int* done_m; int* mask_b; int* mask_m;
+    double pred_factor;
 };
 
 // v = exp(-f^2/2 - log_ndtr(y f) - log(2 pi)/2); grad = v y; W = v^2 + grad f; Ws = sqrt(W); b = W f + grad
@@ -454,6 +460,7 @@ __global__ void __launch_bounds__(256) k_newton_finish(NewtonVecs nv) {
         if (threadIdx.x == 0) {
             nv.active[b] = 0;
             atomicSub(nv.n_active, 1);
+            if (nv.done_m) nv.mask_b[b] = nv.mask_m[b] = 0;
         }
         return;
     }
@@ -490,9 +497,20 @@ __global__ void __launch_bounds__(256) k_newton_finish(NewtonVecs nv) {
         }
         if (nv.done_m) {
             // Newton converges quadratically here (diff_{k+1} ~ 0.6-1.4 diff_k^2 on GP-probit data, profiles/): the next
-            // iteration is predicted to be the chain's last one if pred_factor * diff^2 < tol.  A wrong guess only costs time.
-            if (!still) nv.done_m[b] = nv.round_is_m;
-            else if (nv.pred_factor * diff * diff < nv.tol) atomicAdd(nv.n_active + 1, 1);
+            // iteration is predicted to be the chain's last one if pred_factor * diff^2 < tol.  A wrong guess only costs
+            // time: an M-space iteration that does not finish is n^3/3 more work, a finish that was not predicted pays the
+            // separate covariance phase -- the latter is the expensive one (latency-bound on few chains), hence factor < 1.
+            const int was_m = nv.mask_m[b];
+            if (!still) {
+                nv.done_m[b] = was_m;
+                nv.mask_b[b] = nv.mask_m[b] = 0;
+                if (!was_m) atomicAdd(nv.n_active + 2, 1);
+            } else {
+                const int next_m = nv.pred_factor * diff * diff < nv.tol ? 1 : 0;
+                nv.mask_m[b] = next_m;
+                nv.mask_b[b] = 1 - next_m;
+                if (next_m) atomicAdd(nv.n_active + 1, 1);
+            }
         }
     }
 }

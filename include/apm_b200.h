@@ -215,6 +215,12 @@ int apm_profile_read(apm_ctx* ctx, int max_entries, char* names, double* ms, int
  * it as gpu_launches). */
 int64_t apm_launch_count(apm_ctx* ctx, int reset);
 
+/* Work the DMMA kernel families actually executed since creation / the last reset, in units of n^3/3 flops per chain:
+ * out[0] = chain-Choleskys factored by k_chol_* (masked-out chains and the factorisations the hybrid Newton
+ * iteration skips are not counted), out[1] = M' = I + Y'Y'^T builds by k_syrk_rev.  bench.py's per-kernel roofline
+ * uses these instead of the reference's nominal operation count (lpa.py:92, 111-112; est.py:206, 209). */
+int apm_work_count(apm_ctx* ctx, int64_t* out, int reset);
+
 /* Tuning aid: average milliseconds of one batched Cholesky of the context's current K matrices (B chains,
  * after apm_kernel_build) into slots 0..B-1.  mode 0 = default path, 1 = per-step launches. */
 int apm_dev_chol_bench(apm_ctx* ctx, int B, int reps, int mode, double* ms_out);

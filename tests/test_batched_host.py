@@ -49,6 +49,27 @@ def test_batched_chains_match_single_chain_and_reference(method):
     assert out['rounds'] >= n_iter
 
 
+@pytest.mark.parametrize('method', ['ess+rdss', 'pmmh'])
+def test_chain_groups_do_not_change_the_chains(method):
+    """A list of backends = chain groups on their own scheduler threads: every chain's trace, reject counts and
+    cubic-op counts equal those of the single-group run."""
+    g = load_golden('samplers')
+    X, y = g['X'], g['y']
+    N, n_iter = 4, 60
+    seeds = [1000 + N, 77, 4242, 5, 6]
+    mk = lambda backends: batched.BatchedAPMSampler(backends, X.shape[0], N, 2, method, batched.make_log_prior(X.shape[1], False),
+                                                    seeds, prop_scales=[0.5, 0.5], slice_width=1.)
+    init = lambda prng: synth.draw_theta_prior(prng, X.shape[1], ard=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        one = mk(OracleBackend(X, y)).get_samples(None, n_iter, theta_init_sampler=init)
+        two = mk([OracleBackend(X, y), OracleBackend(X, y)]).get_samples(None, n_iter, theta_init_sampler=init)
+    assert np.all(two['failed'] == 0)
+    for k in ('thetas', 'n_reject', 'n_cubic_ops', 'n_full', 'n_cached'):
+        assert np.array_equal(one[k], two[k]), k
+    assert first_divergence(two['thetas'][0], g['%s_N%d_thetas' % (method, N)][:n_iter]) is None
+
+
 def test_shard_chains_partition():
     from apm_b200.distributed import shard_chains
     for n, w in [(10, 1), (10, 3), (256, 8), (5, 8)]:

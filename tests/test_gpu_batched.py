@@ -47,3 +47,33 @@ def test_batched_device_rng_mode():
     # chains are distinct and moved
     assert np.std(out['thetas'][:, -1, 0]) > 0
     eng.close()
+
+
+def test_chain_groups_on_two_contexts_match_single_group():
+    """Two engine contexts driven by two scheduler threads (chain groups): identical per-chain traces in parity mode,
+    chain 0 still reproduces the reference's golden chain; device-RNG mode runs on per-group streams."""
+    import torch
+    g = load_golden('samplers')
+    X, y = g['X'], g['y']
+    N, n_iter, method = 4, 150, 'ess+rdss'
+    seeds = [1000 + N] + [50 + c for c in range(7)]
+    B = len(seeds)
+    engs = [_capi.Engine(X, y, kernel='iso', max_chains=B, n_slots=2 * B, max_nimp=N) for _ in range(3)]
+    mk = lambda backends, **kw: batched.BatchedAPMSampler(backends, X.shape[0], N, 2, method, batched.make_log_prior(X.shape[1], False),
+                                                          seeds, prop_scales=[0.5, 0.5], **kw)
+    init = lambda prng: synth.draw_theta_prior(prng, X.shape[1], ard=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        one = mk(batched.EngineBackend(engs[0])).get_samples(None, n_iter, theta_init_sampler=init)
+        two = mk([batched.EngineBackend(engs[1]), batched.EngineBackend(engs[2])]).get_samples(None, n_iter, theta_init_sampler=init)
+    assert np.all(two['failed'] == 0)
+    for k in ('thetas', 'n_reject', 'n_cubic_ops', 'n_full', 'n_cached'):
+        assert np.array_equal(one[k], two[k]), k
+    assert first_divergence(two['thetas'][0], g['%s_N%d_thetas' % (method, N)][:n_iter]) is None
+    dev = torch.device('cuda', 0)
+    drv = mk([batched.EngineBackend(engs[1]), batched.EngineBackend(engs[2])], rng='device', device=dev)
+    out = drv.get_samples(np.tile(g['%s_N%d_thetas' % (method, N)][0], (B, 1)), 20)
+    assert np.all(out['failed'] == 0) and np.all(np.isfinite(out['thetas']))
+    assert np.std(out['thetas'][:, -1, 0]) > 0
+    for e in engs:
+        e.close()

@@ -213,6 +213,59 @@ def test_lanes_match_single_path():
     eng.close()
 
 
+def _engine_with_env(env, *args, **kw):
+    """apm_create reads its tuning switches from the environment: set them only around the constructor."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return _capi.Engine(*args, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_hybrid_newton_matches_reference_form_and_is_batch_independent():
+    """The fused FULL estimate runs the iteration predicted to be a chain's last in M-space (its Cholesky factor is the
+    one the covariance needs).  Same estimates, iteration counts and caches as the reference's B-space form
+    (APM_NO_HYBRID_NEWTON) up to rounding; a wrong prediction (forced by extreme APM_PRED_FACTOR values) only costs
+    time; the form is chosen per chain, so a chain's bits do not depend on its batch-mates."""
+    n, D, N, B = 200, 4, 6, 40
+    X, y, th = synth.make_dataset(n, D, seed=21)
+    rs = np.random.RandomState(5)
+    thetas = th[None] + 0.8 * rs.normal(size=(B, D + 1))          # spread: 3 to 6 Newton iterations
+    u = rs.normal(size=(B, n, N))
+    kw = dict(kernel='ard', max_chains=B, n_slots=B, max_nimp=N)
+    ref_eng = _engine_with_env({'APM_NO_HYBRID_NEWTON': '1'}, X, y, **kw)
+    ref, ops_ref, st_ref = ref_eng.estimate_full(thetas, u, np.arange(B))
+    assert np.all(st_ref == 0) and len(set(ops_ref.tolist())) > 1
+    u2 = rs.normal(size=(B, n, N))
+    cref, _ = ref_eng.estimate_cached(np.arange(B), u2)
+    for env in ({}, {'APM_PRED_FACTOR': '1e-6'}, {'APM_PRED_FACTOR': '1e6'}):
+        eng = _engine_with_env(env, X, y, **kw)
+        val, ops, st = eng.estimate_full(thetas, u, np.arange(B))
+        assert np.all(st == 0) and np.array_equal(ops, ops_ref), env
+        assert np.max(np.abs(val - ref) / np.abs(ref)) < 1e-12, env
+        cval, _ = eng.estimate_cached(np.arange(B), u2)
+        assert np.max(np.abs(cval - cref) / np.abs(cref)) < 1e-12, env
+        Kc, Cc, f, ld = eng.slot_export(3)
+        Kr, Cr, fr, ldr = ref_eng.slot_export(3)
+        assert np.max(np.abs(Cc - Cr)) < 1e-11 * np.max(np.abs(Cr)) and np.max(np.abs(f - fr)) < 1e-11
+        if not env:
+            # batch composition: one by one, reversed order and in two halves -> the same bits per chain
+            one = np.array([eng.estimate_full(thetas[b:b + 1], u[b:b + 1], [b])[0][0] for b in range(0, B, 7)])
+            assert np.array_equal(one, val[::7])
+            rev, _, _ = eng.estimate_full(thetas[::-1].copy(), u[::-1].copy(), np.arange(B))
+            assert np.array_equal(rev[::-1], val)
+            half, _, _ = eng.estimate_full(thetas[B // 2:], u[B // 2:], np.arange(B // 2))
+            assert np.array_equal(half, val[B // 2:])
+        eng.close()
+    ref_eng.close()
+
+
 def test_device_resident_u_and_slot_roundtrip():
     import torch
     X, y, th = synth.make_dataset(150, 4, seed=9)
