@@ -364,9 +364,9 @@ def run_gpu_arm(args):
             'bound': 'tensor', 'kernel': dom, 'achieved': d['achieved'], 'peak': peak_dmma, 'unit': 'TFLOP/s',
             'frac': d['frac'],
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_chol_dataflow launch (256 chains, n = 768) from the
-            # `ncu --set full` capture summarised in profiles/r1c_ncu_top_kernels_full.md: 4.21 GB + 1.20 GB
+            # `ncu --set full` capture summarised in profiles/r1e_ncu_top_kernels_full.md: 4.21 GB + 1.20 GB
             'traffic': 5.41e9 if (dom == 'k_chol' and n == 768 and B == 256) else None,
-            'traffic_note': 'bytes per launch from ncu (profiles/r1c_ncu_top_kernels_full.md); minimum (read K, write L) '
+            'traffic_note': 'bytes per launch from ncu (profiles/r1e_ncu_top_kernels_full.md); minimum (read K, write L) '
                             'is 1.28 GB, the blocked left-looking operand traffic with a working set > L2 is 4.7 GB',
             'achieved_per_launch_gflop': flops[dom] / d['launches'] / 1e9,
             'avg_launch_ms': d['ms_total'] / d['launches'],
@@ -430,7 +430,7 @@ def main():
     ap.add_argument('--impl', default='apm_b200', choices=['apm_b200', 'reference'])
     ap.add_argument('--chains', type=int, default=0, help='chains per GPU (default 256)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--apm-iters', type=int, default=30, help='iterations of the batched ESS+RDSS sampler leg (chains drain at the end of a run: short runs understate the steady state)')
+    ap.add_argument('--apm-iters', type=int, default=100, help='iterations of the batched ESS+RDSS sampler leg (chains drain at the end of a run: short runs understate the steady state)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
