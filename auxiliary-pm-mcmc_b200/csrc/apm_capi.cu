@@ -91,6 +91,7 @@ struct apm_ctx {
     std::vector<char> slot_mode;
     double* dLdB = nullptr;
     int *dFlowCounter = nullptr, *dFlowProgress = nullptr, *dFlowSkip = nullptr;
+    int* dSmSem = nullptr; int sem_limit = 0;   // per-SM GEMM tokens of the Cholesky tasks (0: off), APM_GEMM_TOKENS
     int flow_grid = 0;        // persistent grid of k_chol_dataflow (SMs x occupancy); 0 = per-step launches
     int flow_group = 1 << 20; // chains per scheduling group (default: all chains = step-major order)
     double *dSymvDirect = nullptr, *dSymvPart = nullptr;   // scratch of the symmetric mat-vec
@@ -294,6 +295,9 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
     A(dev_alloc(c, &c->dFlowCounter, 4 * (MAX_LANES + 1)));
     A(dev_alloc(c, &c->dFlowProgress, B * (size_t)c->nb));
     A(dev_alloc(c, &c->dFlowSkip, B));
+    A(dev_alloc(c, &c->dSmSem, 1024));
+    cudaMemset(c->dSmSem, 0, 1024 * sizeof(int));
+    if (getenv("APM_GEMM_TOKENS")) c->sem_limit = atoi(getenv("APM_GEMM_TOKENS"));
     if (rc != APM_OK) {
         apm_destroy(c);
         return rc;
@@ -598,6 +602,7 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     p.status = c->dStatus; p.fail_code = fail_code;
     p.active = active;
     p.nchains = B;
+    p.sm_sem = c->sem_limit > 0 ? c->dSmSem : nullptr; p.sem_limit = c->sem_limit;
     cudaStream_t st = c->launch_stream ? c->launch_stream : c->stream;
     if (c->flow_grid > 0 && st == c->stream) {
         // single cooperative launch (all CTAs co-resident: tasks wait on each other through progress counters)

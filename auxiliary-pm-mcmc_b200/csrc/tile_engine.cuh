@@ -492,7 +492,34 @@ struct CholParams {
     int* status; int fail_code;                 // per-chain status (skip chain if non-zero)
     const int* active;                          // optional Newton mask (skip chain if 0)
     int nchains;
+    // per-SM "GEMM token" semaphore (null: off): at most sem_limit of an SM's co-resident CTAs run their panel GEMM at
+    // the same time, which staggers the phases of equally long tasks (see gemm_token_acquire)
+    int* sm_sem; int sem_limit;
 };
+
+// Co-resident CTAs of this kernel work on equally long tasks and, once started together, stay in lock-step: all of
+// them in the DMMA-bound panel GEMM (sharing the pipe three ways), then all of them in the latency-bound staging /
+// triangular-solve phases (pipe idle).  A counting semaphore per SM (global memory, indexed by %smid) lets only
+// sem_limit CTAs into the GEMM phase at once, so the others run their solve phases beside it.  Token holders never
+// wait on anything, so there is no deadlock; acquire/release are one thread + the block barriers that exist anyway.
+__device__ __forceinline__ unsigned smid() {
+    unsigned v;
+    asm volatile("mov.u32 %0, %%smid;\n" : "=r"(v));
+    return v;
+}
+__device__ __forceinline__ void gemm_token_acquire(int* sem, int limit) {
+    if (threadIdx.x == 0) {
+        int* s = sem + smid();
+        while (atomicAdd(s, 1) >= limit) {
+            atomicSub(s, 1);
+            __nanosleep(400);
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void gemm_token_release(int* sem) {   // call after a block barrier that ends the GEMM
+    if (threadIdx.x == 0) atomicSub(sem + smid(), 1);
+}
 
 // Dependency tracking of the single-launch ("dataflow") variant: progress[chain][row] = number of finished
 // column blocks of that block row; a task spins (one thread, acquire loads) until its operands exist.
@@ -588,7 +615,10 @@ __device__ __forceinline__ void chol_task(const CholParams& p, const CholFlow& f
         prefetch_tile_l2(dst + (size_t)k * TB * p.ldd + k * TB, p.ldd);
         if (k == 0) prefetch_tile_l2(src + (size_t)i * TB * p.lds + i * TB, p.lds);
         else prefetch_tile_l2(dii, p.ldd);
+        const bool token = p.sm_sem != nullptr && k > 0;
+        if (token) gemm_token_acquire(p.sm_sem, p.sem_limit);
         gemm_nt_64x64<true>(acc, dst + (size_t)i * TB * p.ldd, p.ldd, dst + (size_t)k * TB * p.ldd, p.ldd, k * TB, smem);
+        if (token) gemm_token_release(p.sm_sem);
         PHASE_MARK(1);  // panel GEMM
         tile_put_acc(s.Ts, acc);
 #if !(APM_SKEL & 8)
