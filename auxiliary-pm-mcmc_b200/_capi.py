@@ -14,7 +14,7 @@ EXPORTS = [
     'apm_version', 'apm_last_error', 'apm_create', 'apm_destroy', 'apm_set_stream', 'apm_synchronize',
     'apm_set_overlap', 'apm_set_newton', 'apm_set_approximation', 'apm_ep', 'apm_get_info', 'apm_kernel_build', 'apm_kernel_grad', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
-    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_work_count', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
+    'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_work_count', 'apm_create_companion', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
 ]
 
 KERNEL_ISO, KERNEL_ARD = 0, 1
@@ -43,6 +43,7 @@ def lib():
     L.apm_create.argtypes = [vp, vp, ct.c_int, ct.c_int, ct.c_int, ct.c_double, ct.c_int, ct.c_int, ct.c_int,
                              ct.c_int, ct.POINTER(vp)]
     L.apm_destroy.argtypes = [vp]
+    L.apm_create_companion.argtypes = [vp, ct.c_int, ct.c_int, ct.POINTER(vp)]
     L.apm_set_stream.argtypes = [vp, ct.c_uint64]
     L.apm_synchronize.argtypes = [vp]
     L.apm_set_overlap.argtypes = [vp, ct.c_int]
@@ -127,7 +128,24 @@ class Engine(object):
         self._h = h
         self._L = L
 
+    def companion(self, max_chains=None, max_nimp=None):
+        """A context of its own (streams, workspaces) that shares this engine's cache slots: cached estimates on it
+        may run while another thread is inside estimate_full on this engine (different slots).  See
+        include/apm_b200.h:apm_create_companion."""
+        comp = object.__new__(Engine)
+        comp.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ('_h', '_companions')})
+        comp.max_chains = int(max_chains) if max_chains is not None else self.max_chains
+        comp.max_nimp = int(max_nimp) if max_nimp is not None else self.max_nimp
+        h = ct.c_void_p()
+        check(self._L.apm_create_companion(self._h, comp.max_chains, comp.max_nimp, ct.byref(h)))
+        comp._h = h
+        comp._parent = self                      # keeps the slot owner alive
+        self.__dict__.setdefault('_companions', []).append(comp)
+        return comp
+
     def close(self):
+        for comp in self.__dict__.pop('_companions', []):
+            comp.close()
         if getattr(self, '_h', None):
             self._L.apm_destroy(self._h)
             self._h = None

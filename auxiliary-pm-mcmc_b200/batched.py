@@ -90,7 +90,8 @@ class BatchedAPMSampler(object):
     """
 
     def __init__(self, backend, n_data, n_imp, n_theta, method, log_prior, seeds, prop_scales=None, slice_width=1.,
-                 max_slice_iters=1000, rng='parity', device=None, full_batch_frac=0.8):
+                 max_slice_iters=1000, rng='parity', device=None, full_batch_frac=0.8, async_full=False,
+                 async_batch_frac=0.5):
         if method not in ('mi+mh', 'ess+mh', 'mi+rdss', 'ess+rdss', 'pmmh'):
             raise ValueError('unknown method %r' % method)
         if rng not in ('parity', 'device'):
@@ -110,6 +111,11 @@ class BatchedAPMSampler(object):
         # scheduling policy: FULL estimates are latency-bound for small batches, so they are held back until this
         # fraction of the live chains is waiting for one (or nobody has a cheap CACHED request left)
         self.full_batch_frac = float(full_batch_frac)
+        # device-RNG mode only: FULL estimates run on a worker thread (own CUDA stream) while this thread keeps serving
+        # the CACHED requests of the other chains through a companion context that shares the engine's cache slots
+        self.async_full = bool(async_full)
+        self.async_batch_frac = float(async_batch_frac)
+        self._async_state = None
         self._gens = [None] * len(self.backends)
         if rng == 'device':
             import torch
@@ -426,6 +432,138 @@ class BatchedAPMSampler(object):
                     chains[c].accept_u = False
         return rounds
 
+
+    def _schedule_device_async(self, backend, chains, traces, n_sample, gen=None):
+        """Device-RNG scheduler with asynchronous FULL estimates.  A FULL round is GPU-throughput-bound and takes ~10 ms;
+        meanwhile the chains that are in their u-update only need CACHED estimates (O(n^2 N), latency-bound) and Python
+        bookkeeping.  The FULL call therefore runs on a worker thread and its own stream (ctypes releases the GIL), and
+        this thread keeps scheduling CACHED rounds on a companion context (apm_create_companion: same cache slots,
+        own workspaces).  A chain is never in both: the FULL call writes the proposal slots of its chains, the CACHED
+        calls read the current slots of the others."""
+        import concurrent.futures
+        torch = self._torch
+        B, n, N = len(chains), self.n, self.N
+        gen = self._gen if gen is None else gen
+        eng = backend.engine
+        if self._async_state is None:
+            self._async_state = {}
+        st_ = self._async_state.get(id(eng))             # one companion / stream / worker per engine (chain group)
+        if st_ is None:
+            st_ = dict(engine=eng, comp=eng.companion(), stream=torch.cuda.Stream(device=self.device),
+                       pool=concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix='apm-full'))
+            self._async_state[id(eng)] = st_
+        comp, full_stream, pool = st_['comp'], st_['stream'], st_['pool']
+        comp.use_torch_stream()                          # CACHED rounds: this thread's current stream
+        eng.set_stream(full_stream.cuda_stream)          # FULL rounds: the worker's stream
+        kw = dict(dtype=torch.float64, device=self.device)
+        U = torch.zeros(B, n, N, **kw)
+        V = torch.zeros(B, n, N, **kw)
+        Uprop = torch.zeros(B, n, N, **kw)
+        for ch in chains:
+            ch.accept_u = False
+        gens = [self._run_chain_device(ch, n_sample, traces[c]) for c, ch in enumerate(chains)]
+        pending = {c: next(g) for c, g in enumerate(gens)}
+        inflight = None                                  # (future, chain list, thetas, log priors)
+        rounds = 0
+        import time
+        stats = dict(full_calls=0, full_chains=0, cached_calls=0, cached_chains=0, t_submit=0., t_flight=0., t_total=time.perf_counter())
+        self.async_stats = stats                         # of the last (group's) run: scheduling diagnostics
+
+        def idx_t(lst):
+            return torch.tensor(lst, dtype=torch.long, device=self.device)
+
+        def run_full(thetas, u_in, slots, ready):
+            with torch.cuda.device(self.device), torch.cuda.stream(full_stream):
+                full_stream.wait_event(ready)            # u_in was gathered on the scheduler's stream
+                return eng.estimate_full(thetas, u_in, slots)
+
+        def harvest(fl):
+            fut, full, thetas, lp, _keep = fl
+            vals, ops, st = fut.result()
+            results = {}
+            for j, c in enumerate(full):
+                ch = chains[c]
+                ch.n_full += 1
+                if st[j] != 0:
+                    results[c] = ChainFailure(int(st[j]))
+                else:
+                    ch.n_cubic_ops += int(ops[j])
+                    results[c] = float(vals[j]) + float(lp[j])
+            return results
+
+        def finish_round(results):
+            for c in results:
+                pending.pop(c, None)
+            pending.update(self._resume(chains, gens, results))
+            acc = [c for c in results if chains[c].accept_u]
+            if acc:
+                ia = idx_t(acc)
+                U[ia] = Uprop.index_select(0, ia)
+                for c in acc:
+                    chains[c].accept_u = False
+
+        def is_cached(r):
+            return r[0] in ('cached_new', 'cached_ell')
+
+        while pending or inflight is not None:
+            rounds += 1
+            # --- a finished FULL call is harvested as soon as it is seen (with no CACHED work left: wait for it); its
+            # chains are resumed at once so that those which need another FULL estimate join the next call
+            if inflight is not None and (inflight[0].done() or not any(is_cached(r) for r in pending.values())):
+                res = harvest(inflight)
+                stats['t_flight'] += time.perf_counter() - stats['t_submit']
+                inflight = None
+                finish_round(res)
+            # --- submit the next FULL call: enough chains are waiting for one, or nobody has CACHED work left
+            if inflight is None:
+                full = [c for c, r in pending.items() if not is_cached(r)]
+                if full and (len(full) >= self.async_batch_frac * len(pending) or len(full) == len(pending)):
+                    newu = [c for c in full if pending[c][0] == 'full_newu']
+                    if newu:
+                        U[idx_t(newu)] = torch.randn(len(newu), n, N, generator=gen, **kw)
+                    thetas = np.stack([pending[c][1] for c in full])
+                    slots = [chains[c].prop_slot for c in full]
+                    u_in = U.index_select(0, idx_t(full)).contiguous()
+                    ready = torch.cuda.Event()
+                    ready.record()
+                    inflight = (pool.submit(run_full, thetas, u_in, slots, ready), full, thetas, None, u_in)
+                    stats['t_submit'] = time.perf_counter()
+                    stats['full_calls'] += 1
+                    stats['full_chains'] += len(full)
+                    inflight = inflight[:3] + (self._log_prior_many(thetas), u_in)     # while the call runs
+                    for c in full:
+                        del pending[c]
+            # --- CACHED requests of the chains that are not in flight
+            cached = [c for c, r in pending.items() if is_cached(r)]
+            if cached:
+                results = {}
+                mi = [c for c in cached if pending[c][0] == 'cached_new']
+                if mi:
+                    Uprop[idx_t(mi)] = torch.randn(len(mi), n, N, generator=gen, **kw)
+                ell = [c for c in cached if pending[c][0] == 'cached_ell']
+                if ell:
+                    fresh = [c for c in ell if pending[c][2]]
+                    if fresh:
+                        V[idx_t(fresh)] = torch.randn(len(fresh), n, N, generator=gen, **kw)
+                    it = idx_t(ell)
+                    phis = np.array([pending[c][1] for c in ell])
+                    cs = torch.tensor(np.cos(phis), **kw)[:, None, None]
+                    sn = torch.tensor(np.sin(phis), **kw)[:, None, None]
+                    Uprop[it] = U.index_select(0, it) * cs + V.index_select(0, it) * sn       # mu.py:382
+                slots = [chains[c].cur_slot for c in cached]
+                vals, st = comp.estimate_cached(slots, Uprop.index_select(0, idx_t(cached)).contiguous())
+                stats['cached_calls'] += 1
+                stats['cached_chains'] += len(cached)
+                lp = self._log_prior_many(np.stack([chains[c].theta for c in cached]))
+                for j, c in enumerate(cached):
+                    chains[c].n_cached += 1
+                    results[c] = ChainFailure(int(st[j])) if st[j] != 0 else float(vals[j]) + float(lp[j])
+                finish_round(results)
+        torch.cuda.current_stream(self.device).synchronize()
+        stats['t_total'] = time.perf_counter() - stats['t_total']
+        eng.use_torch_stream()                           # hand the engine back on the caller's stream
+        return rounds
+
     def _run_groups(self, schedule, chains, traces, n_sample, bounds):
         """One scheduler thread per chain group; in device mode each on its own CUDA stream (the group's engine is
         bound to it, so the torch tensor work and the engine's kernels of a group stay ordered)."""
@@ -481,7 +619,9 @@ class BatchedAPMSampler(object):
             theta_init = np.asarray(theta_init, dtype=np.float64)
             chains = [_Chain(c, self.seeds[c], theta_init[c], local[c]) for c in range(B)]
         traces = np.full((B, n_sample, self.P), np.nan)
-        schedule = self._schedule_device if self.rng == 'device' else self._schedule_parity
+        schedule = self._schedule_parity
+        if self.rng == 'device':
+            schedule = self._schedule_device_async if self.async_full else self._schedule_device
         if G == 1:
             rounds = schedule(self.backends[0], chains, traces, n_sample, self._gens[0])
         else:

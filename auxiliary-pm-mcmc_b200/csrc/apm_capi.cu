@@ -108,7 +108,8 @@ struct apm_ctx {
     // host thread on its own streams (per-step Cholesky launches), so that the latency-bound Newton kernels, the
     // host round trips and the stragglers of one group overlap the DMMA kernels of the others.  A lane is a view of
     // the root context: the same buffers with every per-chain pointer offset to the group's first chain.
-    apm_ctx* root = nullptr;            // non-null in a lane view
+    apm_ctx* root = nullptr;            // non-null in a lane view (and in a companion context: the slot owner)
+    bool cached_only = false;           // companion context (apm_create_companion): shares the parent's cache slots, cached estimates only
     std::vector<apm_ctx*> lanes;        // root only
     int n_lanes = 1, lane_min_chains = 32, lane_min_batch = 128;
     cudaEvent_t ev_fork = nullptr;
@@ -211,8 +212,12 @@ static int set_kernel_attrs() {
 extern "C" const char* apm_version(void) { return "apm_b200 0.1.0 (sm_100a, fp64 DMMA tile engine)"; }
 extern "C" const char* apm_last_error(void) { return g_err.c_str(); }
 
-extern "C" int apm_create(const double* X, const double* y, int n, int D, int kernel_kind, double epsilon,
-                          int max_chains, int n_slots, int max_nimp, int device, apm_ctx** out) {
+extern "C" int apm_destroy(apm_ctx* c);
+
+// parent != null: companion context -- its cache slots ARE the parent's (no slot storage of its own) and its per-chain
+// matrix workspaces are sized for one chain (it only runs the O(n^2 N) cached estimates)
+static int create_impl(const double* X, const double* y, int n, int D, int kernel_kind, double epsilon, int max_chains,
+                       int n_slots, int max_nimp, int device, apm_ctx* parent, apm_ctx** out) {
     if (!X || !y || !out || n <= 0 || D <= 0 || max_chains <= 0 || n_slots <= 0 || max_nimp <= 0 ||
         (kernel_kind != APM_KERNEL_ISO && kernel_kind != APM_KERNEL_ARD)) {
         set_err("apm_create: invalid argument");
@@ -256,23 +261,32 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         if (getenv("APM_CHOL_GROUP")) c->flow_group = atoi(getenv("APM_CHOL_GROUP")) > 0 ? atoi(getenv("APM_CHOL_GROUP")) : (1 << 20);
     }
     const size_t B = max_chains, np = c->np;
+    const size_t Bm = parent ? 1 : B;      // chains with full matrix workspaces
+    const size_t own_slots = parent ? 0 : (size_t)n_slots;
+    c->cached_only = parent != nullptr;
     int rc = APM_OK;
     auto A = [&](int r) { if (rc == APM_OK) rc = r; };
     A(dev_alloc(c, &c->dX, np * D));
     A(dev_alloc(c, &c->dy, np));
-    A(dev_alloc(c, &c->dK, B * c->mat));
-    A(dev_alloc(c, &c->dLB, B * c->mat));
-    A(dev_alloc(c, &c->dZ, B * c->mat));
-    A(dev_alloc(c, &c->dSlotLK, (size_t)n_slots * c->mat));
-    A(dev_alloc(c, &c->dSlotLC, (size_t)n_slots * c->mat));
-    A(dev_alloc(c, &c->dSlotMu, (size_t)n_slots * np));
-    A(dev_alloc(c, &c->dSlotMt, (size_t)n_slots * np));
-    A(dev_alloc(c, &c->dSlotLdK, (size_t)n_slots * c->nb));
-    A(dev_alloc(c, &c->dSlotLdC, (size_t)n_slots * c->nb));
+    A(dev_alloc(c, &c->dK, Bm * c->mat));
+    A(dev_alloc(c, &c->dLB, Bm * c->mat));
+    A(dev_alloc(c, &c->dZ, Bm * c->mat));
+    if (!parent) {
+        A(dev_alloc(c, &c->dSlotLK, own_slots * c->mat));
+        A(dev_alloc(c, &c->dSlotLC, own_slots * c->mat));
+        A(dev_alloc(c, &c->dSlotMu, own_slots * np));
+        A(dev_alloc(c, &c->dSlotMt, own_slots * np));
+        A(dev_alloc(c, &c->dSlotLdK, own_slots * c->nb));
+        A(dev_alloc(c, &c->dSlotLdC, own_slots * c->nb));
+    } else {
+        c->dSlotLK = parent->dSlotLK; c->dSlotLC = parent->dSlotLC; c->dSlotMu = parent->dSlotMu;
+        c->dSlotMt = parent->dSlotMt; c->dSlotLdK = parent->dSlotLdK; c->dSlotLdC = parent->dSlotLdC;
+        c->root = parent;                      // slot_flags() / slot_modes() resolve to the owner
+    }
     A(dev_alloc(c, &c->dLdB, B * c->nb));
-    A(dev_alloc(c, &c->dInvB, B * (size_t)c->nb * TB * TB));
+    A(dev_alloc(c, &c->dInvB, Bm * (size_t)c->nb * TB * TB));
     A(dev_alloc(c, &c->dSymvDirect, B * np));
-    A(dev_alloc(c, &c->dSymvPart, B * (size_t)c->nb * c->nb * 64));
+    A(dev_alloc(c, &c->dSymvPart, Bm * (size_t)c->nb * c->nb * 64));
     for (int v = 0; v < V_COUNT; v++) A(dev_alloc(c, &c->dVec[v], B * np));
     const size_t usz = B * (size_t)c->maxNpad * np;
     A(dev_alloc(c, &c->dUT, usz));
@@ -345,7 +359,9 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         return APM_ERR_CUDA;
     }
     // lane views (streams and events of their own; buffers are the root's)
-    if (getenv("APM_LANES")) {
+    if (parent) {
+        c->n_lanes = 1;
+    } else if (getenv("APM_LANES")) {
         c->n_lanes = atoi(getenv("APM_LANES"));
     } else {
         // default: 8 lanes, but never more host threads than this process's share of the cores (lane threads wait on
@@ -393,6 +409,36 @@ extern "C" int apm_create(const double* X, const double* y, int n, int D, int ke
         }
     }
     *out = c;
+    return APM_OK;
+}
+
+extern "C" int apm_create(const double* X, const double* y, int n, int D, int kernel_kind, double epsilon,
+                          int max_chains, int n_slots, int max_nimp, int device, apm_ctx** out) {
+    return create_impl(X, y, n, D, kernel_kind, epsilon, max_chains, n_slots, max_nimp, device, nullptr, out);
+}
+
+// A second context on the parent's data set and device, with streams, workspaces and pinned staging of its own, whose
+// cache slots are the parent's: apm_estimate_cached(_weights) on it may run WHILE the parent is inside
+// apm_estimate_full, as long as the two calls touch different slots (the samplers' current / proposed slots of
+// different chains).  Destroy it before the parent.
+extern "C" int apm_create_companion(apm_ctx* parent, int max_chains, int max_nimp, apm_ctx** out) {
+    if (!parent || !out || parent->root != nullptr) {
+        set_err("apm_create_companion: parent must be a context created by apm_create");
+        return APM_ERR_INVALID;
+    }
+    CU_TRY(cudaSetDevice(parent->device));
+    std::vector<double> Xp((size_t)parent->np * parent->D), yp(parent->np);
+    CU_TRY(cudaMemcpy(Xp.data(), parent->dX, sizeof(double) * Xp.size(), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(yp.data(), parent->dy, sizeof(double) * yp.size(), cudaMemcpyDeviceToHost));
+    return create_impl(Xp.data(), yp.data(), parent->n, parent->D, parent->kind, parent->eps, max_chains, parent->nslots,
+                       max_nimp, parent->device, parent, out);
+}
+
+static int not_companion(apm_ctx* c) {
+    if (c && c->cached_only) {
+        set_err("companion contexts (apm_create_companion) only run cached estimates");
+        return APM_ERR_INVALID;
+    }
     return APM_OK;
 }
 
@@ -1114,6 +1160,7 @@ static int fetch_results(apm_ctx* c, int B, double* out_d, int n_out, double* ou
 // ------------------------------------------------------------------------------------------------
 extern "C" int apm_kernel_build(apm_ctx* c, const double* theta, int B, int kernel_kind, double epsilon, double* K_out,
                                 int K_on_device) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (!theta || !K_out) return APM_ERR_INVALID;
     const int kind = kernel_kind < 0 ? c->kind : kernel_kind;
@@ -1131,6 +1178,7 @@ extern "C" int apm_kernel_build(apm_ctx* c, const double* theta, int B, int kern
 }
 
 extern "C" int apm_kernel_grad(apm_ctx* c, const double* theta, int B, int kernel_kind, double* dK_out, int dK_on_device) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (!theta || !dK_out) return APM_ERR_INVALID;
     const int kind = kernel_kind < 0 ? c->kind : kernel_kind;
@@ -1189,6 +1237,7 @@ static int import_matrices(apm_ctx* c, const double* M, int on_device, int B, do
 
 extern "C" int apm_laplace(apm_ctx* c, const double* K, int K_on_device, int B, int calc_cov, int calc_lml, double* f_out,
                            double* C_out, int C_on_device, double* lml_out, int* cubic_ops_out, int* chain_status) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (!K) return APM_ERR_INVALID;
     APM_TRY(reset_status(c, B));
@@ -1222,6 +1271,7 @@ extern "C" int apm_laplace(apm_ctx* c, const double* K, int K_on_device, int B, 
 
 extern "C" int apm_ep(apm_ctx* c, const double* K, int K_on_device, int B, int calc_cov, double* f_out, double* C_out,
                       int C_on_device, double* nu_out, double* tau_out, int* cubic_ops_out, int* chain_status) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (!K) return APM_ERR_INVALID;
     APM_TRY(reset_status(c, B));
@@ -1316,6 +1366,7 @@ static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, 
 
 extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
                                  const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (!theta || !u || !slots || !logml_out) return APM_ERR_INVALID;
     // small batches stay on the single-launch dataflow path (a lane needs enough chains to fill its kernels)
@@ -1431,6 +1482,7 @@ extern "C" int apm_estimate_cached_weights(apm_ctx* c, const int* slots, const d
 
 extern "C" int apm_laplace_lml(apm_ctx* c, const double* theta, int B, double* lml_out, int* cubic_ops_out,
                                int* chain_status) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (!theta || !lml_out) return APM_ERR_INVALID;
     APM_TRY(reset_status(c, B));
@@ -1446,6 +1498,7 @@ extern "C" int apm_laplace_lml(apm_ctx* c, const double* theta, int B, double* l
 
 extern "C" int apm_estimate_prior_mc(apm_ctx* c, const double* theta, const int* slots, const double* u, int u_on_device,
                                      int N, int B, double* logml_out, int* chain_status) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (!slots || !u || !logml_out) return APM_ERR_INVALID;
     cancel_prefetch(c);
@@ -1475,6 +1528,7 @@ __global__ void k_logdet_parts(const double* L, int np, double* parts) {
 }
 
 extern "C" int apm_slot_export(apm_ctx* c, int slot, double* K_chol, double* C_chol, double* f_post, double* logdets2) {
+    APM_TRY(not_companion(c));
     if (!c || slot < 0 || slot >= c->nslots) return APM_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->device));
     const size_t n = c->n;
@@ -1512,6 +1566,7 @@ extern "C" int apm_slot_export(apm_ctx* c, int slot, double* K_chol, double* C_c
 }
 
 extern "C" int apm_slot_import(apm_ctx* c, int slot, const double* K_chol, const double* C_chol, const double* f_post) {
+    APM_TRY(not_companion(c));
     if (!c || slot < 0 || slot >= c->nslots || !K_chol) return APM_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->device));
     APM_TRY(import_matrices(c, K_chol, 0, 1, c->dSlotLK + (size_t)slot * c->mat, (long long)c->mat));
@@ -1536,6 +1591,7 @@ extern "C" int apm_slot_import(apm_ctx* c, int slot, const double* K_chol, const
 
 extern "C" int apm_slot_factor(apm_ctx* c, int slot, const double* K, const double* C, int on_device, const double* f_post,
                                int* chain_status) {
+    APM_TRY(not_companion(c));
     if (!c || slot < 0 || slot >= c->nslots || !K || !C || !f_post) return APM_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->device));
     slot_flags(c)[slot] = 0;
@@ -1562,6 +1618,7 @@ extern "C" int apm_slot_factor(apm_ctx* c, int slot, const double* K, const doub
 }
 
 extern "C" int apm_slot_copy(apm_ctx* c, const int* src, const int* dst, int B) {
+    APM_TRY(not_companion(c));
     if (!c || !src || !dst || B <= 0) return APM_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->device));
     for (int b = 0; b < B; b++) {
@@ -1584,6 +1641,7 @@ extern "C" int apm_slot_copy(apm_ctx* c, const int* src, const int* dst, int B) 
 // of the K matrices currently in the context (after apm_kernel_build) into slots 0..B-1.  mode 0: default
 // path, 1: force per-step launches.
 extern "C" int apm_dev_chol_bench(apm_ctx* c, int B, int reps, int mode, double* ms_out) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (B > c->nslots || !ms_out) return APM_ERR_INVALID;
     APM_TRY(reset_status(c, B));
@@ -1629,6 +1687,7 @@ extern "C" int apm_dev_chol_bench(apm_ctx* c, int B, int reps, int mode, double*
 
 // dev: time k_syrk_sub (a pure tile GEMM, depth n) at a forced occupancy (extra dynamic smem)
 extern "C" int apm_dev_syrk_bench(apm_ctx* c, int B, int reps, int smem_bytes, double* ms_out) {
+    APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     APM_TRY(reset_status(c, B));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

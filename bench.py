@@ -302,7 +302,7 @@ def run_gpu_arm(args):
     # ---- APM-MCMC iterations/s: ESS-u + RD-SS-theta in lock-step over the same chains (device-resident u)
     from apm_b200 import batched
     drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, 'ess+rdss', batched.make_log_prior(D, True),
-                                    [1000 + rank * B + c for c in range(B)], rng='device', device=dev)
+                                    [1000 + rank * B + c for c in range(B)], rng='device', device=dev, async_full=True)
     apm_iters = args.apm_iters
     drv.get_samples(thetas[0], 3)          # warm-up (allocations, first-use initialisation)
     barrier()
@@ -407,7 +407,7 @@ def run_gpu_arm(args):
             'cpu_baseline': cpu,
             'cached_estimates_per_s': world * B * max(args.steps, 3) / (ms_cached * 1e-3),
             'apm_iters_per_s': {'value': world * B * apm_iters / t_apm, 'unit': 'chain-iterations/s',
-                                'method': 'E-SS u + RD-SS theta, lock-step, %d chains/GPU, %d iterations, device RNG' % (B, apm_iters),
+                                'method': 'E-SS u + RD-SS theta, lock-step, %d chains/GPU, %d iterations, device RNG, asynchronous FULL rounds (worker thread + companion context for the CACHED rounds)' % (B, apm_iters),
                                 'full_estimates_per_iter': float(apm_out['n_full'].mean() - 1) / apm_iters,
                                 'cached_estimates_per_iter': float(apm_out['n_cached'].mean()) / apm_iters,
                                 'failed_chains': int((apm_out['failed'] != 0).sum()), 'timing': 'host wall clock incl. the Python scheduler and the drain of the last iterations'},

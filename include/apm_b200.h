@@ -65,6 +65,13 @@ int apm_create(const double* X, const double* y, int n, int D, int kernel_kind, 
                int max_chains, int n_slots, int max_nimp, int device, apm_ctx** out);
 int apm_destroy(apm_ctx* ctx);
 
+/* Companion context: streams, workspaces and pinned staging of its own on the parent's data set and device, but its
+ * cache slots ARE the parent's.  apm_estimate_cached / apm_estimate_cached_weights on the companion may run while
+ * another host thread is inside apm_estimate_full on the parent, provided the two calls touch different slots (the
+ * reference's samplers hold a current and a proposed cache per chain: smp.py:401-417).  Only the cached estimates are
+ * allowed on it; destroy it before the parent.  Used by apm_b200.batched's asynchronous scheduler. */
+int apm_create_companion(apm_ctx* parent, int max_chains, int max_nimp, apm_ctx** out);
+
 /* Run all work of this context on the given CUDA stream (cudaStream_t as an integer, e.g.
  * torch.cuda.current_stream().cuda_stream).  0 = the legacy default stream. */
 int apm_set_stream(apm_ctx* ctx, uint64_t cuda_stream);

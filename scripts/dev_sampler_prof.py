@@ -16,7 +16,8 @@ if G > 1:      # chain groups: one context and one scheduler thread per group, n
     dev = torch.device('cuda', 0)
     drv = batched.BatchedAPMSampler([batched.EngineBackend(e) for e in engs], n, N, D + 1, method, batched.make_log_prior(D, True),
                                     [1000 + c for c in range(B)], prop_scales=np.full(D + 1, 0.1), rng='device', device=dev,
-                                    full_batch_frac=float(os.environ.get('FRAC', 0.8)))
+                                    full_batch_frac=float(os.environ.get('FRAC', 0.8)), async_full=bool(int(os.environ.get('ASYNC', 0))),
+                                    async_batch_frac=float(os.environ.get('AFRAC', 0.5)))
     th0 = synth.bulk_thetas(B, D, seed=1000)
     for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -34,11 +35,13 @@ def tf(*a):
     torch.cuda.synchronize(); t = time.perf_counter(); r = of(*a); log['full'].append((len(r[0]), time.perf_counter() - t)); return r
 def tc(*a):
     torch.cuda.synchronize(); t = time.perf_counter(); r = oc(*a); log['cached'].append((len(r[0]), time.perf_counter() - t)); return r
-eng.estimate_full, eng.estimate_cached = tf, tc
+if not int(os.environ.get('ASYNC', 0)):      # per-call timing synchronises the device: not with the asynchronous scheduler
+    eng.estimate_full, eng.estimate_cached = tf, tc
 dev = torch.device('cuda', 0)
 drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, method, batched.make_log_prior(D, True),
                                 [1000 + c for c in range(B)], prop_scales=np.full(D + 1, 0.1), rng='device', device=dev,
-                                full_batch_frac=float(os.environ.get('FRAC', 0.8)))
+                                full_batch_frac=float(os.environ.get('FRAC', 0.8)), async_full=bool(int(os.environ.get('ASYNC', 0))),
+                                async_batch_frac=float(os.environ.get('AFRAC', 0.5)))
 th0 = synth.bulk_thetas(B, D, seed=1000)
 for rep in range(2):
     log['full'].clear(); log['cached'].clear()
@@ -49,6 +52,8 @@ for rep in range(2):
     print('%s B=%d iters=%d: %.3f s -> %.0f chain-iters/s; rounds %d; FULL calls %d (%.3f s) sizes %s; CACHED calls %d (%.3f s) sizes %s; other %.3f s'
           % (method, B, iters, dt, B * iters / dt, out['rounds'], len(log['full']), tf_, [b for b, _ in log['full']][:40],
              len(log['cached']), tc_, [b for b, _ in log['cached']][:40], dt - tf_ - tc_), flush=True)
+    if getattr(drv, 'async_stats', None):
+        print('   async:', {k: (round(v, 3) if isinstance(v, float) else v) for k, v in drv.async_stats.items()}, flush=True)
     if os.environ.get('DUMP'):
         print('FULL (size, ms):', ' '.join('%d:%.1f' % (b, t * 1e3) for b, t in log['full']))
         print('CACHED (size, ms):', ' '.join('%d:%.2f' % (b, t * 1e3) for b, t in log['cached']))

@@ -49,6 +49,55 @@ def test_batched_device_rng_mode():
     eng.close()
 
 
+@pytest.mark.parametrize('method', ['ess+rdss', 'mi+mh', 'pmmh'])
+def test_batched_async_full_scheduler(method):
+    """Device-RNG mode with asynchronous FULL estimates: the FULL call runs on a worker thread / stream while the
+    scheduler serves CACHED requests through a companion context (shared cache slots).  The chains must behave like
+    the synchronous scheduler's: every cached estimate equals a fresh FULL estimate for the same (theta, u), which the
+    chain checks itself through its log_f bookkeeping -- here: finite traces, plausible acceptance, no failures, and the
+    same posterior location as the synchronous run."""
+    import torch
+    X, y, th = synth.make_dataset(96, 3, seed=2)
+    B, N, iters = 24, 8, 60
+    dev = torch.device('cuda', 0)
+    res = {}
+    for mode in (False, True):
+        eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N)
+        eng.use_torch_stream()
+        drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), 96, N, 4, method, batched.make_log_prior(3, True),
+                                        [10 + c for c in range(B)], prop_scales=np.full(4, 0.3), rng='device', device=dev,
+                                        async_full=mode)
+        out = drv.get_samples(np.tile(th, (B, 1)), iters)
+        assert np.all(out['failed'] == 0) and np.all(np.isfinite(out['thetas']))
+        assert np.all(out['n_full'] >= iters - 1)
+        res[mode] = out
+        eng.close()
+    # same target distribution: pooled second-half means agree within Monte-Carlo error
+    a = res[False]['thetas'][:, iters // 2:].reshape(-1, 4)
+    b = res[True]['thetas'][:, iters // 2:].reshape(-1, 4)
+    assert np.all(np.abs(a.mean(0) - b.mean(0)) < 4. * (a.std(0) + b.std(0)) / np.sqrt(B))
+
+
+def test_companion_context_shares_slots_and_refuses_full():
+    X, y, th = synth.make_dataset(70, 2, seed=4)
+    rs = np.random.RandomState(0)
+    B, N = 3, 5
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N)
+    comp = eng.companion()
+    thetas = th[None] + 0.1 * rs.normal(size=(B, 3))
+    u = rs.normal(size=(B, 70, N))
+    full, _, st = eng.estimate_full(thetas, u, [0, 2, 4])
+    assert np.all(st == 0)
+    c_own, _ = eng.estimate_cached([0, 2, 4], u)
+    c_comp, _ = comp.estimate_cached([0, 2, 4], u)
+    assert np.array_equal(c_own, c_comp) and np.allclose(c_comp, full, rtol=1e-12)
+    with pytest.raises(_capi.ApmError):
+        comp.estimate_full(thetas, u, [1, 3, 5])
+    with pytest.raises(_capi.ApmError):
+        comp.estimate_cached([1], u[:1])          # slot 1 holds no cache: validity flags are the owner's
+    eng.close()
+
+
 def test_chain_groups_on_two_contexts_match_single_group():
     """Two engine contexts driven by two scheduler threads (chain groups): identical per-chain traces in parity mode,
     chain 0 still reproduces the reference's golden chain; device-RNG mode runs on per-group streams."""
