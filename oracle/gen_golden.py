@@ -185,6 +185,34 @@ def gen_samplers(ref):
     np.savez_compressed(os.path.join(OUT, 'samplers.npz'), **out)
 
 
+def gen_samplers_fullsize(ref):
+    """Chains of the unmodified reference at the headline shapes (BASELINE configs 1-2: pima n=768 D=8 and breast n=682
+    D=9, N_imp = 64, isotropic kernel as in the notebooks): accept/reject parity where the benchmark is quoted."""
+    out = {}
+    for tag, n, D, seed, cases in (('pima', 768, 8, 0, (('ess+rdss', 50), ('mi+mh', 50), ('pmmh', 40))),
+                                   ('breast', 682, 9, 1, (('ess+rdss', 50),))):
+        X, y, _ = synth.make_dataset(n, D, seed=seed)
+        out[tag + '_X'], out[tag + '_y'] = X, y
+        for method, n_iter in cases:
+            N = 64
+            prng = np.random.RandomState()
+            holder = []
+            smp = build_sampler(ref, method, X, y, N, prng, holder)
+            prng.seed(1000 + N)
+            theta_init = synth.draw_theta_prior(prng, D, ard=False)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                res = smp.get_samples(theta_init, n_iter)
+            thetas = res[0] if isinstance(res, tuple) else res
+            n_rej = np.atleast_1d(res[1]) if isinstance(res, tuple) else np.zeros(0)
+            key = '%s_%s_N%d_' % (tag, method, N)
+            out[key + 'thetas'] = thetas
+            out[key + 'n_reject'] = np.asarray(n_rej, dtype=np.int64)
+            out[key + 'cubic_ops'] = holder[0].n_cubic_ops
+            print(tag, method, N, 'final theta', thetas[-1], 'rej', n_rej, 'ops', holder[0].n_cubic_ops, flush=True)
+    np.savez_compressed(os.path.join(OUT, 'samplers_fullsize.npz'), **out)
+
+
 def gen_utils(ref):
     xs = np.linspace(-3, 3, 13)
     np.savez_compressed(
@@ -198,6 +226,9 @@ if __name__ == '__main__':
         print('warning: run with OPENBLAS_NUM_THREADS=1 for a deterministic oracle', file=sys.stderr)
     ref = ref_loader.load_reference()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[1] == '--only':          # regenerate one fixture file, leave the others alone
+        globals()['gen_' + sys.argv[2]](ref)
+        sys.exit(0)
     gen_utils(ref)
     gen_kernels(ref)
     gen_laplace(ref)
@@ -207,4 +238,5 @@ if __name__ == '__main__':
     gen_estimator(ref, 'pima_iso', 768, 8, 'iso', (1, 64), 2, 0, False)
     gen_estimator(ref, 'breast_ard', 682, 9, 'ard', (64,), 2, 1, False)
     gen_samplers(ref)
+    gen_samplers_fullsize(ref)
     print('golden vectors written to', OUT)

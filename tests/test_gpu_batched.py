@@ -126,3 +126,32 @@ def test_chain_groups_on_two_contexts_match_single_group():
     assert np.std(out['thetas'][:, -1, 0]) > 0
     for e in engs:
         e.close()
+
+
+@pytest.mark.parametrize('tag,method', [('pima', 'ess+rdss'), ('pima', 'mi+mh'), ('pima', 'pmmh'), ('breast', 'ess+rdss')])
+def test_headline_shape_chains_match_reference(tag, method):
+    """Accept/reject parity where the benchmark is quoted (BASELINE configs 1-2): chains of the UNMODIFIED reference at
+    pima (n = 768, D = 8) and breast (n = 682, D = 9) shape with N_imp = 64 (tests/golden/samplers_fullsize.npz,
+    oracle/gen_golden.py:gen_samplers_fullsize) against chain 0 of a lock-step batch on the GPU: identical theta traces,
+    reject counts and cubic-op counts over all golden iterations."""
+    g = load_golden('samplers_fullsize')
+    X, y = g[tag + '_X'], g[tag + '_y']
+    N = 64
+    key = '%s_%s_N%d_' % (tag, method, N)
+    ref = g[key + 'thetas']
+    n_iter = ref.shape[0]
+    seeds = [1000 + N, 7, 8, 9]
+    B = len(seeds)
+    eng = _capi.Engine(X, y, kernel='iso', max_chains=B, n_slots=2 * B, max_nimp=N)
+    drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), X.shape[0], N, 2, method,
+                                    batched.make_log_prior(X.shape[1], False), seeds, prop_scales=[0.5, 0.5])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out = drv.get_samples(None, n_iter, theta_init_sampler=lambda prng: synth.draw_theta_prior(prng, X.shape[1], ard=False))
+    assert np.all(out['failed'] == 0)
+    div = first_divergence(out['thetas'][0], ref)
+    assert div is None, 'chain diverges from the reference at iteration %d' % div
+    assert out['n_cubic_ops'][0] == int(g[key + 'cubic_ops'])
+    if g[key + 'n_reject'].size:
+        assert np.array_equal(out['n_reject'][0][-g[key + 'n_reject'].size:], g[key + 'n_reject'])
+    eng.close()

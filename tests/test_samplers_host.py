@@ -30,6 +30,18 @@ def test_chain_matches_reference(method, N):
     assert ops == int(g[key + 'cubic_ops'])
 
 
+def test_headline_shape_chain_matches_reference():
+    """The oracle restatement under the host samplers reproduces the reference's own chain at the headline shape
+    (pima-shaped n = 768, D = 8, N_imp = 64, E-SS u + RD-SS theta): first 12 iterations of the golden trace."""
+    g = load_golden('samplers_fullsize')
+    n_iter = 12
+    gg = dict(X=g['pima_X'], y=g['pima_y'])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        thetas, n_rej, ops = run_golden_case('ess+rdss', 64, gg, n_iter, **ORACLE_IMPL)
+    assert first_divergence(thetas, g['pima_ess+rdss_N64_thetas'][:n_iter]) is None
+
+
 def test_adaptive_run_matches_reference():
     g = load_golden('samplers')
     prng = np.random.RandomState()
