@@ -1114,11 +1114,14 @@ static int run_is_tail(apm_ctx* c, int N, int B, const int* dSlots, double* d_lo
     e.y = c->dy; e.n = c->n; e.N = N;
     e.logdetK = c->dSlotLdK; e.logdetC = c->dSlotLdC; e.ld_stride = c->nb; e.nb = c->nb; e.slot_idx = dSlots;
     e.status = c->dStatus;
-    e.logml = d_logml; e.logw = d_logw;
+    e.logml = d_logml; e.logw = d_logw ? d_logw : c->dLogw;
     e.mode = mode;
     e.mt = (mode == 0 && factored) ? c->dSlotMt : nullptr; e.mt_bs = c->np;   // L_K^-1 f_s = mu~ + w_s
     prof_begin(c, KID_EPILOGUE);
-    k_is_epilogue<<<B, 256, sizeof(double) * N, c->stream>>>(e);
+    k_is_logw<<<dim3((N + 7) / 8, B), 256, 0, c->stream>>>(e);
+    APM_TRY(check_launch(c, "k_is_logw"));
+    prof_begin(c, KID_EPILOGUE);
+    k_is_epilogue<<<B, 256, 0, c->stream>>>(e);
     return check_launch(c, "k_is_epilogue");
 }
 

@@ -57,32 +57,49 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
     const double sigma = prm[0];
     const int tx = tid & 31, ty = tid >> 5;
     double* Kb = p.K + (long long)b * p.k_bs;
-#pragma unroll 1
+    // every thread owns 8 rows x 2 columns; the feature loop is outermost so that the length-scale, its reciprocal and
+    // the two column coordinates are read once per feature (12 shared-memory reads per 16 elements instead of 64).
+    // Per element the terms are still accumulated in ascending k, as the reference's scalar loop does.
+    double acc[8][2];
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) acc[rr][0] = acc[rr][1] = 0.0;
+    const double* xi = Xi + (ty * 8) * D;
+    if (p.ard) {
+        for (int k = 0; k < D; k++) {
+            const double tau = prm[k + 1], rtau = prm[D + 1 + k];
+            const double xj0 = XjT[k * 64 + tx * 2], xj1 = XjT[k * 64 + tx * 2 + 1];
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const double x = xi[rr * D + k];
+                const double d0 = div_by(__dsub_rn(x, xj0), tau, rtau), d1 = div_by(__dsub_rn(x, xj1), tau, rtau);
+                acc[rr][0] = __dadd_rn(acc[rr][0], __dmul_rn(d0, d0));
+                acc[rr][1] = __dadd_rn(acc[rr][1], __dmul_rn(d1, d1));
+            }
+        }
+    } else {
+        for (int k = 0; k < D; k++) {
+            const double xj0 = XjT[k * 64 + tx * 2], xj1 = XjT[k * 64 + tx * 2 + 1];
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const double x = xi[rr * D + k];
+                const double d0 = __dsub_rn(x, xj0), d1 = __dsub_rn(x, xj1);
+                acc[rr][0] = __dadd_rn(acc[rr][0], __dmul_rn(d0, d0));
+                acc[rr][1] = __dadd_rn(acc[rr][1], __dmul_rn(d1, d1));
+            }
+        }
+    }
+#pragma unroll
     for (int rr = 0; rr < 8; rr++) {
         const int r = ty * 8 + rr;
         const int gi = ti * 64 + r;
         double out[2];
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
-            const int c = tx * 2 + cc;
-            const int gj = tj * 64 + c;
-            double acc = 0.0;
-            if (p.ard) {
-                for (int k = 0; k < D; k++) {
-                    const double d = div_by(__dsub_rn(Xi[r * D + k], XjT[k * 64 + c]), prm[k + 1], prm[D + 1 + k]);
-                    acc = __dadd_rn(acc, __dmul_rn(d, d));
-                }
-                acc = __dmul_rn(sigma, exp(-acc * 0.5));
-            } else {
-                for (int k = 0; k < D; k++) {
-                    const double d = __dsub_rn(Xi[r * D + k], XjT[k * 64 + c]);
-                    acc = __dadd_rn(acc, __dmul_rn(d, d));
-                }
-                acc = __dmul_rn(sigma, exp(div_by(-acc, prm[1], prm[2])));
-            }
-            if (gi == gj) acc = sigma + p.eps;
-            if (gi >= p.n || gj >= p.n) acc = (gi == gj) ? 1.0 : 0.0;
-            out[cc] = acc;
+            const int gj = tj * 64 + tx * 2 + cc;
+            double v = p.ard ? __dmul_rn(sigma, exp(-acc[rr][cc] * 0.5)) : __dmul_rn(sigma, exp(div_by(-acc[rr][cc], prm[1], prm[2])));
+            if (gi == gj) v = sigma + p.eps;
+            if (gi >= p.n || gj >= p.n) v = (gi == gj) ? 1.0 : 0.0;
+            out[cc] = v;
         }
         *reinterpret_cast<double2*>(Kb + (size_t)gi * p.np + tj * 64 + tx * 2) = make_double2(out[0], out[1]);
         Ts[r * VSP + tx * 2] = out[0];
@@ -660,7 +677,8 @@ __global__ void __launch_bounds__(256) k_laplace_lml(NewtonVecs nv, const double
 }
 
 // ------------------------------------------------------------------------------------------------
-// Importance-sampling epilogue (estimators.py:225-240), one CTA per chain:
+// Importance-sampling epilogue (estimators.py:225-240) in two stages (k_is_logw: a warp per sample; k_is_epilogue: the
+// log-sum-exp of a chain):
 //   lw_s = sum_i log Phi(y_i F_si) - q_K/2 - sum log diag L_K + q_u/2 + sum log diag L_C
 //   with q_K = |L_K^{-1} f_s|^2 (rows of Zf) and q_u = |u_s|^2 (== (f_s-mu)^T C^{-1} (f_s-mu), est.py:232-234)
 //   out = logsumexp_s lw_s - log N
@@ -671,13 +689,84 @@ struct EpilogueParams {
     const double* y; int n, N;
     const double* logdetK; const double* logdetC; int ld_stride; int nb; const int* slot_idx;   // per slot parts
     const int* status;
-    double* logml; double* logw;   // logw optional [chain][N]
+    double* logml; double* logw;   // logw: [chain][N] log-weights (always written; workspace of the two stages)
     int mode;
     const double* mt; long long mt_bs;   // optional [slot][np]: L_K^{-1} f_s = mt + Zf row (factored cache, see run_is_tail)
 };
 
+// stage 1: one warp per (chain, sample): lw_s -> p.logw[chain][s].  grid (ceil(N / 8), chains), 256 threads.
+// The element loop is unrolled by 4 with all loads issued first (the kernel is memory-latency bound otherwise); every
+// lane still accumulates its elements in increasing order.
+__global__ void __launch_bounds__(256) k_is_logw(EpilogueParams p) {
+    const int b = blockIdx.y;
+    if (p.status && p.status[b] != 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * 8 + warp;
+    if (s >= p.N) return;
+    const double* Fr = p.F + (long long)b * p.bs + (size_t)s * p.ld;
+    double ll = 0.0, qk = 0.0, qu = 0.0;
+    if (p.mode == 0) {
+        const double* Zr = p.Zf + (long long)b * p.bs + (size_t)s * p.ld;
+        const double* Ur = p.UT + (long long)b * p.bs + (size_t)s * p.ld;
+        const double* mt = p.mt ? p.mt + chain_index(p.slot_idx, b) * p.mt_bs : nullptr;
+        int i = lane;
+        for (; i + 96 < p.n; i += 128) {
+            double f[4], z[4], u[4], yy[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                f[q] = Fr[i + 32 * q];
+                z[q] = Zr[i + 32 * q];
+                u[q] = Ur[i + 32 * q];
+                yy[q] = p.y[i + 32 * q];
+                if (mt) z[q] += mt[i + 32 * q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                ll += log_ndtr(yy[q] * f[q]);
+                qk = fma(z[q], z[q], qk);
+                qu = fma(u[q], u[q], qu);
+            }
+        }
+        for (; i < p.n; i += 32) {
+            ll += log_ndtr(p.y[i] * Fr[i]);
+            const double z = mt ? mt[i] + Zr[i] : Zr[i], u = Ur[i];
+            qk = fma(z, z, qk);
+            qu = fma(u, u, qu);
+        }
+    } else {
+        int i = lane;
+        for (; i + 96 < p.n; i += 128) {
+            double f[4], yy[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                f[q] = Fr[i + 32 * q];
+                yy[q] = p.y[i + 32 * q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) ll += log_ndtr(yy[q] * f[q]);
+        }
+        for (; i < p.n; i += 32) ll += log_ndtr(p.y[i] * Fr[i]);
+    }
+    ll = warp_sum(ll);
+    qk = warp_sum(qk);
+    qu = warp_sum(qu);
+    if (lane == 0) {
+        double v = ll;
+        if (p.mode == 0) {
+            double ldK = 0.0, ldC = 0.0;
+            const long long sl = chain_index(p.slot_idx, b);
+            for (int k = 0; k < p.nb; k++) {
+                ldK += p.logdetK[(size_t)sl * p.ld_stride + k];
+                ldC += p.logdetC[(size_t)sl * p.ld_stride + k];
+            }
+            v = ll + (-0.5 * qk - ldK) - (-0.5 * qu - ldC);
+        }
+        p.logw[(size_t)b * p.N + s] = v;
+    }
+}
+
+// stage 2: logml[chain] = logsumexp_s lw_s - log N (estimators.py:240), one CTA per chain
 __global__ void __launch_bounds__(256) k_is_epilogue(EpilogueParams p) {
-    extern __shared__ __align__(16) double lw[];   // [N]
     __shared__ double red[8];
     const int b = blockIdx.x;
     if (p.status && p.status[b] != 0) {
@@ -685,40 +774,7 @@ __global__ void __launch_bounds__(256) k_is_epilogue(EpilogueParams p) {
         return;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double ldK = 0.0, ldC = 0.0;
-    if (p.mode == 0) {
-        const long long sl = chain_index(p.slot_idx, b);
-        for (int k = 0; k < p.nb; k++) {
-            ldK += p.logdetK[(size_t)sl * p.ld_stride + k];
-            ldC += p.logdetC[(size_t)sl * p.ld_stride + k];
-        }
-    }
-    for (int s = warp; s < p.N; s += 8) {
-        const double* Fr = p.F + (long long)b * p.bs + (size_t)s * p.ld;
-        double ll = 0.0, qk = 0.0, qu = 0.0;
-        if (p.mode == 0) {
-            const double* Zr = p.Zf + (long long)b * p.bs + (size_t)s * p.ld;
-            const double* Ur = p.UT + (long long)b * p.bs + (size_t)s * p.ld;
-            const double* mt = p.mt ? p.mt + chain_index(p.slot_idx, b) * p.mt_bs : nullptr;
-            for (int i = lane; i < p.n; i += 32) {
-                ll += log_ndtr(p.y[i] * Fr[i]);
-                const double z = mt ? mt[i] + Zr[i] : Zr[i], u = Ur[i];
-                qk = fma(z, z, qk);
-                qu = fma(u, u, qu);
-            }
-        } else {
-            for (int i = lane; i < p.n; i += 32) ll += log_ndtr(p.y[i] * Fr[i]);
-        }
-        ll = warp_sum(ll);
-        qk = warp_sum(qk);
-        qu = warp_sum(qu);
-        if (lane == 0) {
-            const double v = (p.mode == 0) ? (ll + (-0.5 * qk - ldK) - (-0.5 * qu - ldC)) : ll;
-            lw[s] = v;
-            if (p.logw) p.logw[(size_t)b * p.N + s] = v;
-        }
-    }
-    __syncthreads();
+    const double* lw = p.logw + (size_t)b * p.N;
     double m = -INFINITY;
     for (int s = threadIdx.x; s < p.N; s += 256) m = fmax(m, lw[s]);
     m = warp_max(m);
