@@ -11,6 +11,8 @@ n, D, N, B = 768, 8, 64, int(os.environ.get('B', 256))
 reps = int(os.environ.get('REPS', 12))
 X, y, th = synth.make_dataset(n, D, seed=0)
 eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=B, max_nimp=N)
+if os.environ.get('MAXIT'):
+    eng.set_newton(1e-4, int(os.environ['MAXIT']))   # experiment: retire the stragglers (they fail with status 2)
 thetas = [synth.bulk_thetas(B, D, seed=s) for s in range(4)]
 us = [torch.randn(B, n, N, dtype=torch.float64, device='cuda') for _ in range(2)]
 slots = np.arange(B)
