@@ -463,7 +463,7 @@ class BatchedAPMSampler(object):
             ch.accept_u = False
         gens = [self._run_chain_device(ch, n_sample, traces[c]) for c, ch in enumerate(chains)]
         pending = {c: next(g) for c, g in enumerate(gens)}
-        inflight = None                                  # (future, chain list, thetas, log priors)
+        inflight = None                                  # (future, chain list, thetas, log priors, u of the call)
         rounds = 0
         import time
         stats = dict(full_calls=0, full_chains=0, cached_calls=0, cached_chains=0, t_submit=0., t_flight=0., t_total=time.perf_counter())
@@ -526,11 +526,12 @@ class BatchedAPMSampler(object):
                     u_in = U.index_select(0, idx_t(full)).contiguous()
                     ready = torch.cuda.Event()
                     ready.record()
-                    inflight = (pool.submit(run_full, thetas, u_in, slots, ready), full, thetas, None, u_in)
+                    fut = pool.submit(run_full, thetas, u_in, slots, ready)
                     stats['t_submit'] = time.perf_counter()
                     stats['full_calls'] += 1
                     stats['full_chains'] += len(full)
-                    inflight = inflight[:3] + (self._log_prior_many(thetas), u_in)     # while the call runs
+                    # the log priors are evaluated while the call runs; u_in is kept alive until it is harvested
+                    inflight = (fut, full, thetas, self._log_prior_many(thetas), u_in)
                     for c in full:
                         del pending[c]
             # --- CACHED requests of the chains that are not in flight

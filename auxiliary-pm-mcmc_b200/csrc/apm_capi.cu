@@ -79,6 +79,8 @@ struct apm_ctx {
     bool hybrid_newton = true;
     double pred_factor = 0.15;   // measured optimum 0.1-0.2 (profiles/): a missed prediction costs a latency-bound covariance phase
     int *dMaskM = nullptr, *dMaskB = nullptr, *dDoneM = nullptr;
+    // f_new = s / W^1/2 instead of the second mat-vec of a B-space Newton step (k_fnew_from_s); APM_FNEW_THR=0 disables it
+    double fnew_thr = 1e-2;
     bool newton_b_finishers = true;   // set by run_newton: some chain finished in a B-space round (needs the covariance phase)
     size_t mat = 0;  // np*np
     double *dX = nullptr, *dy = nullptr;
@@ -327,6 +329,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
     c->hybrid_newton = getenv("APM_NO_HYBRID_NEWTON") == nullptr;
+    if (getenv("APM_FNEW_THR")) c->fnew_thr = atof(getenv("APM_FNEW_THR"));
     if (getenv("APM_PRED_FACTOR") && atof(getenv("APM_PRED_FACTOR")) > 0) c->pred_factor = atof(getenv("APM_PRED_FACTOR"));
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -813,7 +816,13 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
                                                       (long long)c->nb * TB * TB, nvB);
             APM_TRY(check_launch(c, "k_trsv2"));
             // f_new = K a                                              (lpa.py:95)
-            APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew, maskB));
+            if (c->fnew_thr > 0) {
+                prof_begin(c, KID_MATVEC);
+                k_fnew_from_s<<<B, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, nvB, c->fnew_thr);
+                APM_TRY(check_launch(c, "k_fnew_from_s"));
+            } else {
+                APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew, maskB));
+            }
             swap.back();
         }
         if (nM > 0) {

@@ -274,6 +274,65 @@ __global__ void k_newton_prep(NewtonVecs nv) {
     }
 }
 
+// f_new = K a without the mat-vec (lpa.py:95).  With s = B^-1 t, t = W^1/2 K b and a = b - W^1/2 s (lpa.py:94):
+//   B s = t  <=>  s + W^1/2 K W^1/2 s = W^1/2 K b  <=>  W^1/2 K a = s,   i.e.   (K a)_i = s_i / W^1/2_i  exactly.
+// Dividing amplifies the rounding error of s_i (~ eps cond(B) |s|) by 1 / W^1/2_i, so components whose W^1/2 is below
+// `thr` (probit: y_i f_i large and positive, a few per cent of the data) are computed as the row product K[i,:] a instead:
+// the result stays within ~1e-13 of the mat-vec while the 8 n^2-byte read of K shrinks to the flagged rows.
+// One CTA (256 threads) per chain.
+__global__ void __launch_bounds__(256) k_fnew_from_s(const double* __restrict__ K, long long k_bs, int ld, NewtonVecs nv,
+                                                     double thr) {
+    __shared__ int flagged[1024];
+    __shared__ int n_flagged;
+    const int b = blockIdx.x;
+    if (!nv.active[b] || nv.status[b] != 0) return;
+    const long long o = (long long)b * nv.vs;
+    if (threadIdx.x == 0) n_flagged = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nv.np; i += 256) {
+        double v = 0.0;
+        if (i < nv.n) {
+            const double ws = nv.Ws[o + i];
+            if (ws >= thr) v = nv.s[o + i] / ws;
+            else {
+                const int q = atomicAdd(&n_flagged, 1);
+                if (q < 1024) flagged[q] = i;
+            }
+        }
+        nv.fnew[o + i] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* Kb = K + (long long)b * k_bs;
+    const double* a = nv.a + o;
+    if (n_flagged <= 1024) {
+        for (int q = warp; q < n_flagged; q += 8) {
+            const int i = flagged[q];
+            const double* row = Kb + (size_t)i * ld;
+            double acc0 = 0.0, acc1 = 0.0;
+            int j = lane * 2;
+            for (; j + 1 < nv.n; j += 64) {
+                const double2 m = *reinterpret_cast<const double2*>(row + j);
+                acc0 = fma(m.x, a[j], acc0);
+                acc1 = fma(m.y, a[j + 1], acc1);
+            }
+            if (j < nv.n) acc0 = fma(row[j], a[j], acc0);
+            const double v = warp_sum(acc0 + acc1);
+            if (lane == 0) nv.fnew[o + i] = v;
+        }
+    } else {
+        // more small-curvature components than the list holds: every row below the threshold by its own warp
+        for (int i = warp; i < nv.n; i += 8) {
+            if (nv.Ws[o + i] >= thr) continue;
+            const double* row = Kb + (size_t)i * ld;
+            double acc = 0.0;
+            for (int j = lane; j < nv.n; j += 32) acc = fma(row[j], a[j], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) nv.fnew[o + i] = acc;
+        }
+    }
+}
+
 // out[i] = rs[i] * sum_j M[i][j] x[j]; grid (np/32, chains), 256 threads (8 warps x 4 rows)
 __global__ void __launch_bounds__(256) k_matvec(const double* __restrict__ M, long long m_bs, int ld, int ncols,
                                                 const double* __restrict__ x, const double* __restrict__ rs,
