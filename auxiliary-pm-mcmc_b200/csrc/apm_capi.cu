@@ -785,13 +785,15 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
         APM_TRY(check_launch(c, "k_fill_int"));
         CU_TRY(cudaMemsetAsync(c->dMaskM, 0, sizeof(int) * B, c->stream));
     }
+    // mat-vec-free B-space step (k_newton_prep / k_trsv2 / k_fnew_from_s): no K-sized read besides the Cholesky itself
+    const bool matfree = c->fnew_thr > 0;
     NewtonVecs nvB = nv, nvM = nv;     // k_trsv2 skips the chains outside nv.active
     nvB.active = const_cast<int*>(maskB);
     nvM.active = const_cast<int*>(maskM);
     int n_act = B, nB = B, nM = 0;
     for (int it = 0; it < c->max_iters; it++) {
         prof_begin(c, KID_NEWTON_VEC);
-        k_newton_prep<<<B, 256, 0, c->stream>>>(nv);
+        k_newton_prep<<<B, 256, 0, c->stream>>>(nv, matfree ? 1 : 0);
         APM_TRY(check_launch(c, "k_newton_prep"));
         // mixed round: the two forms touch disjoint chains, so the minority form runs beside the other on aux_stream
         // (helpers launch on c->stream: it is swapped for the duration of that form)
@@ -805,8 +807,8 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
         }
         if (nB > 0) {
             if (b_on_aux) swap.to_aux();
-            // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b))
-            APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t, maskB));
+            // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b)); mat-vec-free: t = b / Ws
+            if (!matfree) APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t, maskB));
             // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
             APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
                              nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB, nB));
@@ -816,9 +818,9 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
                                                       (long long)c->nb * TB * TB, nvB);
             APM_TRY(check_launch(c, "k_trsv2"));
             // f_new = K a                                              (lpa.py:95)
-            if (c->fnew_thr > 0) {
+            if (matfree) {
                 prof_begin(c, KID_MATVEC);
-                k_fnew_from_s<<<B, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, nvB, c->fnew_thr);
+                k_fnew_from_s<<<B, 256, 0, c->stream>>>(c->dK, (long long)c->mat, c->np, nvB, c->fnew_thr, 1);
                 APM_TRY(check_launch(c, "k_fnew_from_s"));
             } else {
                 APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew, maskB));

@@ -254,7 +254,9 @@ struct NewtonVecs {
 };
 
 // v = exp(-f^2/2 - log_ndtr(y f) - log(2 pi)/2); grad = v y; W = v^2 + grad f; Ws = sqrt(W); b = W f + grad
-__global__ void k_newton_prep(NewtonVecs nv) {
+// rhs_c != 0: also t = c = b / W^1/2, the right-hand side of the mat-vec-free Newton step (see k_fnew_from_s): with
+// W^1/2 K W^1/2 = B - I the reference's t = W^1/2 K b (lpa.py:94) equals (B - I) c, hence s = B^-1 t = c - B^-1 c.
+__global__ void k_newton_prep(NewtonVecs nv, int rhs_c) {
     const int b = blockIdx.x;
     if (!nv.active[b] || nv.status[b] != 0) return;
     const long long o = (long long)b * nv.vs;
@@ -271,6 +273,7 @@ __global__ void k_newton_prep(NewtonVecs nv) {
         nv.W[o + i] = W;
         nv.Ws[o + i] = Ws;
         nv.bvec[o + i] = bv;
+        if (rhs_c) nv.t[o + i] = Ws > 0.0 ? bv / Ws : 0.0;
     }
 }
 
@@ -280,8 +283,11 @@ __global__ void k_newton_prep(NewtonVecs nv) {
 // `thr` (probit: y_i f_i large and positive, a few per cent of the data) are computed as the row product K[i,:] a instead:
 // the result stays within ~1e-13 of the mat-vec while the 8 n^2-byte read of K shrinks to the flagged rows.
 // One CTA (256 threads) per chain.
+// rhs_c != 0 (mat-vec-free step, see k_newton_prep): k_trsv2 solved with the right-hand side c = b / W^1/2, so nv.s holds
+// B^-1 c; s = c - B^-1 c and a = b - W^1/2 s are formed here first (k_trsv2 itself stays as it is: its load schedule is
+// sensitive to any change of the kernel).
 __global__ void __launch_bounds__(256) k_fnew_from_s(const double* __restrict__ K, long long k_bs, int ld, NewtonVecs nv,
-                                                     double thr) {
+                                                     double thr, int rhs_c) {
     __shared__ int flagged[1024];
     __shared__ int n_flagged;
     const int b = blockIdx.x;
@@ -291,6 +297,11 @@ __global__ void __launch_bounds__(256) k_fnew_from_s(const double* __restrict__ 
     __syncthreads();
     for (int i = threadIdx.x; i < nv.np; i += 256) {
         double v = 0.0;
+        if (rhs_c) {
+            const double si = nv.t[o + i] - nv.s[o + i];
+            nv.s[o + i] = si;
+            nv.a[o + i] = nv.bvec[o + i] - nv.Ws[o + i] * si;
+        }
         if (i < nv.n) {
             const double ws = nv.Ws[o + i];
             if (ws >= thr) v = nv.s[o + i] / ws;
