@@ -344,7 +344,9 @@ def run_gpu_arm(args):
         }
         hbm_bytes = {  # algorithmic bytes of the bandwidth-bound families
             'k_build_K': chains_done * 8. * n * n,
-            'k_matvec': iters_prof * 2. * 8. * (n * (n + 64) / 2.),   # symmetric mat-vec: lower tiles only
+            # triangular mat-vecs of the M-space Newton rounds (L_K^T b and L_K mu~, lower tiles of L_K each); the B-space
+            # rounds are mat-vec-free (k_fnew_from_s reads O(n) vectors)
+            'k_matvec': syrk_units * 2. * 8. * (n * (n + 64) / 2.),
         }
         kern = {}
         for name, (ms, cnt) in prof.items():
