@@ -81,6 +81,7 @@ struct apm_ctx {
     int *dMaskM = nullptr, *dMaskB = nullptr, *dDoneM = nullptr;
     // f_new = s / W^1/2 instead of the second mat-vec of a B-space Newton step (k_fnew_from_s); APM_FNEW_THR=0 disables it
     double fnew_thr = 1e-2;
+    bool syrk_direct = true;   // M' from L_K directly (k_syrk_lk) instead of k_make_Y + k_syrk_rev; APM_SYRK_VIA_Y=1: the latter
     bool newton_b_finishers = true;   // set by run_newton: some chain finished in a B-space round (needs the covariance phase)
     size_t mat = 0;  // np*np
     double *dX = nullptr, *dy = nullptr;
@@ -201,6 +202,7 @@ static int set_kernel_attrs() {
     CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_syrk_lk, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_gemm_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_build_K, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -329,6 +331,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
     c->hybrid_newton = getenv("APM_NO_HYBRID_NEWTON") == nullptr;
+    c->syrk_direct = getenv("APM_SYRK_VIA_Y") == nullptr;
     if (getenv("APM_FNEW_THR")) c->fnew_thr = atof(getenv("APM_FNEW_THR"));
     if (getenv("APM_PRED_FACTOR") && atof(getenv("APM_PRED_FACTOR")) > 0) c->pred_factor = atof(getenv("APM_PRED_FACTOR"));
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -714,6 +717,18 @@ static NewtonVecs make_nv(apm_ctx* c) {
 // slots and W^1/2 (see tile_engine.cuh "Factored posterior covariance")
 static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mask, int units = -1) {
     c->syrk_units += units < 0 ? B : units;
+    if (c->syrk_direct) {
+        // straight from L_K (k-major operand stages): no transposed, scaled copy of L_K
+        SyrkLkParams s;
+        s.LK = c->dSlotLK; s.lk_bs = (long long)c->mat; s.ldk = c->np; s.lk_idx = dSlots;
+        s.W = c->dVec[V_W]; s.w_bs = c->np;
+        s.M = c->dLB; s.m_bs = (long long)c->mat; s.ldm = c->np;
+        s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
+        s.status = c->dStatus; s.mask = mask;
+        prof_begin(c, KID_SYRK);
+        k_syrk_lk<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
+        return check_launch(c, "k_syrk_lk");
+    }
     dim3 yg(c->np / 32, c->np / 32, B), yb(32, 8);
     prof_begin(c, KID_TRANSPOSE);
     k_make_Y<<<yg, yb, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->dVec[V_WS], c->np, c->dZ,
