@@ -366,9 +366,9 @@ def run_gpu_arm(args):
             'bound': 'tensor', 'kernel': dom, 'achieved': d['achieved'], 'peak': peak_dmma, 'unit': 'TFLOP/s',
             'frac': d['frac'],
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_chol_dataflow launch (256 chains, n = 768) from the
-            # `ncu --set full` capture summarised in profiles/r1g_ncu_top_kernels_full.md: 4.21 GB + 1.20 GB
+            # `ncu --set full` capture summarised in profiles/r1h_ncu_top_kernels_full.md: 4.21 GB + 1.20 GB
             'traffic': 5.41e9 if (dom == 'k_chol' and n == 768 and B == 256) else None,
-            'traffic_note': 'bytes per launch from ncu (profiles/r1g_ncu_top_kernels_full.md); minimum (read K, write L) '
+            'traffic_note': 'bytes per launch from ncu (profiles/r1h_ncu_top_kernels_full.md); minimum (read K, write L) '
                             'is 1.28 GB, the blocked left-looking operand traffic with a working set > L2 is 4.7 GB',
             'achieved_per_launch_gflop': flops[dom] / d['launches'] / 1e9,
             'avg_launch_ms': d['ms_total'] / d['launches'],

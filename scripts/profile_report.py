@@ -18,7 +18,7 @@ ref = os.path.join(G, 'bench_%s_reference.json' % tag)
 if os.path.isfile(ref):
     rr = json.load(open(ref)); print('reference arm %.1f est/s on %d cores -> x%.0f' % (rr['value'], rr['cpu_baseline']['cores'], d['e2e']['value'] / rr['value']))
 print('cpu_baseline', d['cpu_baseline'])
-fam = {'k_chol_dataflow': 'k_chol', 'k_chol_step': 'k_chol', 'k_syrk_rev': 'k_syrk_sub', 'k_symv_lower': 'k_matvec', 'k_symv_reduce': 'k_matvec',
+fam = {'k_chol_dataflow': 'k_chol', 'k_chol_step': 'k_chol', 'k_syrk_rev': 'k_syrk_sub', 'k_syrk_lk': 'k_syrk_sub', 'k_symv_lower': 'k_matvec', 'k_symv_reduce': 'k_matvec',
        'k_lt_matvec': 'k_matvec', 'k_l_matvec_rev': 'k_matvec', 'k_fnew_from_s': 'k_matvec', 'k_make_Y': 'k_transpose_u', 'k_antitranspose': 'k_transpose_u',
        'k_transpose_u': 'k_transpose_u', 'k_newton_prep': 'k_newton_vec', 'k_newton_finish': 'k_newton_vec', 'k_is_logw': 'k_is_epilogue'}
 lines = [l for l in open(os.path.join(G, 'launches_%s_lane1.csv' % tag)) if not l.startswith('==')]
