@@ -289,12 +289,33 @@ class Engine(object):
         return f, C, nu, tau, ops, st
 
     # -- gpdemo.estimators
+    def _check_batch(self, keep, sl, B, unique=True):
+        """u must be (B, n, N) (or (n, N) for B = 1), slots one per chain, in range and distinct: the C side indexes
+        host / device memory with these without further checks."""
+        shape = tuple(keep.shape)
+        if len(shape) == 2:
+            shape = (1,) + shape
+        if len(shape) != 3 or shape[0] != B or shape[1] != self.n:
+            raise ValueError('u must have shape (%d, %d, N), got %r' % (B, self.n, tuple(keep.shape)))
+        N = shape[2]
+        if N < 1 or N > self.max_nimp:
+            raise ValueError('N = %d importance samples out of range for this engine (max_nimp = %d)' % (N, self.max_nimp))
+        if B < 1 or B > self.max_chains:
+            raise ValueError('batch of %d chains out of range for this engine (max_chains = %d)' % (B, self.max_chains))
+        if sl.shape != (B,):
+            raise ValueError('need one slot per chain (%d), got %r' % (B, sl.shape))
+        if sl.min() < 0 or sl.max() >= self.n_slots:
+            raise ValueError('slot index out of range (n_slots = %d)' % self.n_slots)
+        if unique and np.unique(sl).shape[0] != B:
+            raise ValueError('slots of one batch must be distinct')
+        return N
+
     def estimate_full(self, theta, u, slots):
         th = self._theta(theta)
         B = th.shape[0]
         p, dev, keep = self._bulk(u)
-        N = keep.shape[-1]
         sl = i32(np.atleast_1d(slots))
+        N = self._check_batch(keep, sl, B)
         out = np.empty(B)
         ops = np.empty(B, dtype=np.int32)
         st = np.empty(B, dtype=np.int32)
@@ -305,7 +326,7 @@ class Engine(object):
         sl = i32(np.atleast_1d(slots))
         B = sl.shape[0]
         p, dev, keep = self._bulk(u)
-        N = keep.shape[-1]
+        N = self._check_batch(keep, sl, B, unique=False)
         out = np.empty(B)
         st = np.empty(B, dtype=np.int32)
         check(self._L.apm_estimate_cached(self._h, _ptr(sl), p, dev, N, B, _ptr(out), _ptr(st)))
@@ -315,7 +336,7 @@ class Engine(object):
         sl = i32(np.atleast_1d(slots))
         B = sl.shape[0]
         p, dev, keep = self._bulk(u)
-        N = keep.shape[-1]
+        N = self._check_batch(keep, sl, B, unique=False)
         out = np.empty((B, N))
         check(self._L.apm_estimate_cached_weights(self._h, _ptr(sl), p, dev, N, B, _ptr(out)))
         return out
@@ -337,20 +358,21 @@ class Engine(object):
             th = self._theta(theta)
             thp = _ptr(th)
         p, dev, keep = self._bulk(u)
-        N = keep.shape[-1]
+        N = self._check_batch(keep, sl, B, unique=theta is not None)
         out = np.empty(B)
         st = np.empty(B, dtype=np.int32)
         check(self._L.apm_estimate_prior_mc(self._h, thp, _ptr(sl), p, dev, N, B, _ptr(out), _ptr(st)))
         return out, st
 
     # -- slots
-    def slot_export(self, slot, want_K=True, want_C=True):
+    def slot_export(self, slot, want_K=True, want_C=True, want_f=None):
+        want_f = want_C if want_f is None else want_f        # a prior-MC cache (chol K only) has neither C_chol nor f_post
         Kc = np.empty((self.n, self.n)) if want_K else None
         Cc = np.empty((self.n, self.n)) if want_C else None
-        f = np.empty(self.n)
+        f = np.empty(self.n) if want_f else None
         ld = np.empty(2)
         check(self._L.apm_slot_export(self._h, int(slot), _ptr(Kc) if want_K else None,
-                                      _ptr(Cc) if want_C else None, _ptr(f), _ptr(ld)))
+                                      _ptr(Cc) if want_C else None, _ptr(f) if want_f else None, _ptr(ld)))
         return Kc, Cc, f, ld
 
     def slot_import(self, slot, K_chol, C_chol=None, f_post=None):

@@ -18,6 +18,8 @@
 
 #include "../../include/apm_b200.h"
 #include "tile_engine.cuh"
+#include "chol_flow.cuh"
+#include "tmap_host.h"
 #include "vec_kernels.cuh"
 
 using namespace apm;
@@ -94,6 +96,15 @@ struct apm_ctx {
     std::vector<char> slot_mode;
     double* dLdB = nullptr;
     int *dFlowCounter = nullptr, *dFlowProgress = nullptr, *dFlowSkip = nullptr;
+    // k_chol_flow (TMA / mbarrier dataflow Cholesky): tensor maps over the three matrix buffers it factors into, and two
+    // sets of queue state + packed diagonal blocks (set 1: launches on the aux stream, which overlap the main stream's)
+    CUtensorMap tmLB, tmSlotLK, tmSlotLC;
+    bool tma_ok = false;
+    int *dFlow2Progress[2] = {nullptr, nullptr}, *dFlow2Skip[2] = {nullptr, nullptr};
+    double* dDiagPack[2] = {nullptr, nullptr};
+    int flow2_grid = 0;           // resident CTAs of k_chol_flow on the whole GPU
+    int flow2_ctas_per_chain = 0; // lanes: cap the persistent grid at this many CTAs per chain (0: no cap)
+    bool chol_old = false;        // APM_CHOL_OLD=1: the round-1 cp.async kernels (A/B measurements)
     int* dSmSem = nullptr; int sem_limit = 0;   // per-SM GEMM tokens of the Cholesky tasks (0: off), APM_GEMM_TOKENS
     int flow_grid = 0;        // persistent grid of k_chol_dataflow (SMs x occupancy); 0 = per-step launches
     int flow_group = 1 << 20; // chains per scheduling group (default: all chains = step-major order)
@@ -199,6 +210,7 @@ static int set_kernel_attrs() {
     if (g_attr_done) return APM_OK;
     CU_TRY(cudaFuncSetAttribute(k_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
@@ -313,6 +325,11 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     A(dev_alloc(c, &c->dFlowCounter, 4 * (MAX_LANES + 1)));
     A(dev_alloc(c, &c->dFlowProgress, B * (size_t)c->nb));
     A(dev_alloc(c, &c->dFlowSkip, B));
+    for (int q = 0; q < 2; q++) {
+        A(dev_alloc(c, &c->dFlow2Progress[q], B * (size_t)c->nb));
+        A(dev_alloc(c, &c->dFlow2Skip[q], B));
+        A(dev_alloc(c, &c->dDiagPack[q], Bm * (size_t)c->nb * DP_DOUBLES));
+    }
     A(dev_alloc(c, &c->dSmSem, 1024));
     cudaMemset(c->dSmSem, 0, 1024 * sizeof(int));
     if (getenv("APM_GEMM_TOKENS")) c->sem_limit = atoi(getenv("APM_GEMM_TOKENS"));
@@ -327,6 +344,23 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
         set_err("apm_create: pinned host allocation failed");
         apm_destroy(c);
         return APM_ERR_NOMEM;
+    }
+    {
+        // tensor maps of the Cholesky targets (the round-1 kernels remain behind APM_CHOL_OLD=1 for A/B timing)
+        c->chol_old = getenv("APM_CHOL_OLD") != nullptr;
+        c->tma_ok = make_matrix_tmap(&c->tmLB, c->dLB, c->np, (long long)Bm) &&
+                    make_matrix_tmap(&c->tmSlotLK, c->dSlotLK, c->np, (long long)n_slots) &&
+                    make_matrix_tmap(&c->tmSlotLC, c->dSlotLC, c->np, (long long)n_slots);
+        if (!c->tma_ok && !c->chol_old) {
+            set_err("apm_create: cuTensorMapEncodeTiled failed (TMA descriptors of the Cholesky operands)");
+            apm_destroy(c);
+            return APM_ERR_CUDA;
+        }
+        int occ = 0, sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_flow, CF_THREADS, CF_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
+        c->flow2_grid = occ * sms;
+        if (getenv("APM_FLOW_GRID") && atoi(getenv("APM_FLOW_GRID")) > 0) c->flow2_grid = atoi(getenv("APM_FLOW_GRID"));
     }
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
@@ -398,7 +432,8 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
             v->stream = v->copy_stream = v->aux_stream = nullptr;
             v->ev_k_ready = v->ev_lk_done = v->copy_done = v->ev_fork = v->ev_mix_fork = v->ev_mix_join = nullptr;
             v->u_staged = false;
-            if (!getenv("APM_LANE_FLOW")) v->flow_grid = 0;   // per-step Cholesky launches: no spinning CTAs beside other lanes' kernels
+            if (!getenv("APM_LANE_FLOW")) v->flow_grid = 0;   // (round-1 kernels) per-step Cholesky launches: no spinning CTAs beside other lanes' kernels
+            v->flow2_ctas_per_chain = getenv("APM_LANE_CTAS_PER_CHAIN") ? atoi(getenv("APM_LANE_CTAS_PER_CHAIN")) : 4;
             c->lanes.push_back(v);
             if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -643,6 +678,43 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
                     long long dst_bs, const int* dst_idx, const double* scale, int add_identity, double* logdet_parts,
                     const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr, int units = -1) {
     c->chol_units += units < 0 ? B : units;
+    if (!c->chol_old) {
+        // one persistent launch: warp-specialised TMA / mbarrier dataflow kernel (chol_flow.cuh)
+        const apm_ctx* r = c->root && !c->cached_only ? c->root : c;
+        cudaStream_t st = c->launch_stream ? c->launch_stream : c->stream;
+        const int set = (st == c->aux_stream) ? 1 : 0;
+        const CUtensorMap* tm = nullptr;
+        int m0 = 0;
+        if (dst_idx) {
+            tm = (dst == c->dSlotLK) ? &c->tmSlotLK : (dst == c->dSlotLC ? &c->tmSlotLC : nullptr);
+        } else if (dst >= r->dLB && dst < r->dLB + (size_t)r->maxB * r->mat) {
+            tm = &c->tmLB;
+            m0 = (int)((dst - r->dLB) / (long long)r->mat);
+        }
+        if (!tm) {
+            set_err("run_chol: destination buffer has no tensor map");
+            return APM_ERR_INVALID;
+        }
+        CholFlowParams q;
+        q.src = src; q.src_bs = src_bs; q.lds = c->np; q.src_idx = src_idx;
+        q.dst = dst; q.dst_bs = dst_bs; q.ldd = c->np; q.dst_idx = dst_idx; q.dst_m0 = m0; q.np = c->np;
+        q.scale = scale; q.scale_bs = c->np; q.add_identity = add_identity; q.nb = c->nb;
+        q.logdet_parts = logdet_parts; q.logdet_stride = c->nb; q.logdet_idx = logdet_idx;
+        q.inv_out = inv_out; q.inv_bs = (long long)c->nb * TB * TB;
+        q.status = c->dStatus; q.fail_code = fail_code; q.active = active; q.nchains = B;
+        q.counter = c->dFlowCounter + 2 * set; q.progress = c->dFlow2Progress[set]; q.list = c->dFlow2Skip[set];
+        q.diagpack = c->dDiagPack[set];
+        q.spin_ns = 64;
+        const int total_tasks = B * c->nb * (c->nb + 1) / 2;
+        prof_begin(c, KID_MISC);
+        k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb);
+        APM_TRY(check_launch(c, "k_chol_flow_init"));
+        int grid = c->flow2_grid < total_tasks ? c->flow2_grid : total_tasks;
+        if (c->flow2_ctas_per_chain > 0 && grid > c->flow2_ctas_per_chain * B) grid = c->flow2_ctas_per_chain * B;
+        prof_begin(c, KID_CHOL);
+        k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, q);
+        return check_launch(c, "k_chol_flow");
+    }
     CholParams p;
     p.src = src; p.src_bs = src_bs; p.lds = c->np; p.src_idx = src_idx;
     p.dst = dst; p.dst_bs = dst_bs; p.ldd = c->np; p.dst_idx = dst_idx;
@@ -1383,6 +1455,11 @@ static void lane_bind(apm_ctx* v, int lane, int off, int cnt, int N) {
     v->dStatus = r->dStatus + o; v->dActive = r->dActive + o; v->dIters = r->dIters + o;
     v->dSlotsA = r->dSlotsA + o; v->dSlotsB = r->dSlotsB + o;
     v->dFlowSkip = r->dFlowSkip + o; v->dFlowProgress = r->dFlowProgress + o * nb;
+    for (int q = 0; q < 2; q++) {
+        v->dFlow2Progress[q] = r->dFlow2Progress[q] + o * nb;
+        v->dFlow2Skip[q] = r->dFlow2Skip[q] + o;
+        v->dDiagPack[q] = r->dDiagPack[q] + o * nb * DP_DOUBLES;
+    }
     v->dNActive = r->dNActive + 4 * (lane + 1); v->dFlowCounter = r->dFlowCounter + 4 * (lane + 1);
     v->hKp = r->hKp + o * (2 * r->D + 1); v->hOut = r->hOut + o * 2; v->hInts = r->hInts + o * 4;
     v->hNActive = r->hNActive + 4 * (lane + 1);
@@ -1485,7 +1562,13 @@ static int cached_common(apm_ctx* c, const int* slots, const double* u, int u_on
     // all slots factored (written by apm_estimate_full) or all explicit (imported): use them as they are; a mixed batch
     // converts its factored slots to explicit chol(C) first
     int n_fact = 0;
-    for (int b = 0; b < B; b++) n_fact += slot_modes(c)[slots[b]] == 1;
+    for (int b = 0; b < B; b++) {
+        if (slot_modes(c)[slots[b]] == 2) {
+            set_err("slot " + std::to_string(slots[b]) + " holds a prior-MC cache (chol K only): no posterior approximation to sample from");
+            return APM_ERR_INVALID;
+        }
+        n_fact += slot_modes(c)[slots[b]] == 1;
+    }
     if (n_fact != 0 && n_fact != B) {
         for (int b = 0; b < B; b++) APM_TRY(slot_make_explicit(c, slots[b]));
         n_fact = 0;
@@ -1534,13 +1617,24 @@ extern "C" int apm_estimate_prior_mc(apm_ctx* c, const double* theta, const int*
     if (theta) {
         APM_TRY(full_front(c, theta, B, slots));
     } else {
+        // cached chol(K): the slot must hold a valid cache (any mode: the prior-MC tail only reads its L_K)
         APM_TRY(reset_status(c, B));
-        APM_TRY(upload_slots(c, slots, B, c->dSlotsA, false));
+        APM_TRY(upload_slots(c, slots, B, c->dSlotsA, true));
     }
     APM_TRY(stage_u(c, u, u_on_device, N, B));
     APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, nullptr, 1));
     CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
-    return fetch_results(c, B, c->dOut, 1, logml_out, nullptr, 0, chain_status);
+    std::vector<int> st(B);
+    APM_TRY(fetch_results(c, B, c->dOut, 1, logml_out, nullptr, 0, st.data()));
+    for (int b = 0; b < B; b++) {
+        if (theta) {
+            // the slot now holds chol(K) of this theta only: valid for prior-MC re-use, with no chol(C) / f_post behind it
+            slot_modes(c)[slots[b]] = 2;
+            slot_flags(c)[slots[b]] = (st[b] == 0);
+        }
+        if (chain_status) chain_status[b] = st[b];
+    }
+    return APM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1569,6 +1663,10 @@ extern "C" int apm_slot_export(apm_ctx* c, int slot, double* K_chol, double* C_c
         APM_TRY(check_launch(c, "k_export_lower"));
         CU_TRY(cudaMemcpyAsync(K_chol, stage, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if ((C_chol || f_post) && slot_modes(c)[slot] == 2) {
+        set_err("slot holds a prior-MC cache (chol K only)");
+        return APM_ERR_INVALID;
     }
     if (C_chol) {
         APM_TRY(slot_make_explicit(c, slot));     // a factored slot forms chol(C) = L_K V^-1 only now
@@ -1613,7 +1711,7 @@ extern "C" int apm_slot_import(apm_ctx* c, int slot, const double* K_chol, const
         CU_TRY(cudaMemcpyAsync(c->dSlotMu + (size_t)slot * c->np, f_post, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
     }
     CU_TRY(cudaStreamSynchronize(c->stream));
-    slot_modes(c)[slot] = 0;
+    slot_modes(c)[slot] = C_chol ? 0 : 2;      // chol(K) alone: a prior-MC cache
     slot_flags(c)[slot] = 1;
     return APM_OK;
 }

@@ -1,0 +1,559 @@
+// chol_flow.cuh -- batched blocked fp64 Cholesky as ONE persistent, warp-specialised dataflow kernel (sm_100a).
+//
+// Replaces LAPACK dpotrf of the reference's hot path (lpa.py:92; estimators.py:206, 209) for a batch of chains.
+//
+// Structure (per CTA: 1 producer warp + 4 consumer warps, 3 CTAs per SM):
+//   * tasks of the left-looking blocked factorisation on 64x64 tiles, claimed from a global queue in dependency order:
+//       diag(k)     : L_kk = chol(A_kk - sum_{j<k} L_kj L_kj^T)
+//       panel(k, i) : L_ik = (A_ik - sum_{j<k} L_ij L_kj^T) L_kk^{-T},  i > k
+//     A = diag(scale) * src * diag(scale) (+ I): B = I + W^1/2 K W^1/2 (lpa.py:91) is never stored.
+//   * the PRODUCER lane claims the next task while the consumers still work on the current one, polls the per-row
+//     progress counters (acquire loads), and streams the GEMM operands as 64 x 16 fp64 boxes (8 KB, one 128-byte
+//     swizzle row per matrix row) with TMA (cp.async.bulk.tensor.2d + mbarrier complete_tx) into a ring of stages; the
+//     packed diagonal block L_kk (36 lower 8x8 blocks + the 8 inverses of its diagonal 8x8 blocks, 22.5 KB contiguous in
+//     global memory, written by diag(k)) arrives by one 1-D bulk copy.  Dependencies are checked per operand block, so a
+//     panel GEMM runs before L_kk exists and a diagonal GEMM runs ahead of the last panel of its row (look-ahead for free).
+//   * the CONSUMER warps own 16 rows x 64 columns of the tile as DMMA accumulators (2 x 8 m8n8 tiles) from the source-tile
+//     load to the final store: GEMM from the swizzled stages (full/empty mbarriers, no block barrier in the k-loop), then
+//     the triangular solve entirely in registers on the tensor pipe.  The m8n8k4 contraction index is a free
+//     permutation as long as A and B agree: with k -> columns {2t, 2t+1} the A fragment of X * M IS the lane's own pair of
+//     accumulator values, so   X_p = T_p * inv(L_pp)^T   and   T_q -= X_p * L_qp^T   need no shuffle and no shared-memory
+//     round trip; B fragments are single 16-byte loads from the packed 8x8 blocks.
+//   * diag(k): 8 column panels; the warp owning the 8x8 diagonal block factors AND inverts it with quad shuffles
+//     (lane (g,t) holds D[g][2t..2t+1]), publishes both through the packed block buffer, every warp solves its rows on the
+//     tensor pipe and publishes them as the B operand of the trailing update: 2 named barriers per panel.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace apm {
+
+constexpr int CF_CONSUMER_WARPS = 4;
+constexpr int CF_CONSUMERS = CF_CONSUMER_WARPS * 32;
+constexpr int CF_THREADS = CF_CONSUMERS + 32;
+constexpr int CF_KC = 16;                              // doubles per k-chunk = one 128-byte swizzle row
+constexpr int CF_CHUNK_BYTES = TB * CF_KC * 8;         // 8192: one operand box
+#ifndef APM_CF_STAGES
+#define APM_CF_STAGES 3
+#endif
+#ifndef APM_CF_MIN_CTAS
+#define APM_CF_MIN_CTAS 3
+#endif
+constexpr int CF_STAGES = APM_CF_STAGES;
+constexpr int DP_LBLOCKS = 36;                         // lower 8x8 blocks (q >= p) of a 64x64 triangle, block (q,p) at q(q+1)/2 + p
+constexpr int DP_DOUBLES = (DP_LBLOCKS + 8) * 64;      // + inverses of the 8 diagonal 8x8 blocks
+constexpr int DP_BYTES = DP_DOUBLES * 8;               // 22528
+constexpr int CF_CTRL_BYTES = 512;
+constexpr int CF_SMEM_BYTES = 1024 + CF_STAGES * 2 * CF_CHUNK_BYTES + DP_BYTES + CF_CTRL_BYTES;   // 1024: manual alignment slack
+
+__device__ __forceinline__ int dp_block(int q, int p) { return (q * (q + 1) / 2 + p) * 64; }
+__device__ __forceinline__ int dp_inv(int p) { return (DP_LBLOCKS + p) * 64; }
+
+// ---- mbarrier / TMA / proxy-fence wrappers (PTX ISA 8.x, sm_90+) ---------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "APM_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra APM_MBAR_DONE;\n"
+        "bra APM_MBAR_WAIT;\n"
+        "APM_MBAR_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// generic <-> async proxy ordering.  The unqualified form only fences the shared-memory view (SASS FENCE.VIEW.ASYNC.S): data
+// that crosses CTAs through GLOBAL memory and is read or written by TMA / bulk copies needs the .global form
+// (FENCE.VIEW.ASYNC.G) on both sides of the release / acquire of its flag.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+
+__device__ __forceinline__ int cf_ld_relaxed(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cf_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cf_consumer_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(CF_CONSUMERS) : "memory"); }
+
+// ---- parameters ----------------------------------------------------------------------------------------------------
+struct CholFlowParams {
+    const double* src; long long src_bs; int lds; const int* src_idx;
+    double* dst; long long dst_bs; int ldd; const int* dst_idx;
+    int dst_m0;                  // tensor-map matrix index of chain 0 when dst_idx == null (lane views: offset into the root buffer)
+    int np;                      // rows per matrix in the tensor map (n padded)
+    const double* scale; long long scale_bs;
+    int add_identity;
+    int nb;
+    double* logdet_parts; int logdet_stride; const int* logdet_idx;
+    double* inv_out; long long inv_bs;          // optional (L_kk^{-1})^T of every diagonal block, [chain][nb][64*64]
+    int* status; int fail_code;
+    const int* active;
+    int nchains;
+    int* counter;                // [0] task queue head, [1] number of chains to factorise (both written by k_chol_flow_init)
+    int* progress;               // [nchains][nb] finished column blocks per block row
+    int* list;                   // [nchains] compacted indices of the chains to factorise (status == 0 and active)
+    double* diagpack;            // [nchains][nb][DP_DOUBLES]
+    int spin_ns;
+};
+
+// Zero the queue head and the progress counters, and compact the chains to factorise (status == 0 and inside the optional
+// Newton mask) into an ordered list: a launch for a few straggler chains enumerates only their tasks.  One launch instead
+// of two memsets + a snapshot kernel; block 0 / warp 0 does the (ballot) compaction.
+__global__ void k_chol_flow_init(int* counter, int* progress, int* list, const int* status, const int* active, int nchains, int nb) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nchains * nb) progress[e] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        int count = 0;
+        for (int b0 = 0; b0 < nchains; b0 += 32) {
+            const int b = b0 + threadIdx.x;
+            const bool on = b < nchains && status[b] == 0 && (!active || active[b]);
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) list[count + __popc(m & ((1u << threadIdx.x) - 1u))] = b;
+            count += __popc(m);
+        }
+        if (threadIdx.x == 0) {
+            counter[0] = 0;
+            counter[1] = count;
+        }
+    }
+}
+
+struct CfTask { int type, k, b, i; };   // type 0: panel(k, i), 1: diag(k), -1: no more tasks
+
+// ---- consumer-side pieces -----------------------------------------------------------------------------------------
+// accumulators of one consumer warp: rows 16*warp + 8*mt + g, columns 8*nt + 2t (+1)
+typedef double CfAcc[2][8][2];
+
+__device__ __forceinline__ void cf_load_src(CfAcc& acc, const double* __restrict__ S, int ld, const double* rs, const double* cs,
+                                            bool add_identity, int warp, int g, int t) {
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        const int r = warp * 16 + mt * 8 + g;
+        const double rsv = rs ? rs[r] : 1.0;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const int c = nt * 8 + 2 * t;
+            double2 v = __ldcg(reinterpret_cast<const double2*>(S + (size_t)r * ld + c));
+            if (rs || cs) {
+                v.x = rsv * v.x * (cs ? cs[c] : 1.0);
+                v.y = rsv * v.y * (cs ? cs[c + 1] : 1.0);
+            }
+            if (add_identity) {
+                if (r == c) v.x += 1.0;
+                if (r == c + 1) v.y += 1.0;
+            }
+            acc[mt][nt][0] = v.x;
+            acc[mt][nt][1] = v.y;
+        }
+    }
+}
+
+// acc -= A(rows of this warp) * B(all 64 rows)^T over one 16-deep chunk.  Stage layout: row r at r*128 bytes, its 16-byte
+// segment c at position c ^ (r & 7) (TMA SWIZZLE_128B).  DMMA kk contracts the columns {2kk, 2kk+1, 2kk+8, 2kk+9}: lane t
+// reads segment kk ^ 4(t>>1), half t&1 -- the 16 lanes of a half-warp then hit 16 distinct 8-byte bank pairs.
+template <bool DIAG>
+__device__ __forceinline__ void cf_gemm_chunk(CfAcc& acc, const unsigned char* sA, const unsigned char* sB, int warp, int g, int t) {
+    const uint32_t lo0 = (uint32_t)(((((t >> 1) << 2) ^ g) << 4) | ((t & 1) << 3));
+    const unsigned char* a_base = sA + (warp * 16 + g) * 128;
+    const unsigned char* b_base = sB + g * 128;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        const uint32_t lo = lo0 ^ (uint32_t)(kk << 4);
+        double a[2], b[8];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) a[mt] = -*reinterpret_cast<const double*>(a_base + mt * 1024 + lo);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+            if (!DIAG || nt <= 2 * warp + 1) b[nt] = *reinterpret_cast<const double*>(b_base + nt * 1024 + lo);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+            if (!DIAG || nt <= 2 * warp + 1) {
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            }
+    }
+}
+
+// acc <- acc * L^{-T} with L packed in dp (blocks + diagonal-block inverses); all in registers on the tensor pipe.
+// SKIP_ZERO: acc is the identity (rows above a panel are structurally zero there): panels p < row tile are skipped.
+template <bool SKIP_ZERO>
+__device__ __forceinline__ void cf_trsm_regs(CfAcc& acc, const double* dp, int warp, int g, int t) {
+    const int off = g * 8 + 2 * t;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        if (SKIP_ZERO && p < 2 * warp) continue;
+        const double2 bi = *reinterpret_cast<const double2*>(dp + dp_inv(p) + off);
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            double x0 = 0.0, x1 = 0.0;
+            dmma884(x0, x1, acc[mt][p][0], bi.x);
+            dmma884(x0, x1, acc[mt][p][1], bi.y);
+            acc[mt][p][0] = x0;
+            acc[mt][p][1] = x1;
+        }
+#pragma unroll
+        for (int q = p + 1; q < 8; q++) {
+            const double2 bl = *reinterpret_cast<const double2*>(dp + dp_block(q, p) + off);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                dmma884(acc[mt][q][0], acc[mt][q][1], -acc[mt][p][0], bl.x);
+                dmma884(acc[mt][q][0], acc[mt][q][1], -acc[mt][p][1], bl.y);
+            }
+        }
+    }
+}
+
+// Cholesky factor AND inverse of an 8x8 SPD block distributed over a warp in DMMA accumulator layout: lane (g, t) holds
+// D[g][2t], D[g][2t+1] in (d0, d1).  Returns L (strict upper zeroed) in (d0, d1) and L^-1 in (y0, y1).  Right-looking, one
+// column per step; communication by shuffles only.  L_jj = piv * rsqrt(piv) as in the round-1 engine.  One copy of the code
+// (noinline): it runs 8 times per diagonal task on one warp.
+struct CfChol8 { double d0, d1, y0, y1; int bad; };
+__device__ __noinline__ CfChol8 cf_chol8_inv8(double d0, double d1, int g, int t) {
+    const unsigned FULL = 0xffffffffu;
+    double y0 = (g == 2 * t) ? 1.0 : 0.0;
+    double y1 = (g == 2 * t + 1) ? 1.0 : 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int jt = j >> 1;
+        const double dj = (j & 1) ? d1 : d0;
+        const double piv = __shfl_sync(FULL, dj, j * 4 + jt);
+        if (!(piv > 0.0)) bad = 1;
+        const double r = rsqrt(piv);
+        double lij = __shfl_sync(FULL, dj, g * 4 + jt) * r;                 // L[g][j] for rows below the pivot
+        lij = (g > j) ? lij : ((g == j) ? piv * r : 0.0);
+        const double lm0 = __shfl_sync(FULL, lij, (2 * t) * 4);             // L[2t][j], L[2t+1][j]
+        const double lm1 = __shfl_sync(FULL, lij, (2 * t + 1) * 4);
+        if (2 * t > j) d0 = fma(-lij, lm0, d0);
+        if (2 * t + 1 > j) d1 = fma(-lij, lm1, d1);
+        if (t == jt) {
+            if (j & 1) d1 = lij; else d0 = lij;
+        }
+        // L Y = I by forward elimination: row j of Y is final after scaling, rows below lose their multiple of it
+        const double yj0 = __shfl_sync(FULL, y0, j * 4 + t) * r;
+        const double yj1 = __shfl_sync(FULL, y1, j * 4 + t) * r;
+        if (g == j) {
+            y0 = yj0;
+            y1 = yj1;
+        } else if (g > j) {
+            y0 = fma(-lij, yj0, y0);
+            y1 = fma(-lij, yj1, y1);
+        }
+    }
+    CfChol8 o;
+    o.d0 = d0; o.d1 = d1; o.y0 = y0; o.y1 = y1; o.bad = bad;
+    return o;
+}
+
+// acc (64x64 SPD tile, lower part valid) <- its Cholesky factor; dp <- packed blocks + diagonal-block inverses.
+// dg0 / dg1: this lane's diagonal entry of L in the warp's first / second row tile (1.0 for lanes that hold none).
+__device__ __forceinline__ void cf_potrf_regs(CfAcc& acc, double* dp, int warp, int g, int t, bool& bad, double& dg0, double& dg1) {
+    const int off = g * 8 + 2 * t;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        if (warp == (p >> 1)) {
+            const CfChol8 c8 = cf_chol8_inv8(acc[p & 1][p][0], acc[p & 1][p][1], g, t);
+            acc[p & 1][p][0] = c8.d0;
+            acc[p & 1][p][1] = c8.d1;
+            bad = bad || c8.bad;
+            const double dv = (g == 2 * t) ? c8.d0 : ((g == 2 * t + 1) ? c8.d1 : 1.0);
+            if (p & 1) dg1 = dv; else dg0 = dv;
+            *reinterpret_cast<double2*>(dp + dp_block(p, p) + off) = make_double2(c8.d0, c8.d1);
+            *reinterpret_cast<double2*>(dp + dp_inv(p) + off) = make_double2(c8.y0, c8.y1);
+        }
+        if (p == 7) break;
+        cf_consumer_bar();
+        const double2 bi = *reinterpret_cast<const double2*>(dp + dp_inv(p) + off);
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            const int m = 2 * warp + mt;
+            if (m > p) {
+                double x0 = 0.0, x1 = 0.0;
+                dmma884(x0, x1, acc[mt][p][0], bi.x);
+                dmma884(x0, x1, acc[mt][p][1], bi.y);
+                acc[mt][p][0] = x0;
+                acc[mt][p][1] = x1;
+                *reinterpret_cast<double2*>(dp + dp_block(m, p) + off) = make_double2(x0, x1);
+            }
+        }
+        cf_consumer_bar();
+#pragma unroll
+        for (int q = p + 1; q < 8; q++) {
+            if (2 * warp + 1 < q) continue;
+            const double2 bl = *reinterpret_cast<const double2*>(dp + dp_block(q, p) + off);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                if (2 * warp + mt >= q) {
+                    dmma884(acc[mt][q][0], acc[mt][q][1], -acc[mt][p][0], bl.x);
+                    dmma884(acc[mt][q][0], acc[mt][q][1], -acc[mt][p][1], bl.y);
+                }
+            }
+        }
+    }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const __grid_constant__ CUtensorMap tm, CholFlowParams p) {
+    extern __shared__ unsigned char cf_smem_raw[];
+    const uint32_t raw = smem_u32(cf_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = cf_smem_raw + (base - raw);
+    unsigned char* ring = sm;                                                  // stage s: A box at s*16 KB, B box 8 KB behind
+    double* dp = reinterpret_cast<double*>(sm + CF_STAGES * 2 * CF_CHUNK_BYTES);
+    unsigned char* ctrl = reinterpret_cast<unsigned char*>(dp) + DP_BYTES;
+    const uint32_t ring_u = base, dp_u = base + CF_STAGES * 2 * CF_CHUNK_BYTES, ctrl_u = dp_u + DP_BYTES;
+    // control block: mbarriers (8 B each) then task descriptors and scratch
+    const uint32_t bar_full = ctrl_u, bar_empty = ctrl_u + 8 * CF_STAGES;
+    const uint32_t bar_tq_full = ctrl_u + 16 * CF_STAGES, bar_tq_empty = bar_tq_full + 16;
+    const uint32_t bar_dp_full = bar_tq_empty + 16, bar_dp_empty = bar_dp_full + 8;
+    volatile CfTask* tq = reinterpret_cast<volatile CfTask*>(ctrl + 16 * CF_STAGES + 48);       // 2 descriptors
+    double* red = reinterpret_cast<double*>(ctrl + 16 * CF_STAGES + 48 + 2 * sizeof(CfTask));   // 4 partial log-dets
+    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= CF_CTRL_BYTES, "control block too small");
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < CF_STAGES; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, CF_CONSUMER_WARPS);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(bar_tq_full + 8 * s, 1);
+            mbar_init(bar_tq_empty + 8 * s, CF_CONSUMER_WARPS);
+        }
+        mbar_init(bar_dp_full, 1);
+        mbar_init(bar_dp_empty, CF_CONSUMER_WARPS);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int nb = p.nb;
+
+    if (warp == CF_CONSUMER_WARPS) {
+        // ================================ producer ================================
+        if (lane != 0) return;
+        uint32_t it = 0;
+        int n = 0;
+        const int nact = p.counter[1];
+        const int total_tasks = nact * (nb * (nb + 1) / 2);
+        for (;;) {
+            const int tix = atomicAdd(p.counter, 1);
+            int type = -1, k = 0, b = 0, i = 0;
+            if (tix < total_tasks) {
+                // step-major order: step k = [diag(k) of every chain][panel(k, i) chain-major]
+                int r = tix;
+                while (r >= nact * (nb - k)) { r -= nact * (nb - k); k++; }
+                if (r < nact) {
+                    type = 1; b = p.list[r]; i = k;
+                } else {
+                    r -= nact;
+                    type = 0; b = p.list[r / (nb - k - 1)]; i = k + 1 + r % (nb - k - 1);
+                }
+            }
+            const int slot = n & 1;
+            mbar_wait(bar_tq_empty + 8 * slot, ((n >> 1) & 1) ^ 1);
+            tq[slot].type = type; tq[slot].k = k; tq[slot].b = b; tq[slot].i = i;
+            mbar_arrive(bar_tq_full + 8 * slot);
+            if (type < 0) break;
+#ifdef APM_CF_DBG_LOCKSTEP
+            if (n > 0) mbar_wait(bar_dp_empty, (n - 1) & 1);
+#endif
+            const int m = p.dst_idx ? p.dst_idx[b] : p.dst_m0 + b;
+            const int row0 = m * p.np;
+            const int* prog = p.progress + (size_t)b * nb;
+            if (type == 0) {
+                if (k > 0) {
+                    while (cf_ld_relaxed(prog + i) < k) __nanosleep(p.spin_ns);
+                    while (cf_ld_relaxed(prog + k) < k) __nanosleep(p.spin_ns);
+                    __threadfence();
+                    fence_proxy_async_global();
+#ifdef APM_CF_DBG_DELAY
+                    __nanosleep(APM_CF_DBG_DELAY);
+#endif
+                    for (int c = 0; c < 4 * k; c++, it++) {
+                        const uint32_t s = it % CF_STAGES;
+                        mbar_wait(bar_empty + 8 * s, ((it / CF_STAGES) & 1) ^ 1);
+                        mbar_expect_tx(bar_full + 8 * s, 2 * CF_CHUNK_BYTES);
+                        tma_load_2d(ring_u + s * 2 * CF_CHUNK_BYTES, &tm, c * CF_KC, row0 + i * TB, bar_full + 8 * s);
+                        tma_load_2d(ring_u + s * 2 * CF_CHUNK_BYTES + CF_CHUNK_BYTES, &tm, c * CF_KC, row0 + k * TB, bar_full + 8 * s);
+                    }
+                }
+                while (cf_ld_relaxed(prog + k) < k + 1) __nanosleep(p.spin_ns);
+                __threadfence();
+                fence_proxy_async_global();
+#ifdef APM_CF_DBG_DELAY
+                __nanosleep(APM_CF_DBG_DELAY);
+#endif
+                if (n > 0) mbar_wait(bar_dp_empty, (n - 1) & 1);
+                mbar_expect_tx(bar_dp_full, DP_BYTES);
+                bulk_load_1d(dp_u, p.diagpack + ((size_t)b * nb + k) * DP_DOUBLES, DP_BYTES, bar_dp_full);
+            } else {
+                int known = 0;
+                for (int j = 0; j < k; j++) {
+                    if (known < j + 1) {
+                        while ((known = cf_ld_relaxed(prog + k)) < j + 1) __nanosleep(p.spin_ns);
+                        __threadfence();
+                        fence_proxy_async_global();
+#ifdef APM_CF_DBG_DELAY
+                        __nanosleep(APM_CF_DBG_DELAY);
+#endif
+                    }
+                    for (int c = 4 * j; c < 4 * j + 4; c++, it++) {
+                        const uint32_t s = it % CF_STAGES;
+                        mbar_wait(bar_empty + 8 * s, ((it / CF_STAGES) & 1) ^ 1);
+                        mbar_expect_tx(bar_full + 8 * s, CF_CHUNK_BYTES);
+                        tma_load_2d(ring_u + s * 2 * CF_CHUNK_BYTES, &tm, c * CF_KC, row0 + k * TB, bar_full + 8 * s);
+                    }
+                }
+                if (n > 0) mbar_wait(bar_dp_empty, (n - 1) & 1);   // keeps the producer within one task of the consumers
+            }
+            n++;
+        }
+        return;
+    }
+
+    // ================================ consumers ================================
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t it = 0;
+    int n = 0, pc = 0;
+    for (;; n++) {
+        const int slot = n & 1;
+        mbar_wait(bar_tq_full + 8 * slot, (n >> 1) & 1);
+        const int type = tq[slot].type, k = tq[slot].k, b = tq[slot].b, i = tq[slot].i;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tq_empty + 8 * slot);
+        if (type < 0) break;
+        const double* src = p.src + chain_index(p.src_idx, b) * p.src_bs;
+        double* dst = p.dst + chain_index(p.dst_idx, b) * p.dst_bs;
+        const double* sc = p.scale ? p.scale + (long long)b * p.scale_bs : nullptr;
+        int* prog = p.progress + (size_t)b * nb;
+        CfAcc acc;
+        if (type == 0) {
+            cf_load_src(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr, sc ? sc + k * TB : nullptr, false,
+                        warp, g, t);
+            for (int c = 0; c < 4 * k; c++, it++) {
+                const uint32_t s = it % CF_STAGES;
+                mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
+                cf_gemm_chunk<false>(acc, ring + s * 2 * CF_CHUNK_BYTES, ring + s * 2 * CF_CHUNK_BYTES + CF_CHUNK_BYTES, warp, g, t);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+            }
+            mbar_wait(bar_dp_full, pc & 1);
+            pc++;
+            cf_trsm_regs<false>(acc, dp, warp, g, t);
+            double* out = dst + (size_t)i * TB * p.ldd + k * TB;
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++)
+                    *reinterpret_cast<double2*>(out + (size_t)(warp * 16 + mt * 8 + g) * p.ldd + nt * 8 + 2 * t) =
+                        make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            fence_proxy_async_global();             // this thread's tile stores (generic proxy) will be read by other CTAs' TMA
+            cf_consumer_bar();                      // every warp's stores precede the release below (cumulativity)
+            if (tid == 0) cf_st_release(prog + i, k + 1);
+        } else {
+            const double* sck = sc ? sc + k * TB : nullptr;
+            cf_load_src(acc, src + (size_t)k * TB * p.lds + k * TB, p.lds, sck, sck, p.add_identity != 0, warp, g, t);
+            for (int c = 0; c < 4 * k; c++, it++) {
+                const uint32_t s = it % CF_STAGES;
+                mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
+                cf_gemm_chunk<true>(acc, ring + s * 2 * CF_CHUNK_BYTES, ring + s * 2 * CF_CHUNK_BYTES, warp, g, t);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+            }
+            bool bad = false;
+            double dg0 = 1.0, dg1 = 1.0;
+            cf_consumer_bar();      // the other warps may still read dp for the previous task (triangular solve / inverse block)
+            cf_potrf_regs(acc, dp, warp, g, t, bad, dg0, dg1);
+            // L_kk (explicit zeros above the diagonal) -> dst
+            double* out = dst + (size_t)k * TB * p.ldd + k * TB;
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+                    const bool lower = nt <= 2 * warp + mt;
+                    *reinterpret_cast<double2*>(out + (size_t)(warp * 16 + mt * 8 + g) * p.ldd + nt * 8 + 2 * t) =
+                        make_double2(lower ? acc[mt][nt][0] : 0.0, lower ? acc[mt][nt][1] : 0.0);
+                }
+            // partial log-det from the diagonal entries kept by cf_potrf_regs
+            double lg = (g >> 1 == t) ? log(dg0) + log(dg1) : 0.0;
+            lg = warp_sum(lg);
+            if (lane == 0) red[warp] = lg;
+            if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMax(&p.status[b], p.fail_code);
+            fence_proxy_async_smem();               // this thread's writes to dp (generic proxy) before the bulk store reads them
+            fence_proxy_async_global();             // ... and its stores of the L_kk tile before other CTAs' TMA reads
+#ifdef APM_CF_DBG_GENERIC_DP
+            cf_consumer_bar();
+            {
+                double2* gd = reinterpret_cast<double2*>(p.diagpack + ((size_t)b * nb + k) * DP_DOUBLES);
+                const double2* sd = reinterpret_cast<const double2*>(dp);
+                for (int e = tid; e < DP_DOUBLES / 2; e += CF_CONSUMERS) gd[e] = sd[e];
+                fence_proxy_async_global();
+            }
+#endif
+            cf_consumer_bar();
+            if (tid == 0) {
+#ifndef APM_CF_DBG_GENERIC_DP
+                bulk_store_1d(p.diagpack + ((size_t)b * nb + k) * DP_DOUBLES, dp_u, DP_BYTES);
+#endif
+                if (p.logdet_parts)
+                    p.logdet_parts[(size_t)chain_index(p.logdet_idx, b) * p.logdet_stride + k] = (red[0] + red[1]) + (red[2] + red[3]);
+                bulk_store_wait();
+                fence_proxy_async_global();
+                cf_st_release(prog + k, k + 1);
+            }
+            if (p.inv_out) {
+                // (L_kk^{-1})^T = I * L_kk^{-T} for the single right-hand-side solves of the Newton step (k_trsv2)
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        const bool dtile = nt == 2 * warp + mt;
+                        acc[mt][nt][0] = (dtile && g == 2 * t) ? 1.0 : 0.0;
+                        acc[mt][nt][1] = (dtile && g == 2 * t + 1) ? 1.0 : 0.0;
+                    }
+                cf_trsm_regs<true>(acc, dp, warp, g, t);
+                double* io = p.inv_out + (long long)b * p.inv_bs + (size_t)k * TB * TB;
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++)
+                        *reinterpret_cast<double2*>(io + (warp * 16 + mt * 8 + g) * TB + nt * 8 + 2 * t) =
+                            make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            }
+        }
+#ifdef APM_CF_DBG_LOCKSTEP
+        cf_consumer_bar();
+#endif
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dp_empty);   // dp may be overwritten by the next panel task's bulk copy
+    }
+}
+
+}  // namespace apm

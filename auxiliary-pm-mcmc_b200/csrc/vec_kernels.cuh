@@ -769,10 +769,13 @@ struct EpilogueParams {
 // lane still accumulates its elements in increasing order.
 __global__ void __launch_bounds__(256) k_is_logw(EpilogueParams p) {
     const int b = blockIdx.y;
-    if (p.status && p.status[b] != 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = blockIdx.x * 8 + warp;
     if (s >= p.N) return;
+    if (p.status && p.status[b] != 0) {      // failed chain: its log-weights are NaN, never stale workspace contents
+        if (lane == 0) p.logw[(size_t)b * p.N + s] = nan("");
+        return;
+    }
     const double* Fr = p.F + (long long)b * p.bs + (size_t)s * p.ld;
     double ll = 0.0, qk = 0.0, qu = 0.0;
     if (p.mode == 0) {
@@ -853,6 +856,10 @@ __global__ void __launch_bounds__(256) k_is_epilogue(EpilogueParams p) {
     m = red[0];
     for (int w = 1; w < 8; w++) m = fmax(m, red[w]);
     __syncthreads();
+    if (m == -INFINITY) {                    // every weight is zero: scipy's logsumexp gives -inf, not NaN (estimators.py:240)
+        if (threadIdx.x == 0) p.logml[b] = -INFINITY;
+        return;
+    }
     double sum = 0.0;
     for (int s = threadIdx.x; s < p.N; s += 256) sum += exp(lw[s] - m);
     sum = warp_sum(sum);

@@ -14,6 +14,7 @@ Plug-in path: any other `kernel_func(K_out, X, theta)` / `post_approx_func(K, y)
 reference, and the two Cholesky factorisations plus the importance-sampling tail run on the device.
 """
 import functools
+import weakref
 
 import numpy as np
 
@@ -31,17 +32,35 @@ class DeviceCache(object):
     """`cached_results` of one theta held in a device slot; behaves like the reference's
     `(K_chol, C_chol, f_post)` tuple (estimators.py:171-186, 240-241) on demand."""
 
-    def __init__(self, owner, slot):
+    def __init__(self, owner, slot, prior_only=False):
         self._owner = owner
         self.slot = slot
         self._gen = owner._generation
         self._host = None
+        self._prior_only = prior_only      # prior-MC cache: the slot holds chol(K) only
+        owner._live_caches.add(self)
+
+    def on_device(self):
+        """True while the slot of the engine that produced this cache still holds it."""
+        return self.slot is not None and self._gen == self._owner._generation
 
     def _fetch(self):
         if self._host is None:
-            Kc, Cc, f, _ = self._owner._engine.slot_export(self.slot)
-            self._host = (Kc, Cc, f)
+            if not self.on_device():
+                raise RuntimeError('apm_b200: cached_results outlived the engine that held it')
+            if self._prior_only:
+                Kc, _, _, _ = self._owner._engine.slot_export(self.slot, want_C=False)
+                self._host = (Kc, None, None)
+            else:
+                Kc, Cc, f, _ = self._owner._engine.slot_export(self.slot)
+                self._host = (Kc, Cc, f)
         return self._host
+
+    def _detach(self):
+        """The owner is about to rebuild its engine: bring the arrays to the host, forget the slot."""
+        if self.on_device():
+            self._fetch()
+        self.slot = None
 
     def __len__(self):
         return 3
@@ -54,7 +73,7 @@ class DeviceCache(object):
 
     def __del__(self):
         try:
-            if self._gen == self._owner._generation:
+            if self.on_device():
                 self._owner._release_slot(self.slot)
         except Exception:
             pass
@@ -77,6 +96,7 @@ class _DeviceEstimatorBase(object):
         self._engine_key = None
         self._generation = 0
         self._free_slots = []
+        self._live_caches = weakref.WeakSet()
         self._K_host = None
 
     def reset_cubic_op_count(self):
@@ -90,12 +110,21 @@ class _DeviceEstimatorBase(object):
             self.kernel_func(rec, self.X, theta)
         except Exception:
             return None
-        return rec.call
+        call = rec.call
+        if call is not None:
+            # a wrapper that hands the builder a transformed X (rescaled, permuted ...) must be honoured: the fused
+            # path computes on the estimator's own X, so it is only taken when that is what the builder was given
+            Xk = call[3]
+            if Xk is not self.X and not (np.shape(Xk) == np.shape(self.X) and np.array_equal(Xk, self.X)):
+                return None
+        return call
 
     def _get_engine(self, kind, eps, n_imp):
         key = (kind, float(eps))
         if self._engine is None or self._engine_key != key or self._engine.max_nimp < n_imp:
             if self._engine is not None:
+                for cache in list(self._live_caches):      # caches held by a sampler survive as host arrays
+                    cache._detach()
                 self._engine.close()
             self._engine = _capi.Engine(self._Xc, self._yc, kernel=kind, epsilon=eps, max_chains=1,
                                         n_slots=self._N_SLOTS, max_nimp=max(int(n_imp), 1))
@@ -196,7 +225,13 @@ class LogMarginalLikelihoodApproxPosteriorISEstimator(_DeviceEstimatorBase):
         eng = self._get_engine('iso', 0., N)
         slot = self._take_slot()
         try:
-            st = eng.slot_factor(slot, self._K_host, np.asarray(C, dtype=np.float64), f_post)
+            C = np.asarray(C, dtype=np.float64)
+            st = eng.slot_factor(slot, self._K_host, C, f_post)
+            if st == _capi.CHAIN_CHOL_C:
+                # same diagnostic as the reference (estimators.py:210-215): C is on the host on this path
+                e = np.linalg.eigvalsh(C)
+                raise InvalidCovarianceMatrixError('Posterior covariance matrix not PSD: '
+                                                   'sum of negative eigenvalues {0}'.format(e[e <= 0].sum()))
             _lpa.raise_for_status(st)
             out, st2 = eng.estimate_cached([slot], ns)
             _lpa.raise_for_status(int(st2[0]))
@@ -213,17 +248,23 @@ class LogMarginalLikelihoodApproxPosteriorISEstimator(_DeviceEstimatorBase):
         if cached_results is None:
             return self._full(ns, np.asarray(theta, dtype=np.float64))
         N = ns.shape[1]
-        if (isinstance(cached_results, DeviceCache) and cached_results._owner is self
-                and cached_results._gen == self._generation):
+        if isinstance(cached_results, DeviceCache) and cached_results._owner is self and cached_results.on_device():
             eng = self._engine
-            if eng.max_nimp < N:
-                raise ValueError('n_imp_sample grew beyond the size this cache was created for')
-            out, st = eng.estimate_cached([cached_results.slot], ns)
-            _lpa.raise_for_status(int(st[0]))
-            return float(out[0]), cached_results
+            if eng.max_nimp >= N:
+                out, st = eng.estimate_cached([cached_results.slot], ns)
+                _lpa.raise_for_status(int(st[0]))
+                return float(out[0]), cached_results
+            # more importance samples than the engine was sized for: fall through (the cache is brought to the host
+            # when the engine is rebuilt below)
         # a cache produced elsewhere (plain arrays): import it for this call
+        if isinstance(cached_results, DeviceCache) and cached_results._owner is self and cached_results.on_device():
+            cached_results._fetch()
         K_chol, C_chol, f_post = cached_results
-        eng = self._engine if (self._engine is not None and self._engine.max_nimp >= N) else self._get_engine('iso', 0., N)
+        if self._engine is not None and self._engine.max_nimp >= N:
+            eng = self._engine
+        else:
+            key = self._engine_key if self._engine_key is not None else ('iso', 0.)
+            eng = self._get_engine(key[0], key[1], N)
         slot = self._take_slot()
         try:
             eng.slot_import(slot, np.asarray(K_chol), np.asarray(C_chol), np.asarray(f_post))
@@ -274,11 +315,14 @@ class LogMarginalLikelihoodPriorMCEstimator(_DeviceEstimatorBase):
                 self._release_slot(slot)
                 raise
             self.n_cubic_ops += 1                               # estimators.py:322
-            return float(out[0]), DeviceCache(self, slot)
-        if isinstance(K_chol, DeviceCache) and K_chol._owner is self:
+            return float(out[0]), DeviceCache(self, slot, prior_only=True)
+        if isinstance(K_chol, DeviceCache) and K_chol._owner is self and K_chol.on_device() and self._engine.max_nimp >= N:
             out, st = self._engine.estimate_prior_mc(None, [K_chol.slot], ns)
             _lpa.raise_for_status(int(st[0]))
             return float(out[0]), K_chol
+        K_chol_in = K_chol
+        if isinstance(K_chol, DeviceCache):
+            K_chol = K_chol[0]                                  # (detached or foreign cache: its host copy of chol K)
         eng = self._engine if (self._engine is not None and self._engine.max_nimp >= N) else self._get_engine('iso', 0., N)
         slot = self._take_slot()
         try:
@@ -287,4 +331,4 @@ class LogMarginalLikelihoodPriorMCEstimator(_DeviceEstimatorBase):
             _lpa.raise_for_status(int(st[0]))
         finally:
             self._release_slot(slot)
-        return float(out[0]), K_chol
+        return float(out[0]), K_chol_in

@@ -213,6 +213,89 @@ def gen_samplers_fullsize(ref):
     np.savez_compressed(os.path.join(OUT, 'samplers_fullsize.npz'), **out)
 
 
+def gen_samplers_long(ref, which=None):
+    """1000-iteration chains of the unmodified reference at the headline shape (pima n=768, D=8, N_imp=64, isotropic
+    kernel as in the notebooks): the north-star's accept/reject bar ("first 1000 iterations") where the benchmark is quoted.
+    One file per sampler (tests/golden/samplers_long_<method>.npz) so the two can be generated in parallel
+    (`--only samplers_long ess+rdss`); ~10-20 min of CPU each."""
+    n, D, N, n_iter = 768, 8, 64, 1000
+    X, y, _ = synth.make_dataset(n, D, seed=0)
+    for method in ([which] if which else ['ess+rdss', 'mi+mh']):
+        prng = np.random.RandomState()
+        holder = []
+        smp = build_sampler(ref, method, X, y, N, prng, holder)
+        prng.seed(1000 + N)
+        theta_init = synth.draw_theta_prior(prng, D, ard=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            res = smp.get_samples(theta_init, n_iter)
+        thetas = res[0] if isinstance(res, tuple) else res
+        n_rej = np.atleast_1d(res[1]) if isinstance(res, tuple) else np.zeros(0)
+        out = dict(n=n, D=D, N=N, n_iter=n_iter, data_seed=0, chain_seed=1000 + N, thetas=thetas,
+                   n_reject=np.asarray(n_rej, dtype=np.int64), cubic_ops=holder[0].n_cubic_ops)
+        print('long', method, 'final theta', thetas[-1], 'rej', n_rej, 'ops', holder[0].n_cubic_ops, flush=True)
+        np.savez_compressed(os.path.join(OUT, 'samplers_long_%s.npz' % method.replace('+', '_')), **out)
+
+
+def gen_estimator_iters(ref):
+    """Headline-shape (pima n=768, D=8, ARD, N_imp=64) estimator goldens chosen so that the Newton loop takes
+    I = 3, 4, 5, 6 iterations (cubic_ops 6..9): the hybrid-Newton prediction is exercised both ways against the
+    REFERENCE (not against the repo's own APM_NO_HYBRID_NEWTON build).  Candidates are scanned with the cheap
+    Laplace-only estimator; one theta per iteration count is kept."""
+    n, D, N = 768, 8, 64
+    X, y, th_true = synth.make_dataset(n, D, 0)
+    kf = kernels_of(ref, 'ard')
+    rs = np.random.RandomState(4711)
+    found = {}
+    cands = []
+    for ls in (-2.5, -1.5, -0.5, 0.5, 1.5, 2.5, 3.5, 4.5):
+        for lt in (0.0, 0.7, 1.4):
+            cands.append(np.r_[ls, lt + 0.2 * rs.normal(size=D)])
+    for th in cands:
+        lap = ref.est.LogMarginalLikelihoodLaplaceEstimator(X, y, kf)
+        try:
+            lap(th)
+        except Exception as e:   # chol failure at extreme theta: not a candidate
+            print('skip', th[:2], type(e).__name__, flush=True)
+            continue
+        it = lap.n_cubic_ops
+        print('theta0 %.1f tau~%.1f -> I = %d' % (th[0], th[1], it), flush=True)
+        found.setdefault(it, []).append(th)
+        if all(len(found.get(k, [])) >= 1 for k in (3, 4, 5, 6)) and len(found.get(5, [])) >= 2:
+            break
+    thetas, iters = [], []
+    for it in sorted(found):
+        for th in found[it][:2 if it in (3, 5, 6) else 1]:
+            thetas.append(th)
+            iters.append(it)
+    thetas = np.array(thetas)
+    out = dict(X=X, y=y, thetas=thetas, newton_iters=np.array(iters), N=N, kind='ard', eps=EPS)
+    for t, th in enumerate(thetas):
+        est = ref.est.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf, ref.lpa.laplace_approximation)
+        u1 = np.random.RandomState(7100 + t).normal(size=(n, N))
+        u2 = np.random.RandomState(8100 + t).normal(size=(n, N))
+        full, cache = est(u1, th)
+        cached, _ = est(u2, None, cache)
+
+        def kf_ulp(K_out, X_, th_):
+            kf(K_out, X_, th_)
+            E = np.random.RandomState(1).uniform(-1, 1, size=K_out.shape) * 1.1e-16
+            K_out *= 1 + (E + E.T) / 2
+        est_p = ref.est.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf_ulp, ref.lpa.laplace_approximation)
+        key = 't%d_' % t
+        out[key + 'full'] = full
+        out[key + 'cached'] = cached
+        out[key + 'cubic_ops'] = est.n_cubic_ops
+        out[key + 'ulp_sens'] = abs(est_p(u1, th)[0] - full)
+        out[key + 'f_post'] = cache[2]
+        K_tmp = np.empty((n, n))
+        kf(K_tmp, X, th)
+        out[key + 'condK'] = np.linalg.cond(K_tmp)
+        print('iters golden', t, 'I', iters[t], 'ops', est.n_cubic_ops, 'full', full, 'sens', out[key + 'ulp_sens'],
+              'condK %.2e' % out[key + 'condK'], flush=True)
+    np.savez_compressed(os.path.join(OUT, 'estimator_pima_iters.npz'), **out)
+
+
 def gen_utils(ref):
     xs = np.linspace(-3, 3, 13)
     np.savez_compressed(
@@ -227,7 +310,7 @@ if __name__ == '__main__':
     ref = ref_loader.load_reference()
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 2 and sys.argv[1] == '--only':          # regenerate one fixture file, leave the others alone
-        globals()['gen_' + sys.argv[2]](ref)
+        globals()['gen_' + sys.argv[2]](ref, *sys.argv[3:])
         sys.exit(0)
     gen_utils(ref)
     gen_kernels(ref)
@@ -239,4 +322,6 @@ if __name__ == '__main__':
     gen_estimator(ref, 'breast_ard', 682, 9, 'ard', (64,), 2, 1, False)
     gen_samplers(ref)
     gen_samplers_fullsize(ref)
+    gen_estimator_iters(ref)
+    gen_samplers_long(ref)
     print('golden vectors written to', OUT)

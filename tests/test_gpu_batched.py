@@ -155,3 +155,31 @@ def test_headline_shape_chains_match_reference(tag, method):
     if g[key + 'n_reject'].size:
         assert np.array_equal(out['n_reject'][0][-g[key + 'n_reject'].size:], g[key + 'n_reject'])
     eng.close()
+
+
+@pytest.mark.parametrize('method', ['ess+rdss', 'mi+mh'])
+def test_headline_shape_1000_iterations_match_reference(method):
+    """The north-star's bar at the shape the benchmark is quoted on: the accept/reject sequence of the UNMODIFIED reference
+    over the first 1000 iterations at pima shape (n = 768, D = 8, N_imp = 64; tests/golden/samplers_long_*.npz,
+    oracle/gen_golden.py:gen_samplers_long) against chain 0 of a lock-step batch on the GPU: zero divergence, same reject and
+    cubic-op counts."""
+    g = load_golden('samplers_long_' + method.replace('+', '_'))
+    n, D, N, n_iter = int(g['n']), int(g['D']), int(g['N']), int(g['n_iter'])
+    X, y, _ = synth.make_dataset(n, D, seed=int(g['data_seed']))
+    ref = g['thetas']
+    assert ref.shape[0] == n_iter == 1000
+    seeds = [int(g['chain_seed']), 7, 8, 9]
+    B = len(seeds)
+    eng = _capi.Engine(X, y, kernel='iso', max_chains=B, n_slots=2 * B, max_nimp=N)
+    drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, 2, method,
+                                    batched.make_log_prior(D, False), seeds, prop_scales=[0.5, 0.5])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out = drv.get_samples(None, n_iter, theta_init_sampler=lambda prng: synth.draw_theta_prior(prng, D, ard=False))
+    assert np.all(out['failed'] == 0)
+    div = first_divergence(out['thetas'][0], ref)
+    assert div is None, 'chain diverges from the reference at iteration %d of 1000' % div
+    assert out['n_cubic_ops'][0] == int(g['cubic_ops'])
+    if g['n_reject'].size:
+        assert np.array_equal(out['n_reject'][0][-g['n_reject'].size:], g['n_reject'])
+    eng.close()

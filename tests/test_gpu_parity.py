@@ -132,6 +132,34 @@ def test_estimators_vs_reference_golden(name):
     eng.close()
 
 
+def test_newton_iteration_counts_vs_reference_golden():
+    """Headline shape (pima n = 768, D = 8, ARD, N_imp = 64) with thetas chosen so that the reference's Newton loop takes
+    I = 2, 3, 4, 5, 6 iterations (cubic_ops 5..9; tests/golden/estimator_pima_iters.npz, oracle/gen_golden.py:gen_estimator_iters):
+    the hybrid-Newton prediction ("the next iteration is the last") is right for some of these chains and wrong for others, and
+    every one must reproduce the REFERENCE's estimate and operation count -- as one mixed batch and one chain at a time."""
+    g = load_golden('estimator_pima_iters')
+    X, y, thetas, N = g['X'], g['y'], g['thetas'], int(g['N'])
+    n, T = X.shape[0], thetas.shape[0]
+    assert set(int(v) for v in g['newton_iters']) >= {3, 4, 5, 6}
+    eng = _capi.Engine(X, y, kernel='ard', epsilon=float(g['eps']), max_chains=T, max_nimp=N)
+    u1 = np.stack([np.random.RandomState(7100 + t).normal(size=(n, N)) for t in range(T)])
+    u2 = np.stack([np.random.RandomState(8100 + t).normal(size=(n, N)) for t in range(T)])
+    full, ops, st = eng.estimate_full(thetas, u1, np.arange(T))
+    cached, st2 = eng.estimate_cached(np.arange(T), u2)
+    for t in range(T):
+        key = 't%d_' % t
+        tol = max(REL * abs(g[key + 'full']), 10. * float(g[key + 'ulp_sens']))
+        assert st[t] == 0 and st2[t] == 0
+        assert ops[t] == int(g[key + 'cubic_ops']) == int(g['newton_iters'][t]) + 3
+        assert abs(full[t] - g[key + 'full']) < tol, (t, full[t], g[key + 'full'])
+        assert abs(cached[t] - g[key + 'cached']) < tol
+        ftol = max(1e-10, 100. * float(g[key + 'condK']) * 1.1e-16)
+        assert rel_err(eng.slot_export(t)[2], g[key + 'f_post']) < ftol
+        one, ops1, st1 = eng.estimate_full(thetas[t:t + 1], u1[t:t + 1], [T - 1 - t if T - 1 - t != t else t])
+        assert st1[0] == 0 and ops1[0] == ops[t] and one[0] == full[t]        # batch composition does not change a chain's bits
+    eng.close()
+
+
 @pytest.mark.parametrize('n,D,N,kind', [(1, 1, 1, 'iso'), (5, 2, 3, 'ard'), (63, 3, 2, 'iso'), (64, 3, 64, 'ard'),
                                         (65, 2, 65, 'iso'), (200, 5, 130, 'ard')])
 def test_ragged_sizes_vs_oracle(n, D, N, kind):

@@ -125,3 +125,21 @@ def test_oracle_parallel_ep_matches_textbook_sequential_ep():
         # EP matches the first two moments better than Laplace: its mean differs from the Laplace mode
         f_l = orc.laplace_approximation(K, y, calc_cov=False)[0]
         assert np.max(np.abs(f_l - mu_p)) > 1e-3
+
+
+def test_estimator_newton_iteration_counts():
+    """Oracle vs the reference at the headline shape for thetas on which the reference's Newton loop takes 3 / 5 / 6
+    iterations (estimator_pima_iters.npz): the restatement stops at the same iteration (Quirk 3)."""
+    g = load_golden('estimator_pima_iters')
+    X, y, thetas, N = g['X'], g['y'], g['thetas'], int(g['N'])
+    n = X.shape[0]
+    kf = lambda K, X_, th: orc.diagonal_squared_exponential_kernel(K, X_, th, float(g['eps']))  # noqa: E731
+    iters = [int(v) for v in g['newton_iters']]
+    picks = [iters.index(3), iters.index(5), iters.index(6)]       # one theta per count keeps the CPU suite short
+    for t in picks:
+        est = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf, orc.laplace_approximation)
+        u1 = np.random.RandomState(7100 + t).normal(size=(n, N))
+        full, _ = est(u1, thetas[t])
+        key = 't%d_' % t
+        assert est.n_cubic_ops == int(g[key + 'cubic_ops']) == iters[t] + 3
+        assert abs(full - g[key + 'full']) <= max(1e-10 * abs(g[key + 'full']), 10. * float(g[key + 'ulp_sens']))
