@@ -98,7 +98,7 @@ struct apm_ctx {
     int *dFlowCounter = nullptr, *dFlowProgress = nullptr, *dFlowSkip = nullptr;
     // k_chol_flow (TMA / mbarrier dataflow Cholesky): tensor maps over the three matrix buffers it factors into, and two
     // sets of queue state + packed diagonal blocks (set 1: launches on the aux stream, which overlap the main stream's)
-    CUtensorMap tmLB, tmSlotLK, tmSlotLC;
+    CUtensorMap tmLB, tmSlotLK, tmSlotLC, tmK;
     bool tma_ok = false;
     int *dFlow2Progress[2] = {nullptr, nullptr}, *dFlow2Skip[2] = {nullptr, nullptr};
     double* dDiagPack[2] = {nullptr, nullptr};
@@ -349,6 +349,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
         // tensor maps of the Cholesky targets (the round-1 kernels remain behind APM_CHOL_OLD=1 for A/B timing)
         c->chol_old = getenv("APM_CHOL_OLD") != nullptr;
         c->tma_ok = make_matrix_tmap(&c->tmLB, c->dLB, c->np, (long long)Bm) &&
+                    make_matrix_tmap(&c->tmK, c->dK, c->np, (long long)Bm) &&
                     make_matrix_tmap(&c->tmSlotLK, c->dSlotLK, c->np, (long long)n_slots) &&
                     make_matrix_tmap(&c->tmSlotLC, c->dSlotLC, c->np, (long long)n_slots);
         if (!c->tma_ok && !c->chol_old) {
@@ -691,13 +692,25 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
             tm = &c->tmLB;
             m0 = (int)((dst - r->dLB) / (long long)r->mat);
         }
-        if (!tm) {
-            set_err("run_chol: destination buffer has no tensor map");
+        // source: K (Newton / chol K), the LB buffer (M' in place) or a slot's L_C buffer (explicit covariance in place)
+        const CUtensorMap* tms = nullptr;
+        int ms0 = 0;
+        if (src_idx) {
+            tms = (src == c->dSlotLC) ? &c->tmSlotLC : (src == c->dSlotLK ? &c->tmSlotLK : nullptr);
+        } else if (src >= r->dK && src < r->dK + (size_t)r->maxB * r->mat) {
+            tms = &c->tmK;
+            ms0 = (int)((src - r->dK) / (long long)r->mat);
+        } else if (src >= r->dLB && src < r->dLB + (size_t)r->maxB * r->mat) {
+            tms = &c->tmLB;
+            ms0 = (int)((src - r->dLB) / (long long)r->mat);
+        }
+        if (!tm || !tms) {
+            set_err("run_chol: source / destination buffer has no tensor map");
             return APM_ERR_INVALID;
         }
         CholFlowParams q;
         q.src = src; q.src_bs = src_bs; q.lds = c->np; q.src_idx = src_idx;
-        q.dst = dst; q.dst_bs = dst_bs; q.ldd = c->np; q.dst_idx = dst_idx; q.dst_m0 = m0; q.np = c->np;
+        q.dst = dst; q.dst_bs = dst_bs; q.ldd = c->np; q.dst_idx = dst_idx; q.dst_m0 = m0; q.src_m0 = ms0; q.zero = 0; q.np = c->np;
         q.scale = scale; q.scale_bs = c->np; q.add_identity = add_identity; q.nb = c->nb;
         q.logdet_parts = logdet_parts; q.logdet_stride = c->nb; q.logdet_idx = logdet_idx;
         q.inv_out = inv_out; q.inv_bs = (long long)c->nb * TB * TB;
@@ -712,7 +725,7 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
         int grid = c->flow2_grid < total_tasks ? c->flow2_grid : total_tasks;
         if (c->flow2_ctas_per_chain > 0 && grid > c->flow2_ctas_per_chain * B) grid = c->flow2_ctas_per_chain * B;
         prof_begin(c, KID_CHOL);
-        k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, q);
+        k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, q);
         return check_launch(c, "k_chol_flow");
     }
     CholParams p;

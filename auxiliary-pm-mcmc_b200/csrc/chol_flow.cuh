@@ -7,9 +7,10 @@
 //       diag(k)     : L_kk = chol(A_kk - sum_{j<k} L_kj L_kj^T)
 //       panel(k, i) : L_ik = (A_ik - sum_{j<k} L_ij L_kj^T) L_kk^{-T},  i > k
 //     A = diag(scale) * src * diag(scale) (+ I): B = I + W^1/2 K W^1/2 (lpa.py:91) is never stored.
-//   * the PRODUCER lane claims the next task while the consumers still work on the current one, polls the per-row
-//     progress counters (acquire loads), and streams the GEMM operands as 64 x 16 fp64 boxes (8 KB, one 128-byte
-//     swizzle row per matrix row) with TMA (cp.async.bulk.tensor.2d + mbarrier complete_tx) into a ring of stages; the
+//   * the PRODUCER lane claims the next task while the consumers still work on the current one, streams the source tile
+//     (no dependency) and then, after polling the per-row progress counters (acquire loads), the GEMM operands as 64 x 16
+//     fp64 boxes (8 KB, one 128-byte swizzle row per matrix row) with TMA (cp.async.bulk.tensor.2d + mbarrier complete_tx)
+//     into a ring of stages; the
 //     packed diagonal block L_kk (36 lower 8x8 blocks + the 8 inverses of its diagonal 8x8 blocks, 22.5 KB contiguous in
 //     global memory, written by diag(k)) arrives by one 1-D bulk copy.  Dependencies are checked per operand block, so a
 //     panel GEMM runs before L_kk exists and a diagonal GEMM runs ahead of the last panel of its row (look-ahead for free).
@@ -102,13 +103,25 @@ __device__ __forceinline__ void cf_st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void cf_consumer_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(CF_CONSUMERS) : "memory"); }
+// publish barrier of a panel task: only warp 0 (which releases the progress counter) waits, the others just arrive.  Two ids,
+// alternating by task parity: a warp can be at most one task ahead of warp 0.
+__device__ __forceinline__ void cf_publish_arrive(int odd) {
+    if (odd) asm volatile("bar.arrive 3, %0;\n" ::"n"(CF_CONSUMERS) : "memory");
+    else asm volatile("bar.arrive 2, %0;\n" ::"n"(CF_CONSUMERS) : "memory");
+}
+__device__ __forceinline__ void cf_publish_sync(int odd) {
+    if (odd) asm volatile("bar.sync 3, %0;\n" ::"n"(CF_CONSUMERS) : "memory");
+    else asm volatile("bar.sync 2, %0;\n" ::"n"(CF_CONSUMERS) : "memory");
+}
 
 // ---- parameters ----------------------------------------------------------------------------------------------------
 struct CholFlowParams {
     const double* src; long long src_bs; int lds; const int* src_idx;
     double* dst; long long dst_bs; int ldd; const int* dst_idx;
     int dst_m0;                  // tensor-map matrix index of chain 0 when dst_idx == null (lane views: offset into the root buffer)
-    int np;                      // rows per matrix in the tensor map (n padded)
+    int src_m0;                  // same for the source tensor map when src_idx == null
+    int np;                      // rows per matrix in the tensor maps (n padded)
+    int zero;                    // always 0, but only known at run time (see cf_release_stage)
     const double* scale; long long scale_bs;
     int add_identity;
     int nb;
@@ -152,16 +165,22 @@ struct CfTask { int type, k, b, i; };   // type 0: panel(k, i), 1: diag(k), -1: 
 // accumulators of one consumer warp: rows 16*warp + 8*mt + g, columns 8*nt + 2t (+1)
 typedef double CfAcc[2][8][2];
 
-__device__ __forceinline__ void cf_load_src(CfAcc& acc, const double* __restrict__ S, int ld, const double* rs, const double* cs,
-                                            bool add_identity, int warp, int g, int t) {
+// Source tile from the ring: the producer streams the 64x64 tile as four 64x16 boxes (two stages, A-half / B-half each) ahead
+// of the GEMM chunks -- it never depends on another task, so it is in shared memory before the consumers get to the task.
+// Box j holds columns 16j..16j+15; this thread's pair (row r, columns 8nt+2t, +1) is the 16-byte segment 4(nt&1)+t of row r
+// in box nt/2, stored at segment position (4(nt&1)+t) ^ (r & 7).   acc <- diag(rs) * S * diag(cs) (+ I).
+__device__ __forceinline__ void cf_src_from_stage(CfAcc& acc, const unsigned char* stage, int half, const double* rs, const double* cs,
+                                                  bool add_identity, int warp, int g, int t) {
 #pragma unroll
     for (int mt = 0; mt < 2; mt++) {
         const int r = warp * 16 + mt * 8 + g;
         const double rsv = rs ? rs[r] : 1.0;
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
+        for (int q = 0; q < 4; q++) {
+            const int nt = half * 4 + q;                     // this stage covers column tiles 4*half .. 4*half+3
             const int c = nt * 8 + 2 * t;
-            double2 v = __ldcg(reinterpret_cast<const double2*>(S + (size_t)r * ld + c));
+            const unsigned char* box = stage + (q >> 1) * CF_CHUNK_BYTES;
+            double2 v = *reinterpret_cast<const double2*>(box + r * 128 + ((((q & 1) * 4 + t) ^ g) << 4));
             if (rs || cs) {
                 v.x = rsv * v.x * (cs ? cs[c] : 1.0);
                 v.y = rsv * v.y * (cs ? cs[c + 1] : 1.0);
@@ -170,10 +189,28 @@ __device__ __forceinline__ void cf_load_src(CfAcc& acc, const double* __restrict
                 if (r == c) v.x += 1.0;
                 if (r == c + 1) v.y += 1.0;
             }
-            acc[mt][nt][0] = v.x;
-            acc[mt][nt][1] = v.y;
+            if (half == 0) { acc[mt][q][0] = v.x; acc[mt][q][1] = v.y; }
+            else { acc[mt][4 + q][0] = v.x; acc[mt][4 + q][1] = v.y; }
         }
     }
+}
+
+// Hand a ring stage back to the producer.  The stage may only be overwritten (by TMA, asynchronously) after every fragment
+// load of this warp has completed; a load has certainly completed once an instruction that consumes its result has issued.
+// mbarrier.arrive has no data dependency on the loads, so the hardware may perform it while they are still queued (measured:
+// wrong tiles as soon as two CTAs share an SM).  The arrive therefore gets an address operand that depends on `dep`, a value
+// computed from the results of the chunk's last DMMAs / the registers the loads filled: (dep & zero) == 0 at run time.
+__device__ __forceinline__ void cf_release_stage(uint32_t bar, uint32_t dep, int zero, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar + (dep & (uint32_t)zero));
+}
+__device__ __forceinline__ uint32_t cf_acc_dep(const CfAcc& acc) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) d |= (uint32_t)__double2hiint(acc[mt][nt][1]);
+    return d;
 }
 
 // acc -= A(rows of this warp) * B(all 64 rows)^T over one 16-deep chunk.  Stage layout: row r at r*128 bytes, its 16-byte
@@ -197,7 +234,8 @@ __device__ __forceinline__ void cf_gemm_chunk(CfAcc& acc, const unsigned char* s
         for (int nt = 0; nt < 8; nt++)
             if (!DIAG || nt <= 2 * warp + 1) {
 #pragma unroll
-                for (int mt = 0; mt < 2; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+                for (int mt = 0; mt < 2; mt++)
+                    if (!DIAG || nt <= 2 * warp + mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
             }
     }
 }
@@ -321,7 +359,7 @@ __device__ __forceinline__ void cf_potrf_regs(CfAcc& acc, double* dp, int warp, 
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const __grid_constant__ CUtensorMap tm, CholFlowParams p) {
+__global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tms, CholFlowParams p) {
     extern __shared__ unsigned char cf_smem_raw[];
     const uint32_t raw = smem_u32(cf_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -381,11 +419,19 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
             tq[slot].type = type; tq[slot].k = k; tq[slot].b = b; tq[slot].i = i;
             mbar_arrive(bar_tq_full + 8 * slot);
             if (type < 0) break;
-#ifdef APM_CF_DBG_LOCKSTEP
-            if (n > 0) mbar_wait(bar_dp_empty, (n - 1) & 1);
-#endif
             const int m = p.dst_idx ? p.dst_idx[b] : p.dst_m0 + b;
             const int row0 = m * p.np;
+            {
+                // source tile (i, k): four boxes in two stages.  No dependency: nobody writes this tile before this task does.
+                const int srow = (p.src_idx ? p.src_idx[b] : p.src_m0 + b) * p.np + i * TB;
+                for (int h = 0; h < 2; h++, it++) {
+                    const uint32_t s = it % CF_STAGES;
+                    mbar_wait(bar_empty + 8 * s, ((it / CF_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(bar_full + 8 * s, 2 * CF_CHUNK_BYTES);
+                    tma_load_2d(ring_u + s * 2 * CF_CHUNK_BYTES, &tms, k * TB + 32 * h, srow, bar_full + 8 * s);
+                    tma_load_2d(ring_u + s * 2 * CF_CHUNK_BYTES + CF_CHUNK_BYTES, &tms, k * TB + 32 * h + 16, srow, bar_full + 8 * s);
+                }
+            }
             const int* prog = p.progress + (size_t)b * nb;
             if (type == 0) {
                 if (k > 0) {
@@ -393,9 +439,6 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                     while (cf_ld_relaxed(prog + k) < k) __nanosleep(p.spin_ns);
                     __threadfence();
                     fence_proxy_async_global();
-#ifdef APM_CF_DBG_DELAY
-                    __nanosleep(APM_CF_DBG_DELAY);
-#endif
                     for (int c = 0; c < 4 * k; c++, it++) {
                         const uint32_t s = it % CF_STAGES;
                         mbar_wait(bar_empty + 8 * s, ((it / CF_STAGES) & 1) ^ 1);
@@ -407,9 +450,6 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                 while (cf_ld_relaxed(prog + k) < k + 1) __nanosleep(p.spin_ns);
                 __threadfence();
                 fence_proxy_async_global();
-#ifdef APM_CF_DBG_DELAY
-                __nanosleep(APM_CF_DBG_DELAY);
-#endif
                 if (n > 0) mbar_wait(bar_dp_empty, (n - 1) & 1);
                 mbar_expect_tx(bar_dp_full, DP_BYTES);
                 bulk_load_1d(dp_u, p.diagpack + ((size_t)b * nb + k) * DP_DOUBLES, DP_BYTES, bar_dp_full);
@@ -420,9 +460,6 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                         while ((known = cf_ld_relaxed(prog + k)) < j + 1) __nanosleep(p.spin_ns);
                         __threadfence();
                         fence_proxy_async_global();
-#ifdef APM_CF_DBG_DELAY
-                        __nanosleep(APM_CF_DBG_DELAY);
-#endif
                     }
                     for (int c = 4 * j; c < 4 * j + 4; c++, it++) {
                         const uint32_t s = it % CF_STAGES;
@@ -449,20 +486,36 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tq_empty + 8 * slot);
         if (type < 0) break;
-        const double* src = p.src + chain_index(p.src_idx, b) * p.src_bs;
         double* dst = p.dst + chain_index(p.dst_idx, b) * p.dst_bs;
         const double* sc = p.scale ? p.scale + (long long)b * p.scale_bs : nullptr;
         int* prog = p.progress + (size_t)b * nb;
+        const bool diag = type != 0;
         CfAcc acc;
-        if (type == 0) {
-            cf_load_src(acc, src + (size_t)i * TB * p.lds + k * TB, p.lds, sc ? sc + i * TB : nullptr, sc ? sc + k * TB : nullptr, false,
-                        warp, g, t);
+        // ---- source tile A_ik (two stages of the ring)
+        {
+            const double* rs = sc ? sc + i * TB : nullptr;
+            const double* cs = sc ? sc + k * TB : nullptr;
+            const bool ident = diag && p.add_identity != 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++, it++) {
+                const uint32_t s = it % CF_STAGES;
+                mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
+                cf_src_from_stage(acc, ring + s * 2 * CF_CHUNK_BYTES, h, rs, cs, ident, warp, g, t);
+                uint32_t dep = 0;
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) dep |= (uint32_t)__double2hiint(acc[mt][4 * h + q][1]);
+                cf_release_stage(bar_empty + 8 * s, dep, p.zero, lane);
+            }
+        }
+        if (!diag) {
+            // ---- panel(k, i): T = A_ik - L_i,0..k-1 L_k,0..k-1^T ; L_ik = T L_kk^-T
             for (int c = 0; c < 4 * k; c++, it++) {
                 const uint32_t s = it % CF_STAGES;
                 mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
                 cf_gemm_chunk<false>(acc, ring + s * 2 * CF_CHUNK_BYTES, ring + s * 2 * CF_CHUNK_BYTES + CF_CHUNK_BYTES, warp, g, t);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+                cf_release_stage(bar_empty + 8 * s, cf_acc_dep(acc), p.zero, lane);
             }
             mbar_wait(bar_dp_full, pc & 1);
             pc++;
@@ -475,17 +528,20 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                     *reinterpret_cast<double2*>(out + (size_t)(warp * 16 + mt * 8 + g) * p.ldd + nt * 8 + 2 * t) =
                         make_double2(acc[mt][nt][0], acc[mt][nt][1]);
             fence_proxy_async_global();             // this thread's tile stores (generic proxy) will be read by other CTAs' TMA
-            cf_consumer_bar();                      // every warp's stores precede the release below (cumulativity)
-            if (tid == 0) cf_st_release(prog + i, k + 1);
+            // every warp's stores precede warp 0's release (cumulativity through the barrier); warps 1..3 do not wait
+            if (warp == 0) {
+                cf_publish_sync(n & 1);
+                if (lane == 0) cf_st_release(prog + i, k + 1);
+            } else {
+                cf_publish_arrive(n & 1);
+            }
         } else {
-            const double* sck = sc ? sc + k * TB : nullptr;
-            cf_load_src(acc, src + (size_t)k * TB * p.lds + k * TB, p.lds, sck, sck, p.add_identity != 0, warp, g, t);
+            // ---- diag(k): D = A_kk - L_k,0..k-1 L_k,0..k-1^T (tiles on / below the diagonal) ; L_kk = chol(D)
             for (int c = 0; c < 4 * k; c++, it++) {
                 const uint32_t s = it % CF_STAGES;
                 mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
                 cf_gemm_chunk<true>(acc, ring + s * 2 * CF_CHUNK_BYTES, ring + s * 2 * CF_CHUNK_BYTES, warp, g, t);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+                cf_release_stage(bar_empty + 8 * s, cf_acc_dep(acc), p.zero, lane);
             }
             bool bad = false;
             double dg0 = 1.0, dg1 = 1.0;
@@ -508,20 +564,9 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
             if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMax(&p.status[b], p.fail_code);
             fence_proxy_async_smem();               // this thread's writes to dp (generic proxy) before the bulk store reads them
             fence_proxy_async_global();             // ... and its stores of the L_kk tile before other CTAs' TMA reads
-#ifdef APM_CF_DBG_GENERIC_DP
-            cf_consumer_bar();
-            {
-                double2* gd = reinterpret_cast<double2*>(p.diagpack + ((size_t)b * nb + k) * DP_DOUBLES);
-                const double2* sd = reinterpret_cast<const double2*>(dp);
-                for (int e = tid; e < DP_DOUBLES / 2; e += CF_CONSUMERS) gd[e] = sd[e];
-                fence_proxy_async_global();
-            }
-#endif
             cf_consumer_bar();
             if (tid == 0) {
-#ifndef APM_CF_DBG_GENERIC_DP
                 bulk_store_1d(p.diagpack + ((size_t)b * nb + k) * DP_DOUBLES, dp_u, DP_BYTES);
-#endif
                 if (p.logdet_parts)
                     p.logdet_parts[(size_t)chain_index(p.logdet_idx, b) * p.logdet_stride + k] = (red[0] + red[1]) + (red[2] + red[3]);
                 bulk_store_wait();
@@ -548,9 +593,6 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                             make_double2(acc[mt][nt][0], acc[mt][nt][1]);
             }
         }
-#ifdef APM_CF_DBG_LOCKSTEP
-        cf_consumer_bar();
-#endif
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_dp_empty);   // dp may be overwritten by the next panel task's bulk copy
     }

@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dinv0, (size_t)B * nb * 4096 * 8)); CK(cudaMalloc(&dinv1, (size_t)B * nb * 4096 * 8));
     CK(cudaMalloc(&dld0, (size_t)B * nb * 8)); CK(cudaMalloc(&dld1, (size_t)B * nb * 8));
     CK(cudaMalloc(&ddp, (size_t)B * nb * DP_BYTES));
-    CK(cudaMalloc(&dstatus, B * 4)); CK(cudaMalloc(&dactive, B * 4)); CK(cudaMalloc(&dcounter, 64)); CK(cudaMalloc(&dprogress, (size_t)B * nb * 4)); CK(cudaMalloc(&dskip, B * 4));
+    CK(cudaMalloc(&dstatus, B * 4)); CK(cudaMalloc(&dactive, B * 4)); CK(cudaMalloc(&dcounter, 256)); CK(cudaMemset(dcounter, 0, 256)); CK(cudaMalloc(&dprogress, (size_t)B * nb * 4)); CK(cudaMalloc(&dskip, B * 4));
     CK(cudaMemcpy(dX, hX.data(), hX.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dpar, hpar.data(), hpar.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dscale, hscale.data(), hscale.size() * 8, cudaMemcpyHostToDevice));
@@ -79,8 +79,8 @@ int main(int argc, char** argv) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_old, k_chol_dataflow, TILE_THREADS, TILE_SMEM_BYTES));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_new, k_chol_flow, CF_THREADS, CF_SMEM_BYTES));
     printf("occupancy: old %d CTAs/SM, new %d CTAs/SM, %d SMs\n", occ_old, occ_new, sms);
-    CUtensorMap tm0, tm1;
-    if (!make_matrix_tmap(&tm1, dL1, np, B) || !make_matrix_tmap(&tm0, dL0, np, B)) { printf("tensor map creation failed\n"); return 2; }
+    CUtensorMap tmK, tm1;
+    if (!make_matrix_tmap(&tm1, dL1, np, B) || !make_matrix_tmap(&tmK, dK, np, B)) { printf("tensor map creation failed\n"); return 2; }
 
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -126,7 +126,7 @@ int main(int argc, char** argv) {
         {
             CholFlowParams p;
             p.src = inplace ? dL1 : dK; p.src_bs = (long long)mat; p.lds = np; p.src_idx = nullptr;
-            p.dst = dL1; p.dst_bs = (long long)mat; p.ldd = np; p.dst_idx = nullptr; p.dst_m0 = 0; p.np = np;
+            p.dst = dL1; p.dst_bs = (long long)mat; p.ldd = np; p.dst_idx = nullptr; p.dst_m0 = 0; p.src_m0 = 0; p.zero = 0; p.np = np;
             p.scale = scaled ? dscale : nullptr; p.scale_bs = np; p.add_identity = scaled;
             p.nb = nb; p.logdet_parts = dld1; p.logdet_stride = nb; p.logdet_idx = nullptr;
             p.inv_out = scaled ? dinv1 : nullptr; p.inv_bs = (long long)nb * 4096;
@@ -141,7 +141,7 @@ int main(int argc, char** argv) {
                 if (r == 1) CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(dstatus, 0, B * 4));
                 k_chol_flow_init<<<(B * nb + 255) / 256, 256>>>(p.counter, p.progress, p.list, dstatus, p.active, B, nb);
-                k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, p);
+                k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, inplace ? tm1 : tmK, p);
                 if (inplace && r >= 1) break;
             }
             CK(cudaEventRecord(e1));
@@ -150,6 +150,14 @@ int main(int argc, char** argv) {
             CK(cudaGetLastError());
             CK(cudaEventElapsedTime(&ms_new, e0, e1));
             ms_new /= inplace ? 1 : reps;
+#ifdef APM_CF_DBG_VERIFY
+            {
+                int hc[32];
+                CK(cudaMemcpy(hc, dcounter, 128, cudaMemcpyDeviceToHost));
+                printf("verify: (warp-chunk checks) stale A %d, stale B %d; first: k=%d i=%d c=%d b=%d code=%d\n", hc[12], hc[13], hc[15], hc[16], hc[17], hc[18], hc[19]);
+                CK(cudaMemset(dcounter, 0, 256));
+            }
+#endif
         }
         CK(cudaMemcpy(h0.data(), dL0, B * mat * 8, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(h1.data(), dL1, B * mat * 8, cudaMemcpyDeviceToHost));
