@@ -155,7 +155,7 @@ def test_newton_iteration_counts_vs_reference_golden():
         assert abs(cached[t] - g[key + 'cached']) < tol
         ftol = max(1e-10, 100. * float(g[key + 'condK']) * 1.1e-16)
         assert rel_err(eng.slot_export(t)[2], g[key + 'f_post']) < ftol
-        one, ops1, st1 = eng.estimate_full(thetas[t:t + 1], u1[t:t + 1], [T - 1 - t if T - 1 - t != t else t])
+        one, ops1, st1 = eng.estimate_full(thetas[t:t + 1], u1[t:t + 1], [T + t])          # (a spare slot)
         assert st1[0] == 0 and ops1[0] == ops[t] and one[0] == full[t]        # batch composition does not change a chain's bits
     eng.close()
 
