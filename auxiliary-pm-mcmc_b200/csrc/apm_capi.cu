@@ -8,12 +8,10 @@
 // np = n rounded up to 64; padded rows/cols carry the identity so every kernel works on whole tiles.
 #include <cuda_runtime.h>
 #include <math.h>
-#include <sched.h>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/apm_b200.h"
@@ -41,7 +39,6 @@ static void set_err(const std::string& s) { g_err = s; }
         if (r__ != APM_OK) return r__; \
     } while (0)
 
-constexpr int MAX_LANES = 16;
 enum { V_F = 0, V_W, V_WS, V_B, V_A, V_T, V_S, V_FNEW, V_S2, V_COUNT };
 
 // kernel ids for launch accounting / profiling
@@ -83,7 +80,6 @@ struct apm_ctx {
     int *dMaskM = nullptr, *dMaskB = nullptr, *dDoneM = nullptr;
     // f_new = s / W^1/2 instead of the second mat-vec of a B-space Newton step (k_fnew_from_s); APM_FNEW_THR=0 disables it
     double fnew_thr = 1e-2;
-    bool syrk_direct = true;   // M' from L_K directly (k_syrk_lk) instead of k_make_Y + k_syrk_rev; APM_SYRK_VIA_Y=1: the latter
     bool newton_b_finishers = true;   // set by run_newton: some chain finished in a B-space round (needs the covariance phase)
     size_t mat = 0;  // np*np
     double *dX = nullptr, *dy = nullptr;
@@ -95,7 +91,7 @@ struct apm_ctx {
     double* dSlotMt = nullptr;
     std::vector<char> slot_mode;
     double* dLdB = nullptr;
-    int *dFlowCounter = nullptr, *dFlowProgress = nullptr, *dFlowSkip = nullptr;
+    int* dFlowCounter = nullptr;   // per queue set: [0] task queue head, [1] chains to factorise (k_chol_flow_init)
     // k_chol_flow (TMA / mbarrier dataflow Cholesky): tensor maps over the three matrix buffers it factors into, and two
     // sets of queue state + packed diagonal blocks (set 1: launches on the aux stream, which overlap the main stream's)
     CUtensorMap tmLB, tmSlotLK, tmSlotLC, tmK;
@@ -103,11 +99,8 @@ struct apm_ctx {
     int *dFlow2Progress[2] = {nullptr, nullptr}, *dFlow2Skip[2] = {nullptr, nullptr};
     double* dDiagPack[2] = {nullptr, nullptr};
     int flow2_grid = 0;           // resident CTAs of k_chol_flow on the whole GPU
-    int flow2_ctas_per_chain = 0; // lanes: cap the persistent grid at this many CTAs per chain (0: no cap)
-    bool chol_old = false;        // APM_CHOL_OLD=1: the round-1 cp.async kernels (A/B measurements)
-    int* dSmSem = nullptr; int sem_limit = 0;   // per-SM GEMM tokens of the Cholesky tasks (0: off), APM_GEMM_TOKENS
-    int flow_grid = 0;        // persistent grid of k_chol_dataflow (SMs x occupancy); 0 = per-step launches
-    int flow_group = 1 << 20; // chains per scheduling group (default: all chains = step-major order)
+    unsigned long long* dWork = nullptr;   // [0] chain-Choleskys, [1] M' builds executed (counted on the device: the masks are only known there)
+    int newton_r0 = 5;            // Newton rounds queued before the first host round trip (APM_NEWTON_R0)
     double *dSymvDirect = nullptr, *dSymvPart = nullptr;   // scratch of the symmetric mat-vec
     double* dInvB = nullptr;   // (L_kk^{-1})^T diagonal blocks of chol(B): [max_chains][nb][64*64]
     double* dVec[V_COUNT] = {nullptr};
@@ -118,21 +111,9 @@ struct apm_ctx {
     double *hKp = nullptr, *hOut = nullptr;
     int *hInts = nullptr, *hNActive = nullptr;
     std::vector<char> slot_valid;
-    // Lanes: a FULL estimate of many chains is split into up to n_lanes contiguous chain groups, each driven by its own
-    // host thread on its own streams (per-step Cholesky launches), so that the latency-bound Newton kernels, the
-    // host round trips and the stragglers of one group overlap the DMMA kernels of the others.  A lane is a view of
-    // the root context: the same buffers with every per-chain pointer offset to the group's first chain.
-    apm_ctx* root = nullptr;            // non-null in a lane view (and in a companion context: the slot owner)
-    bool cached_only = false;           // companion context (apm_create_companion): shares the parent's cache slots, cached estimates only
-    std::vector<apm_ctx*> lanes;        // root only
-    int n_lanes = 1, lane_min_chains = 32, lane_min_batch = 128;
-    cudaEvent_t ev_fork = nullptr;
-    int lane_rc = 0;
-    std::string lane_err;
+    apm_ctx* root = nullptr;            // companion context (apm_create_companion): the slot owner
+    bool cached_only = false;           // companion context: shares the parent's cache slots, cached estimates only
     int64_t launches = 0;
-    // work actually executed by the DMMA kernel families, in units of n^3/3 flops per chain (apm_work_count): the
-    // Cholesky launches factor only the chains of their mask, the hybrid Newton skips whole factorisations
-    int64_t chol_units = 0, syrk_units = 0;
     int newton_b_finisher_count = 0;   // set by run_newton: chains that finished in a B-space round
     std::vector<void*> allocs;
     // optional per-kernel CUDA-event timing (apm_profile): events bracket every launch on ctx->stream
@@ -208,12 +189,9 @@ static int check_launch(apm_ctx* c, const char* what) {
 static int g_attr_done = 0;
 static int set_kernel_attrs() {
     if (g_attr_done) return APM_OK;
-    CU_TRY(cudaFuncSetAttribute(k_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_chol_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(k_syrk_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_lk, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_gemm_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
@@ -266,16 +244,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->maxNpad = (max_nimp + TB - 1) / TB * TB;
     c->mat = (size_t)c->np * c->np;
     c->slot_mode.assign(n_slots, 0);
-    c->slot_valid.assign(n_slots, 0);  // (lane views share the root's flags: slot_flags())
-    {
-        int occ = 0, sms = 0, coop = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_dataflow, TILE_THREADS, TILE_SMEM_BYTES) == cudaSuccess &&
-            occ > 0 && coop && !getenv("APM_CHOL_STEPWISE"))
-            c->flow_grid = occ * sms / (getenv("APM_FLOW_GRID_DIV") && atoi(getenv("APM_FLOW_GRID_DIV")) > 0 ? atoi(getenv("APM_FLOW_GRID_DIV")) : 1);
-        if (getenv("APM_CHOL_GROUP")) c->flow_group = atoi(getenv("APM_CHOL_GROUP")) > 0 ? atoi(getenv("APM_CHOL_GROUP")) : (1 << 20);
-    }
+    c->slot_valid.assign(n_slots, 0);
     const size_t B = max_chains, np = c->np;
     const size_t Bm = parent ? 1 : B;      // chains with full matrix workspaces
     const size_t own_slots = parent ? 0 : (size_t)n_slots;
@@ -319,20 +288,17 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     A(dev_alloc(c, &c->dStatus, B));
     A(dev_alloc(c, &c->dActive, B));
     A(dev_alloc(c, &c->dIters, B));
-    A(dev_alloc(c, &c->dNActive, 4 * (MAX_LANES + 1)));
+    A(dev_alloc(c, &c->dNActive, 8));
     A(dev_alloc(c, &c->dSlotsA, B));
     A(dev_alloc(c, &c->dSlotsB, B));
-    A(dev_alloc(c, &c->dFlowCounter, 4 * (MAX_LANES + 1)));
-    A(dev_alloc(c, &c->dFlowProgress, B * (size_t)c->nb));
-    A(dev_alloc(c, &c->dFlowSkip, B));
+    A(dev_alloc(c, &c->dFlowCounter, 8));
+    A(dev_alloc(c, &c->dWork, 4));
     for (int q = 0; q < 2; q++) {
         A(dev_alloc(c, &c->dFlow2Progress[q], B * (size_t)c->nb));
         A(dev_alloc(c, &c->dFlow2Skip[q], B));
         A(dev_alloc(c, &c->dDiagPack[q], Bm * (size_t)c->nb * DP_DOUBLES));
     }
-    A(dev_alloc(c, &c->dSmSem, 1024));
-    cudaMemset(c->dSmSem, 0, 1024 * sizeof(int));
-    if (getenv("APM_GEMM_TOKENS")) c->sem_limit = atoi(getenv("APM_GEMM_TOKENS"));
+    if (rc == APM_OK) cudaMemset(c->dWork, 0, 4 * sizeof(unsigned long long));
     if (rc != APM_OK) {
         apm_destroy(c);
         return rc;
@@ -340,19 +306,18 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     if (cudaMallocHost(&c->hKp, B * (2 * D + 1) * sizeof(double)) != cudaSuccess ||
         cudaMallocHost(&c->hOut, B * 2 * sizeof(double)) != cudaSuccess ||
         cudaMallocHost(&c->hInts, B * 4 * sizeof(int)) != cudaSuccess ||
-        cudaMallocHost(&c->hNActive, 4 * (MAX_LANES + 1) * sizeof(int)) != cudaSuccess) {
+        cudaMallocHost(&c->hNActive, 8 * sizeof(int)) != cudaSuccess) {
         set_err("apm_create: pinned host allocation failed");
         apm_destroy(c);
         return APM_ERR_NOMEM;
     }
     {
-        // tensor maps of the Cholesky targets (the round-1 kernels remain behind APM_CHOL_OLD=1 for A/B timing)
-        c->chol_old = getenv("APM_CHOL_OLD") != nullptr;
+        // tensor maps of the Cholesky sources / targets
         c->tma_ok = make_matrix_tmap(&c->tmLB, c->dLB, c->np, (long long)Bm) &&
                     make_matrix_tmap(&c->tmK, c->dK, c->np, (long long)Bm) &&
                     make_matrix_tmap(&c->tmSlotLK, c->dSlotLK, c->np, (long long)n_slots) &&
                     make_matrix_tmap(&c->tmSlotLC, c->dSlotLC, c->np, (long long)n_slots);
-        if (!c->tma_ok && !c->chol_old) {
+        if (!c->tma_ok) {
             set_err("apm_create: cuTensorMapEncodeTiled failed (TMA descriptors of the Cholesky operands)");
             apm_destroy(c);
             return APM_ERR_CUDA;
@@ -366,7 +331,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
     c->hybrid_newton = getenv("APM_NO_HYBRID_NEWTON") == nullptr;
-    c->syrk_direct = getenv("APM_SYRK_VIA_Y") == nullptr;
+    if (getenv("APM_NEWTON_R0") && atoi(getenv("APM_NEWTON_R0")) > 0) c->newton_r0 = atoi(getenv("APM_NEWTON_R0"));
     if (getenv("APM_FNEW_THR")) c->fnew_thr = atof(getenv("APM_FNEW_THR"));
     if (getenv("APM_PRED_FACTOR") && atof(getenv("APM_PRED_FACTOR")) > 0) c->pred_factor = atof(getenv("APM_PRED_FACTOR"));
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -398,57 +363,6 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
         set_err(std::string("apm_create: upload: ") + cudaGetErrorString(e));
         apm_destroy(c);
         return APM_ERR_CUDA;
-    }
-    // lane views (streams and events of their own; buffers are the root's)
-    if (parent) {
-        c->n_lanes = 1;
-    } else if (getenv("APM_LANES")) {
-        c->n_lanes = atoi(getenv("APM_LANES"));
-    } else {
-        // default: 8 lanes, but never more host threads than this process's share of the cores (lane threads wait on
-        // their streams; torchrun exports LOCAL_WORLD_SIZE = processes on this node)
-        int cores = (int)std::thread::hardware_concurrency();
-        cpu_set_t set;
-        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
-        const int procs = getenv("LOCAL_WORLD_SIZE") && atoi(getenv("LOCAL_WORLD_SIZE")) > 0 ? atoi(getenv("LOCAL_WORLD_SIZE")) : 1;
-        c->n_lanes = cores > 0 ? cores / procs : 8;
-        if (c->n_lanes > 8) c->n_lanes = 8;
-    }
-    if (c->n_lanes < 1) c->n_lanes = 1;
-    if (c->n_lanes > MAX_LANES) c->n_lanes = MAX_LANES;
-    if (getenv("APM_LANE_MIN_CHAINS") && atoi(getenv("APM_LANE_MIN_CHAINS")) > 0) c->lane_min_chains = atoi(getenv("APM_LANE_MIN_CHAINS"));
-    if (getenv("APM_LANE_MIN_BATCH") && atoi(getenv("APM_LANE_MIN_BATCH")) > 0) c->lane_min_batch = atoi(getenv("APM_LANE_MIN_BATCH"));
-    if (c->n_lanes > 1) {
-        if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
-            set_err("apm_create: event creation failed");
-            apm_destroy(c);
-            return APM_ERR_CUDA;
-        }
-        for (int l = 0; l < c->n_lanes; l++) {
-            apm_ctx* v = new apm_ctx(*c);
-            v->root = c;
-            v->lanes.clear(); v->allocs.clear(); v->ev_pool.clear(); v->pending.clear(); v->slot_valid.clear(); v->slot_mode.clear();
-            v->prof = false;
-            v->launches = 0;
-            v->stream = v->copy_stream = v->aux_stream = nullptr;
-            v->ev_k_ready = v->ev_lk_done = v->copy_done = v->ev_fork = v->ev_mix_fork = v->ev_mix_join = nullptr;
-            v->u_staged = false;
-            if (!getenv("APM_LANE_FLOW")) v->flow_grid = 0;   // (round-1 kernels) per-step Cholesky launches: no spinning CTAs beside other lanes' kernels
-            v->flow2_ctas_per_chain = getenv("APM_LANE_CTAS_PER_CHAIN") ? atoi(getenv("APM_LANE_CTAS_PER_CHAIN")) : 4;
-            c->lanes.push_back(v);
-            if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaStreamCreateWithFlags(&v->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaEventCreateWithFlags(&v->ev_k_ready, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&v->ev_lk_done, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&v->ev_mix_fork, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&v->ev_mix_join, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&v->copy_done, cudaEventDisableTiming) != cudaSuccess) {
-                set_err("apm_create: lane stream/event creation failed");
-                apm_destroy(c);
-                return APM_ERR_CUDA;
-            }
-        }
     }
     *out = c;
     return APM_OK;
@@ -489,19 +403,6 @@ extern "C" int apm_destroy(apm_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     prof_resolve(c);
-    for (apm_ctx* v : c->lanes) {
-        if (v->stream) cudaStreamDestroy(v->stream);
-        if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
-        if (v->aux_stream) cudaStreamDestroy(v->aux_stream);
-        if (v->ev_k_ready) cudaEventDestroy(v->ev_k_ready);
-        if (v->ev_lk_done) cudaEventDestroy(v->ev_lk_done);
-        if (v->ev_mix_fork) cudaEventDestroy(v->ev_mix_fork);
-        if (v->ev_mix_join) cudaEventDestroy(v->ev_mix_join);
-        if (v->copy_done) cudaEventDestroy(v->copy_done);
-        delete v;
-    }
-    c->lanes.clear();
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->ev_k_ready) cudaEventDestroy(c->ev_k_ready);
@@ -533,17 +434,12 @@ extern "C" int apm_synchronize(apm_ctx* c) {
 extern "C" int apm_set_overlap(apm_ctx* c, int enable) {
     if (!c) return APM_ERR_INVALID;
     c->overlap_chol_k = enable != 0;
-    for (apm_ctx* l : c->lanes) l->overlap_chol_k = c->overlap_chol_k;
     return APM_OK;
 }
 extern "C" int apm_set_newton(apm_ctx* c, double tol, int max_iters) {
     if (!c || !(tol > 0) || max_iters <= 0) return APM_ERR_INVALID;
     c->tol = tol;
     c->max_iters = max_iters;
-    for (apm_ctx* l : c->lanes) {
-        l->tol = tol;
-        l->max_iters = max_iters;
-    }
     return APM_OK;
 }
 extern "C" int apm_set_approximation(apm_ctx* c, int kind, double ep_tol, int ep_max_iters, double ep_damping) {
@@ -597,24 +493,19 @@ extern "C" int apm_profile_read(apm_ctx* c, int max_entries, char* names, double
 }
 extern "C" int apm_work_count(apm_ctx* c, int64_t* out, int reset) {
     if (!c || !out) return APM_ERR_INVALID;
-    out[0] = c->chol_units;
-    out[1] = c->syrk_units;
-    if (reset) c->chol_units = c->syrk_units = 0;
-    for (apm_ctx* l : c->lanes) {
-        out[0] += l->chol_units;
-        out[1] += l->syrk_units;
-        if (reset) l->chol_units = l->syrk_units = 0;
-    }
+    unsigned long long w[2] = {0, 0};
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaMemcpy(w, c->dWork, sizeof(w), cudaMemcpyDeviceToHost));
+    out[0] = (int64_t)w[0];
+    out[1] = (int64_t)w[1];
+    if (reset) CU_TRY(cudaMemset(c->dWork, 0, sizeof(w)));
     return APM_OK;
 }
 extern "C" int64_t apm_launch_count(apm_ctx* c, int reset) {
     if (!c) return 0;
     int64_t v = c->launches;
     if (reset) c->launches = 0;
-    for (apm_ctx* l : c->lanes) {
-        v += l->launches;
-        if (reset) l->launches = 0;
-    }
     return v;
 }
 
@@ -675,104 +566,55 @@ static int build_K(apm_ctx* c, int B, int kind, double eps) {
     return check_launch(c, "k_build_K");
 }
 
+// Batched Cholesky dst = chol(diag(scale) src diag(scale) (+ I)) for the chains with status == 0 inside `active` (null: all):
+// one persistent launch of the warp-specialised TMA / mbarrier dataflow kernel (chol_flow.cuh) preceded by its queue
+// initialisation.  Launches on the aux stream use the second set of queue state (they overlap the main stream's).
+// work_slot >= 0: the number of chains actually factorised is added to dWork[work_slot] as well (M' factorisations).
 static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, const int* src_idx, double* dst,
                     long long dst_bs, const int* dst_idx, const double* scale, int add_identity, double* logdet_parts,
-                    const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr, int units = -1) {
-    c->chol_units += units < 0 ? B : units;
-    if (!c->chol_old) {
-        // one persistent launch: warp-specialised TMA / mbarrier dataflow kernel (chol_flow.cuh)
-        const apm_ctx* r = c->root && !c->cached_only ? c->root : c;
-        cudaStream_t st = c->launch_stream ? c->launch_stream : c->stream;
-        const int set = (st == c->aux_stream) ? 1 : 0;
-        const CUtensorMap* tm = nullptr;
-        int m0 = 0;
-        if (dst_idx) {
-            tm = (dst == c->dSlotLK) ? &c->tmSlotLK : (dst == c->dSlotLC ? &c->tmSlotLC : nullptr);
-        } else if (dst >= r->dLB && dst < r->dLB + (size_t)r->maxB * r->mat) {
-            tm = &c->tmLB;
-            m0 = (int)((dst - r->dLB) / (long long)r->mat);
-        }
-        // source: K (Newton / chol K), the LB buffer (M' in place) or a slot's L_C buffer (explicit covariance in place)
-        const CUtensorMap* tms = nullptr;
-        int ms0 = 0;
-        if (src_idx) {
-            tms = (src == c->dSlotLC) ? &c->tmSlotLC : (src == c->dSlotLK ? &c->tmSlotLK : nullptr);
-        } else if (src >= r->dK && src < r->dK + (size_t)r->maxB * r->mat) {
-            tms = &c->tmK;
-            ms0 = (int)((src - r->dK) / (long long)r->mat);
-        } else if (src >= r->dLB && src < r->dLB + (size_t)r->maxB * r->mat) {
-            tms = &c->tmLB;
-            ms0 = (int)((src - r->dLB) / (long long)r->mat);
-        }
-        if (!tm || !tms) {
-            set_err("run_chol: source / destination buffer has no tensor map");
-            return APM_ERR_INVALID;
-        }
-        CholFlowParams q;
-        q.src = src; q.src_bs = src_bs; q.lds = c->np; q.src_idx = src_idx;
-        q.dst = dst; q.dst_bs = dst_bs; q.ldd = c->np; q.dst_idx = dst_idx; q.dst_m0 = m0; q.src_m0 = ms0; q.zero = 0; q.np = c->np;
-        q.scale = scale; q.scale_bs = c->np; q.add_identity = add_identity; q.nb = c->nb;
-        q.logdet_parts = logdet_parts; q.logdet_stride = c->nb; q.logdet_idx = logdet_idx;
-        q.inv_out = inv_out; q.inv_bs = (long long)c->nb * TB * TB;
-        q.status = c->dStatus; q.fail_code = fail_code; q.active = active; q.nchains = B;
-        q.counter = c->dFlowCounter + 2 * set; q.progress = c->dFlow2Progress[set]; q.list = c->dFlow2Skip[set];
-        q.diagpack = c->dDiagPack[set];
-        q.spin_ns = 64;
-        const int total_tasks = B * c->nb * (c->nb + 1) / 2;
-        prof_begin(c, KID_MISC);
-        k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb);
-        APM_TRY(check_launch(c, "k_chol_flow_init"));
-        int grid = c->flow2_grid < total_tasks ? c->flow2_grid : total_tasks;
-        if (c->flow2_ctas_per_chain > 0 && grid > c->flow2_ctas_per_chain * B) grid = c->flow2_ctas_per_chain * B;
-        prof_begin(c, KID_CHOL);
-        k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, q);
-        return check_launch(c, "k_chol_flow");
-    }
-    CholParams p;
-    p.src = src; p.src_bs = src_bs; p.lds = c->np; p.src_idx = src_idx;
-    p.dst = dst; p.dst_bs = dst_bs; p.ldd = c->np; p.dst_idx = dst_idx;
-    p.scale = scale; p.scale_bs = c->np;
-    p.add_identity = add_identity;
-    p.nb = c->nb;
-    p.logdet_parts = logdet_parts; p.logdet_stride = c->nb; p.logdet_idx = logdet_idx;
-    p.inv_out = inv_out; p.inv_bs = (long long)c->nb * TB * TB;
-    p.status = c->dStatus; p.fail_code = fail_code;
-    p.active = active;
-    p.nchains = B;
-    p.sm_sem = c->sem_limit > 0 ? c->dSmSem : nullptr; p.sem_limit = c->sem_limit;
+                    const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr) {
     cudaStream_t st = c->launch_stream ? c->launch_stream : c->stream;
-    if (c->flow_grid > 0 && st == c->stream) {
-        // single cooperative launch (all CTAs co-resident: tasks wait on each other through progress counters)
-        CholFlow f;
-        f.counter = c->dFlowCounter; f.progress = c->dFlowProgress; f.skip = c->dFlowSkip;
-        f.group = c->flow_group < B ? c->flow_group : B;
-        const int ngroups = (B + f.group - 1) / f.group;
-        f.total_tasks = ngroups * f.group * (1 + c->nb * (c->nb - 1) / 2);
-        f.flags = getenv("APM_FLOW_FLAGS") ? atoi(getenv("APM_FLOW_FLAGS")) : 0;
-        f.spin_ns = getenv("APM_SPIN_NS") ? atoi(getenv("APM_SPIN_NS")) : 100;
-        CU_TRY(cudaMemsetAsync(c->dFlowCounter, 0, sizeof(int), c->stream));
-        CU_TRY(cudaMemsetAsync(c->dFlowProgress, 0, sizeof(int) * (size_t)B * c->nb, c->stream));
-        prof_begin(c, KID_MISC);
-        k_chol_skip_snapshot<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dStatus, active, c->dFlowSkip, B);
-        APM_TRY(check_launch(c, "k_chol_skip_snapshot"));
-        const int grid = c->flow_grid < f.total_tasks ? c->flow_grid : f.total_tasks;
-        void* args[] = {(void*)&p, (void*)&f};
-        prof_begin(c, KID_CHOL);
-        cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_chol_dataflow, dim3(grid), dim3(TILE_THREADS), args,
-                                                    (size_t)TILE_SMEM_BYTES, c->stream);
-        if (e != cudaSuccess) {
-            set_err(std::string("cooperative launch k_chol_dataflow: ") + cudaGetErrorString(e));
-            return APM_ERR_CUDA;
-        }
-        return check_launch(c, "k_chol_dataflow");
+    const int set = (st == c->aux_stream) ? 1 : 0;
+    const CUtensorMap *tm = nullptr, *tms = nullptr;
+    int m0 = 0, ms0 = 0;
+    if (dst_idx) {
+        tm = (dst == c->dSlotLK) ? &c->tmSlotLK : (dst == c->dSlotLC ? &c->tmSlotLC : nullptr);
+    } else if (dst >= c->dLB && dst < c->dLB + (size_t)c->maxB * c->mat) {
+        tm = &c->tmLB;
+        m0 = (int)((dst - c->dLB) / (long long)c->mat);
     }
-    for (int k = -1; k <= c->nb - 2; k++) {
-        const int grid = (k < 0) ? B : B * (c->nb - k - 1);
-        prof_begin(c, KID_CHOL);
-        k_chol_step<<<grid, TILE_THREADS, TILE_SMEM_BYTES, st>>>(p, k);
-        APM_TRY(check_launch(c, "k_chol_step"));
+    // source: K (Newton / chol K), the LB buffer (M' in place) or a slot's L_C buffer (explicit covariance in place)
+    if (src_idx) {
+        tms = (src == c->dSlotLC) ? &c->tmSlotLC : (src == c->dSlotLK ? &c->tmSlotLK : nullptr);
+    } else if (src >= c->dK && src < c->dK + (size_t)c->maxB * c->mat) {
+        tms = &c->tmK;
+        ms0 = (int)((src - c->dK) / (long long)c->mat);
+    } else if (src >= c->dLB && src < c->dLB + (size_t)c->maxB * c->mat) {
+        tms = &c->tmLB;
+        ms0 = (int)((src - c->dLB) / (long long)c->mat);
     }
-    return APM_OK;
+    if (!tm || !tms) {
+        set_err("run_chol: source / destination buffer has no tensor map");
+        return APM_ERR_INVALID;
+    }
+    CholFlowParams q;
+    q.src = src; q.src_bs = src_bs; q.lds = c->np; q.src_idx = src_idx;
+    q.dst = dst; q.dst_bs = dst_bs; q.ldd = c->np; q.dst_idx = dst_idx; q.dst_m0 = m0; q.src_m0 = ms0; q.zero = 0; q.np = c->np;
+    q.scale = scale; q.scale_bs = c->np; q.add_identity = add_identity; q.nb = c->nb;
+    q.logdet_parts = logdet_parts; q.logdet_stride = c->nb; q.logdet_idx = logdet_idx;
+    q.inv_out = inv_out; q.inv_bs = (long long)c->nb * TB * TB;
+    q.status = c->dStatus; q.fail_code = fail_code; q.active = active; q.nchains = B;
+    q.counter = c->dFlowCounter + 2 * set; q.progress = c->dFlow2Progress[set]; q.list = c->dFlow2Skip[set];
+    q.diagpack = c->dDiagPack[set];
+    q.spin_ns = 64;
+    const int total_tasks = B * c->nb * (c->nb + 1) / 2;
+    prof_begin(c, KID_MISC);
+    k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb, c->dWork);
+    APM_TRY(check_launch(c, "k_chol_flow_init"));
+    const int grid = c->flow2_grid < total_tasks ? c->flow2_grid : total_tasks;
+    prof_begin(c, KID_CHOL);
+    k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, q);
+    return check_launch(c, "k_chol_flow");
 }
 
 // out = rs * (K x) for all active chains, reading only the lower tiles of the symmetric K (lpa.py:94-95 mat-vecs)
@@ -798,35 +640,21 @@ static NewtonVecs make_nv(apm_ctx* c) {
     return nv;
 }
 
-// M' = I + Y'Y'^T (lower tiles, reversed coordinates) -> dLB, for chains in `mask` (null: all): Y' from chol(K) in the
-// slots and W^1/2 (see tile_engine.cuh "Factored posterior covariance")
-static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mask, int units = -1) {
-    c->syrk_units += units < 0 ? B : units;
-    if (c->syrk_direct) {
-        // straight from L_K (k-major operand stages): no transposed, scaled copy of L_K
-        SyrkLkParams s;
-        s.LK = c->dSlotLK; s.lk_bs = (long long)c->mat; s.ldk = c->np; s.lk_idx = dSlots;
-        s.W = c->dVec[V_W]; s.w_bs = c->np;
-        s.M = c->dLB; s.m_bs = (long long)c->mat; s.ldm = c->np;
-        s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
-        s.status = c->dStatus; s.mask = mask;
-        prof_begin(c, KID_SYRK);
-        k_syrk_lk<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
-        return check_launch(c, "k_syrk_lk");
-    }
-    dim3 yg(c->np / 32, c->np / 32, B), yb(32, 8);
-    prof_begin(c, KID_TRANSPOSE);
-    k_make_Y<<<yg, yb, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->dVec[V_WS], c->np, c->dZ,
-                                       (long long)c->mat, c->np, c->dStatus, mask);
-    APM_TRY(check_launch(c, "k_make_Y"));
-    SyrkRevParams s;
-    s.Y = c->dZ; s.y_bs = (long long)c->mat; s.ldy = c->np;
+// M' = P (I + L_K^T W L_K) P (lower tiles, reversed coordinates) -> dLB, for chains in `mask` (null: all), straight from
+// chol(K) in the slots (k-major operand stages: see tile_engine.cuh "Factored posterior covariance")
+static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mask) {
+    prof_begin(c, KID_MISC);
+    k_count_mask<<<1, 256, 0, c->stream>>>(mask, c->dStatus, B, c->dWork + 1);
+    APM_TRY(check_launch(c, "k_count_mask"));
+    SyrkLkParams s;
+    s.LK = c->dSlotLK; s.lk_bs = (long long)c->mat; s.ldk = c->np; s.lk_idx = dSlots;
+    s.W = c->dVec[V_W]; s.w_bs = c->np;
     s.M = c->dLB; s.m_bs = (long long)c->mat; s.ldm = c->np;
     s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
     s.status = c->dStatus; s.mask = mask;
     prof_begin(c, KID_SYRK);
-    k_syrk_rev<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
-    return check_launch(c, "k_syrk_rev");
+    k_syrk_lk<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
+    return check_launch(c, "k_syrk_lk");
 }
 
 // Newton mode search (lpa.py:81-102) for chains 0..B-1 whose K sits in c->dK.  On exit f (V_F) is the
@@ -843,36 +671,36 @@ static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mas
 // lk_pending: chol(K) is still running on the aux stream (wait for ev_lk_done before the first M-space step).
 // restores the context's launch stream / Cholesky mode when a scope that redirected them ends (also on error returns)
 struct StreamSwap {
-    apm_ctx* c; cudaStream_t stream; int flow_grid;
-    explicit StreamSwap(apm_ctx* c_) : c(c_), stream(c_->stream), flow_grid(c_->flow_grid) {}
-    void to_aux() { c->stream = c->aux_stream; c->flow_grid = 0; }   // per-step Cholesky launches: no spinning CTAs beside the other form
-    void back() { c->stream = stream; c->flow_grid = flow_grid; }
+    apm_ctx* c; cudaStream_t stream;
+    explicit StreamSwap(apm_ctx* c_) : c(c_), stream(c_->stream) {}
+    void to_aux() { c->stream = c->aux_stream; }
+    void back() { c->stream = stream; }
     ~StreamSwap() { back(); }
 };
 
+// The loop is driven from the device: every kernel of a round works under the per-chain masks that k_newton_finish
+// maintains (dActive; hybrid: dMaskB / dMaskM), a round whose mask is empty costs a few empty launches, and the host only
+// reads the number of still-active chains after `newton_r0` rounds have been queued (then after every further round):
+// one host round trip per estimate on typical data (4-5 iterations) instead of one per iteration.  In a hybrid round the
+// two forms touch disjoint chains: the B-space form runs on the main stream, the M-space form beside it on the aux stream.
 static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pending = false) {
     NewtonVecs nv = make_nv(c);
     const bool hybrid = dSlots != nullptr && c->factored_cov && c->hybrid_newton;
     CU_TRY(cudaMemsetAsync(nv.f, 0, sizeof(double) * (size_t)B * c->np, c->stream));
     CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
     prof_begin(c, KID_MISC);
-    k_fill_int<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dActive, 1, B);
-    APM_TRY(check_launch(c, "k_fill_int"));
-    prof_begin(c, KID_MISC);
-    k_fill_int<<<1, 32, 0, c->stream>>>(c->dNActive, B, 1);
-    APM_TRY(check_launch(c, "k_fill_int"));
-    if (hybrid) {
-        nv.done_m = c->dDoneM;
-        CU_TRY(cudaMemsetAsync(c->dDoneM, 0, sizeof(int) * B, c->stream));
-    }
+    k_newton_init<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dActive, hybrid ? c->dMaskB : nullptr, hybrid ? c->dMaskM : nullptr,
+                                                          hybrid ? c->dDoneM : nullptr, c->dNActive, B);
+    APM_TRY(check_launch(c, "k_newton_init"));
+    if (hybrid) nv.done_m = c->dDoneM;
     const size_t trsv_smem = (size_t)(c->np + 64 + 8 * 64) * sizeof(double);
     if (trsv_smem > 160 * 1024) {
         set_err("run_newton: n too large for the single-CTA triangular solve");
         return APM_ERR_INVALID;
     }
     // The form is chosen PER CHAIN (from its own diff only), so a chain's arithmetic never depends on its batch-mates:
-    // results are bit-identical whatever the batch composition, lane split or GPU count.  A round whose active chains
-    // disagree runs both forms, each under its mask (dMaskB / dMaskM, written by k_newton_finish).
+    // results are bit-identical whatever the batch composition or GPU count.  A round whose active chains disagree runs
+    // both forms, each under its mask (dMaskB / dMaskM, written by k_newton_finish).
     c->newton_b_finishers = false;
     c->newton_b_finisher_count = 0;
     const int* maskB = c->dActive;
@@ -880,38 +708,33 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
     if (hybrid) {
         nv.mask_b = c->dMaskB; nv.mask_m = c->dMaskM;
         maskB = c->dMaskB; maskM = c->dMaskM;
-        prof_begin(c, KID_MISC);
-        k_fill_int<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dMaskB, 1, B);
-        APM_TRY(check_launch(c, "k_fill_int"));
-        CU_TRY(cudaMemsetAsync(c->dMaskM, 0, sizeof(int) * B, c->stream));
     }
     // mat-vec-free B-space step (k_newton_prep / k_trsv2 / k_fnew_from_s): no K-sized read besides the Cholesky itself
     const bool matfree = c->fnew_thr > 0;
     NewtonVecs nvB = nv, nvM = nv;     // k_trsv2 skips the chains outside nv.active
     nvB.active = const_cast<int*>(maskB);
     nvM.active = const_cast<int*>(maskM);
-    int n_act = B, nB = B, nM = 0;
+    const bool two_streams = c->overlap_chol_k && c->aux_stream != nullptr;
+    int n_act = B;
     for (int it = 0; it < c->max_iters; it++) {
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_prep<<<B, 256, 0, c->stream>>>(nv, matfree ? 1 : 0);
         APM_TRY(check_launch(c, "k_newton_prep"));
-        // mixed round: the two forms touch disjoint chains, so the minority form runs beside the other on aux_stream
-        // (helpers launch on c->stream: it is swapped for the duration of that form)
+        // no chain can be in M-space in the first round (the prediction needs a diff)
+        const bool m_form = hybrid && it > 0;
         StreamSwap swap(c);
         cudaStream_t main_stream = c->stream;
-        const bool mixed = nB > 0 && nM > 0 && c->overlap_chol_k && c->aux_stream != nullptr;
-        const bool b_on_aux = mixed && nB <= nM, m_on_aux = mixed && !b_on_aux;
-        if (mixed) {
+        const bool fork = m_form && two_streams;
+        if (fork) {
             CU_TRY(cudaEventRecord(c->ev_mix_fork, main_stream));
             CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_mix_fork, 0));
         }
-        if (nB > 0) {
-            if (b_on_aux) swap.to_aux();
+        {
             // t = Ws * (K b)                                           (lpa.py:94  W_sqrt_K.dot(b)); mat-vec-free: t = b / Ws
             if (!matfree) APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t, maskB));
             // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
             APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB, nB));
+                             nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB));
             // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
             prof_begin(c, KID_TRSV);
             k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
@@ -925,10 +748,9 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
             } else {
                 APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew, maskB));
             }
-            swap.back();
         }
-        if (nM > 0) {
-            if (m_on_aux) swap.to_aux();
+        if (m_form) {
+            if (fork) swap.to_aux();
             if (lk_pending) {
                 CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
                 lk_pending = false;
@@ -939,9 +761,9 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
                                                                 nv.t, c->np, nullptr, c->dStatus, maskM, 1);
             APM_TRY(check_launch(c, "k_lt_matvec"));
             // L' = chol(M'), M' = P (I + L_K^T W L_K) P
-            APM_TRY(run_build_mprime(c, B, dSlots, maskM, nM));
+            APM_TRY(run_build_mprime(c, B, dSlots, maskM));
             APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, nM));
+                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB));
             // s' = M'^-1 t'
             prof_begin(c, KID_TRSV);
             k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
@@ -954,25 +776,19 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
                                                                        maskM);
             APM_TRY(check_launch(c, "k_l_matvec_rev"));
             swap.back();
+            if (fork) {
+                CU_TRY(cudaEventRecord(c->ev_mix_join, c->aux_stream));
+                CU_TRY(cudaStreamWaitEvent(main_stream, c->ev_mix_join, 0));
+            }
         }
-        if (mixed) {
-            CU_TRY(cudaEventRecord(c->ev_mix_join, c->aux_stream));
-            CU_TRY(cudaStreamWaitEvent(main_stream, c->ev_mix_join, 0));
-        }
-        if (hybrid) CU_TRY(cudaMemsetAsync(c->dNActive + 1, 0, 2 * sizeof(int), c->stream));
         prof_begin(c, KID_NEWTON_VEC);
         k_newton_finish<<<B, 256, 0, c->stream>>>(nv);
         APM_TRY(check_launch(c, "k_newton_finish"));
+        if (it + 1 < c->newton_r0 && it + 1 < c->max_iters) continue;     // keep queueing: no host round trip yet
         CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
         n_act = c->hNActive[0];
-        if (hybrid) {
-            nM = c->hNActive[1];                                    // still active and predicted to finish next
-            c->newton_b_finisher_count += c->hNActive[2];           // finished in a B-space round: need the covariance phase
-        } else {
-            nM = 0;
-        }
-        nB = n_act - nM;
+        c->newton_b_finisher_count = hybrid ? c->hNActive[2] : 0;   // (cumulative) finished in a B-space round: need the covariance phase
         if (n_act <= 0) break;
     }
     c->newton_b_finishers = !hybrid || c->newton_b_finisher_count > 0;
@@ -1083,11 +899,10 @@ static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots, const i
         todo = c->dMaskB;
     }
     if (need_cov) {
-        const int units = todo ? c->newton_b_finisher_count : B;
-        APM_TRY(run_build_mprime(c, B, dSlots, todo, units));
+        APM_TRY(run_build_mprime(c, B, dSlots, todo));
         // L' = chol(M') in place (M' has eigenvalues >= 1: cannot fail for finite input)
         APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                         nullptr, APM_CHAIN_CHOL_C, todo, nullptr, units));
+                         nullptr, APM_CHAIN_CHOL_C, todo, nullptr));
     }
     // V = anti-transpose of L' into the slot's L_C buffer; mu~ = L_K^T a.  The importance-sampling tail works with
     // (L_K, V, mu, mu~) directly, so the n^3/3 triangular solve for the explicit L_C = L_K V^-1 is only run if somebody
@@ -1120,14 +935,14 @@ static int slot_make_explicit(apm_ctx* c, int slot) {
     k_antitranspose<<<ag, ab, 0, c->stream>>>(c->dSlotLC, (long long)c->mat, c->dSlotsB, c->dLB, (long long)c->mat, nullptr, c->np,
                                              nullptr);
     APM_TRY(check_launch(c, "k_antitranspose"));
-    CU_TRY(cudaMemsetAsync(c->dFlowSkip, 0, sizeof(int), c->stream));   // a zero status word for the single pseudo-chain
+    CU_TRY(cudaMemsetAsync(c->dFlow2Skip[0], 0, sizeof(int), c->stream));   // a zero status word for the single pseudo-chain
     TrsmRevParams t;
     t.LK = c->dSlotLK; t.lk_bs = (long long)c->mat; t.ldk = c->np; t.lk_idx = c->dSlotsB;
     t.Lp = c->dLB; t.lp_bs = (long long)c->mat; t.ldp = c->np;
     t.X = c->dZ; t.x_bs = (long long)c->mat; t.ldx = c->np;
     t.LC = c->dSlotLC; t.lc_bs = (long long)c->mat; t.ldc = c->np; t.lc_idx = c->dSlotsB;
     t.nb = c->nb;
-    t.status = c->dFlowSkip;
+    t.status = c->dFlow2Skip[0];
     prof_begin(c, KID_TRSM);
     k_trsm_rev<<<c->nb, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(t);
     APM_TRY(check_launch(c, "k_trsm_rev"));
@@ -1445,92 +1260,11 @@ static int full_front(apm_ctx* c, const double* theta, int B, const int* slots, 
     return rc;
 }
 
-// point a lane view at chains [off, off + cnt) of the root's buffers (N: importance samples of this call)
-static void lane_bind(apm_ctx* v, int lane, int off, int cnt, int N) {
-    const apm_ctx* r = v->root;
-    const size_t o = (size_t)off, np = r->np, nb = r->nb;
-    const size_t Npad = (size_t)((N + TB - 1) / TB * TB);
-    v->maxB = cnt;
-    v->dK = r->dK + o * r->mat; v->dLB = r->dLB + o * r->mat; v->dZ = r->dZ + o * r->mat;
-    v->dLdB = r->dLdB + o * nb;
-    v->dInvB = r->dInvB + o * nb * TB * TB;
-    v->dSymvDirect = r->dSymvDirect + o * np;
-    v->dSymvPart = r->dSymvPart + o * nb * nb * 64;
-    for (int k = 0; k < V_COUNT; k++) v->dVec[k] = r->dVec[k] + o * np;
-    v->dUT = r->dUT + o * Npad * np; v->dF = r->dF + o * Npad * np; v->dZf = r->dZf + o * Npad * np;
-    v->dUstage = r->dUstage + o * (size_t)r->n * N;
-    v->dKp = r->dKp + o * (2 * r->D + 1);
-    v->dOut = r->dOut + o * 2;
-    v->dLogw = r->dLogw + o * N;
-    v->dEpDelta = r->dEpDelta + o;
-    v->dMaskM = r->dMaskM + o; v->dMaskB = r->dMaskB + o; v->dDoneM = r->dDoneM + o;
-    v->approx = r->approx; v->ep_tol = r->ep_tol; v->ep_damping = r->ep_damping; v->ep_max_iters = r->ep_max_iters;
-    v->dStatus = r->dStatus + o; v->dActive = r->dActive + o; v->dIters = r->dIters + o;
-    v->dSlotsA = r->dSlotsA + o; v->dSlotsB = r->dSlotsB + o;
-    v->dFlowSkip = r->dFlowSkip + o; v->dFlowProgress = r->dFlowProgress + o * nb;
-    for (int q = 0; q < 2; q++) {
-        v->dFlow2Progress[q] = r->dFlow2Progress[q] + o * nb;
-        v->dFlow2Skip[q] = r->dFlow2Skip[q] + o;
-        v->dDiagPack[q] = r->dDiagPack[q] + o * nb * DP_DOUBLES;
-    }
-    v->dNActive = r->dNActive + 4 * (lane + 1); v->dFlowCounter = r->dFlowCounter + 4 * (lane + 1);
-    v->hKp = r->hKp + o * (2 * r->D + 1); v->hOut = r->hOut + o * 2; v->hInts = r->hInts + o * 4;
-    v->hNActive = r->hNActive + 4 * (lane + 1);
-    v->overlap_chol_k = r->overlap_chol_k; v->factored_cov = r->factored_cov;
-    v->tol = r->tol; v->max_iters = r->max_iters;
-}
-
-static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
-                              const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status);
-
 extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
                                  const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status) {
     APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
     if (!theta || !u || !slots || !logml_out) return APM_ERR_INVALID;
-    // small batches stay on the single-launch dataflow path (a lane needs enough chains to fill its kernels)
-    int G = (c->prof || B < c->lane_min_batch) ? 1 : (int)c->lanes.size();
-    if (G > B / c->lane_min_chains) G = B / c->lane_min_chains;
-    if (G < 2) return estimate_full_impl(c, theta, u, u_on_device, N, B, slots, logml_out, cubic_ops_out, chain_status);
-    if (N <= 0 || N > c->maxN) {
-        set_err("N (importance samples) out of range for this context");
-        return APM_ERR_INVALID;
-    }
-    cancel_prefetch(c);
-    // lanes start after everything already queued on the caller's stream (device-resident u may still be in flight)
-    CU_TRY(cudaEventRecord(c->ev_fork, c->stream));
-    const int per = (B + G - 1) / G;
-    std::vector<std::thread> workers;
-    for (int l = 0; l < G; l++) {
-        const int off = l * per, cnt = (off + per <= B) ? per : B - off;
-        if (cnt <= 0) break;
-        apm_ctx* v = c->lanes[l];
-        lane_bind(v, l, off, cnt, N);
-        v->lane_rc = APM_OK;
-        workers.emplace_back([=]() {
-            cudaSetDevice(v->device);
-            int rc = (cudaStreamWaitEvent(v->stream, c->ev_fork, 0) == cudaSuccess) ? APM_OK : APM_ERR_CUDA;
-            if (rc == APM_OK)
-                rc = estimate_full_impl(v, theta + (size_t)off * c->P, u + (size_t)off * c->n * N, u_on_device, N, cnt, slots + off,
-                                        logml_out + off, cubic_ops_out ? cubic_ops_out + off : nullptr,
-                                        chain_status ? chain_status + off : nullptr);
-            v->lane_rc = rc;
-            if (rc != APM_OK) v->lane_err = g_err;   // g_err is thread-local
-        });
-    }
-    for (auto& w : workers) w.join();
-    for (int l = 0; l < (int)workers.size(); l++) {
-        if (c->lanes[l]->lane_rc != APM_OK) {
-            set_err("lane " + std::to_string(l) + ": " + c->lanes[l]->lane_err);
-            return c->lanes[l]->lane_rc;
-        }
-    }
-    return APM_OK;
-}
-
-static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
-                              const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status) {
-    APM_TRY(check_B(c, B));
     cancel_prefetch(c);
     APM_TRY(prefetch_u(c, u, u_on_device, N, B));
     const bool overlap = c->overlap_chol_k;
@@ -1778,8 +1512,9 @@ extern "C" int apm_slot_copy(apm_ctx* c, const int* src, const int* dst, int B) 
 }
 
 // dev/tuning entry (not part of the reference-facing surface): time `reps` batched Cholesky factorisations
-// of the K matrices currently in the context (after apm_kernel_build) into slots 0..B-1.  mode 0: default
-// path, 1: force per-step launches.
+// of the K matrices currently in the context (after apm_kernel_build).  mode >> 4 selects what is factorised:
+// 0: chol(K) -> slots 0..B-1, 1: chol(I + Ws K Ws) -> LB with inverse diagonal blocks (a Newton round), 2: as 1 with 1/8 of
+// the chains active (a straggler round).
 extern "C" int apm_dev_chol_bench(apm_ctx* c, int B, int reps, int mode, double* ms_out) {
     APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
@@ -1787,14 +1522,11 @@ extern "C" int apm_dev_chol_bench(apm_ctx* c, int B, int reps, int mode, double*
     APM_TRY(reset_status(c, B));
     for (int b = 0; b < B; b++) c->hInts[b] = b;
     CU_TRY(cudaMemcpyAsync(c->dSlotsA, c->hInts, sizeof(int) * B, cudaMemcpyHostToDevice, c->stream));
-    const int saved = c->flow_grid;
     cudaEvent_t e0, e1;
     CU_TRY(cudaEventCreate(&e0));
     CU_TRY(cudaEventCreate(&e1));
     int rc = APM_OK;
-    const int variant = mode >> 4;   // 0: chol(K) -> slot, 1: chol(I + Ws K Ws) -> LB (Newton step), 2: as 1 with 1/8 of the chains active
-    mode &= 15;
-    if (mode == 1) c->flow_grid = 0;
+    const int variant = mode >> 4;
     if (variant >= 1) {
         k_fill_double<<<(unsigned)(((size_t)B * c->np + 255) / 256), 256, 0, c->stream>>>(c->dVec[V_WS], 0.5, (long long)B * c->np);
         k_fill_int<<<(B + 255) / 256, 256, 0, c->stream>>>(c->dActive, 1, B);
@@ -1809,7 +1541,7 @@ extern "C" int apm_dev_chol_bench(apm_ctx* c, int B, int reps, int mode, double*
         if (r == 1) cudaEventRecord(e0, c->stream);
         if (variant == 0)
             rc = run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dSlotLK, (long long)c->mat, c->dSlotsA, nullptr, 0,
-                          c->dSlotLdK, c->dSlotsA, APM_CHAIN_CHOL_K, nullptr, c->dInvB);
+                          c->dSlotLdK, c->dSlotsA, APM_CHAIN_CHOL_K, nullptr, nullptr);
         else
             rc = run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, c->dVec[V_WS], 1,
                           c->dLdB, nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB);
@@ -1820,7 +1552,6 @@ extern "C" int apm_dev_chol_bench(apm_ctx* c, int B, int reps, int mode, double*
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    c->flow_grid = saved;
     *ms_out = ms / reps;
     return rc;
 }
@@ -1886,19 +1617,6 @@ extern "C" int apm_dev_dmma_sweep(int device, int warps_per_sm, int nacc, double
     return cudaGetLastError() == cudaSuccess ? APM_OK : APM_ERR_CUDA;
 }
 
-#ifdef APM_PHASE_TIMING
-extern "C" int apm_dev_phase_read(unsigned long long* cycles, unsigned long long* counts, int reset) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(cycles, g_phase_cycles, sizeof(unsigned long long) * 16);
-    cudaMemcpyFromSymbol(counts, g_phase_counts, sizeof(unsigned long long) * 16);
-    if (reset) {
-        unsigned long long z[16] = {0};
-        cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
-        cudaMemcpyToSymbol(g_phase_counts, z, sizeof(z));
-    }
-    return 0;
-}
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // fp64 peak probes

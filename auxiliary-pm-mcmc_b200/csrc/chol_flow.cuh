@@ -140,7 +140,8 @@ struct CholFlowParams {
 // Zero the queue head and the progress counters, and compact the chains to factorise (status == 0 and inside the optional
 // Newton mask) into an ordered list: a launch for a few straggler chains enumerates only their tasks.  One launch instead
 // of two memsets + a snapshot kernel; block 0 / warp 0 does the (ballot) compaction.
-__global__ void k_chol_flow_init(int* counter, int* progress, int* list, const int* status, const int* active, int nchains, int nb) {
+__global__ void k_chol_flow_init(int* counter, int* progress, int* list, const int* status, const int* active, int nchains, int nb,
+                                 unsigned long long* work) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nchains * nb) progress[e] = 0;
     if (blockIdx.x == 0 && threadIdx.x < 32) {
@@ -155,6 +156,7 @@ __global__ void k_chol_flow_init(int* counter, int* progress, int* list, const i
         if (threadIdx.x == 0) {
             counter[0] = 0;
             counter[1] = count;
+            if (work && count) atomicAdd(work, (unsigned long long)count);   // chain-Choleskys executed (work accounting)
         }
     }
 }

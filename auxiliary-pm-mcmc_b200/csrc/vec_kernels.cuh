@@ -199,33 +199,6 @@ __global__ void k_transpose_u(const double* __restrict__ u, long long u_bs, int 
     }
 }
 
-// Y'[i'][k] = L_K[k][np-1-i'] * Ws[k]  (zero above L_K's diagonal): the transposed, row-reversed, W^1/2-scaled
-// Cholesky factor whose Gram matrix is M' - I (see k_syrk_rev).  32x32 tiles through shared memory.
-__global__ void k_make_Y(const double* __restrict__ LK, long long lk_bs, const int* lk_idx, int ld,
-                         const double* __restrict__ Ws, long long ws_bs, double* __restrict__ Y, long long y_bs, int np,
-                         const int* status, const int* mask) {
-    __shared__ double tile[32][33];
-    const int b = blockIdx.z;
-    if (status[b] != 0 || (mask && !mask[b])) return;
-    const int k0 = blockIdx.y * 32, i0 = blockIdx.x * 32;      // L_K rows k0.., columns i0..
-    // k_syrk_rev starts the k-range of row block i' at the block that holds the triangle's edge: 64-blocks strictly above
-    // L_K's block diagonal are never read, so their zeros are not written either
-    if ((i0 >> 6) > (k0 >> 6)) return;
-    const double* L = LK + chain_index(lk_idx, b) * lk_bs;
-    double* Yb = Y + (long long)b * y_bs;
-    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-    const bool above = (i0 > k0 + 31);             // tile entirely above the diagonal: zeros
-    for (int r = ty; r < 32; r += 8) {
-        const int k = k0 + r, i = i0 + tx;
-        tile[r][tx] = (!above && i <= k) ? L[(size_t)k * ld + i] * Ws[(long long)b * ws_bs + k] : 0.0;
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int i = i0 + r;                      // original column of L_K -> row np-1-i of Y'
-        Yb[(size_t)(np - 1 - i) * np + k0 + tx] = tile[tx][r];
-    }
-}
-
 // per-slot partial log-dets of L_C = L_K U^-T:  sum log diag L_C = sum log diag L_K - sum log diag L'
 __global__ void k_logdet_combine(const double* ldK, const double* ldM, double* ldC, const int* slot_idx, int nb, const int* status) {
     const int b = blockIdx.x, k = threadIdx.x;
@@ -536,6 +509,28 @@ __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, lon
         nv.s[o + i] = s;
         nv.a[o + i] = nv.bvec[o + i] - nv.Ws[o + i] * s;
     }
+}
+
+// start of a Newton mode search: every chain active and (hybrid) in the B-space form; n_active = {B, 0, 0}
+__global__ void k_newton_init(int* active, int* mask_b, int* mask_m, int* done_m, int* n_active, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        active[b] = 1;
+        if (mask_b) { mask_b[b] = 1; mask_m[b] = 0; done_m[b] = 0; }
+    }
+    if (b == 0) { n_active[0] = B; n_active[1] = 0; n_active[2] = 0; }
+}
+
+// *out += number of chains with status == 0 inside mask (null: all) -- work accounting of the masked launches
+__global__ void k_count_mask(const int* mask, const int* status, int B, unsigned long long* out) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) c += (status[b] == 0) && (!mask || mask[b]);
+    if (c) atomicAdd(&cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
 }
 
 // diff = mean((fnew - f)^2); f <- fnew; iteration bookkeeping (lpa.py:96-102)

@@ -5,7 +5,7 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
-#include "../auxiliary-pm-mcmc_b200/csrc/tile_engine.cuh"
+#include "r1_chol_engine.cuh"
 #include "../auxiliary-pm-mcmc_b200/csrc/chol_flow.cuh"
 #include "../auxiliary-pm-mcmc_b200/csrc/tmap_host.h"
 
@@ -140,7 +140,7 @@ int main(int argc, char** argv) {
                 if (inplace) CK(cudaMemcpy(dL1, dK, B * mat * 8, cudaMemcpyDeviceToDevice));
                 if (r == 1) CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(dstatus, 0, B * 4));
-                k_chol_flow_init<<<(B * nb + 255) / 256, 256>>>(p.counter, p.progress, p.list, dstatus, p.active, B, nb);
+                k_chol_flow_init<<<(B * nb + 255) / 256, 256>>>(p.counter, p.progress, p.list, dstatus, p.active, B, nb, nullptr);
                 k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, inplace ? tm1 : tmK, p);
                 if (inplace && r >= 1) break;
             }

@@ -211,10 +211,11 @@ def test_cached_equals_full_and_batch_independence():
     eng.close()
 
 
-def test_lanes_match_single_path():
-    """A FULL estimate of >= 128 chains is split over lane views (host threads + streams, per-step Cholesky
-    launches); smaller batches take the single-launch dataflow path.  Same chains -> bit-identical results,
-    iteration counts and caches, for host and device-resident u, including a ragged last lane."""
+def test_large_batch_matches_split_batches():
+    """One dataflow launch per factorisation over 167 chains (tasks of all chains interleaved on the SMs, Newton rounds
+    queued without host round trips) against the same chains in batches of 50: bit-identical results, iteration counts and
+    caches, for host and device-resident u, and with the Newton loop checked by the host after every round
+    (APM_NEWTON_R0=1) instead of after the first five."""
     import torch
     n, D, N, B = 130, 3, 5, 167
     X, y, th = synth.make_dataset(n, D, seed=11)
@@ -223,22 +224,26 @@ def test_lanes_match_single_path():
     u = rs.normal(size=(B, n, N))
     eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N)
     eng.use_torch_stream()
-    laned, ops_l, st_l = eng.estimate_full(thetas, u, np.arange(B))
-    laned_dev, _, _ = eng.estimate_full(thetas, torch.from_numpy(u).cuda(), np.arange(B))
+    big, ops_l, st_l = eng.estimate_full(thetas, u, np.arange(B))
+    big_dev, _, _ = eng.estimate_full(thetas, torch.from_numpy(u).cuda(), np.arange(B))
     single = np.empty(B)
     ops_s = np.empty(B, dtype=np.int32)
-    for lo in range(0, B, 50):                       # < 128 chains per call: no lanes
+    for lo in range(0, B, 50):
         hi = min(B, lo + 50)
         single[lo:hi], ops_s[lo:hi], st = eng.estimate_full(thetas[lo:hi], u[lo:hi], np.arange(B + lo, B + hi))
         assert np.all(st == 0)
     assert np.all(st_l == 0)
-    assert np.array_equal(laned, single) and np.array_equal(laned_dev, single)
+    assert np.array_equal(big, single) and np.array_equal(big_dev, single)
     assert np.array_equal(ops_l, ops_s)
     u2 = rs.normal(size=(B, n, N))
     c1, _ = eng.estimate_cached(np.arange(B), u2)
     c2, _ = eng.estimate_cached(np.arange(B, 2 * B), u2)
     assert np.array_equal(c1, c2)
     eng.close()
+    eng1 = _engine_with_env({'APM_NEWTON_R0': '1'}, X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N)
+    step, ops_1, st_1 = eng1.estimate_full(thetas, u, np.arange(B))
+    assert np.array_equal(step, big) and np.array_equal(ops_1, ops_l) and np.all(st_1 == 0)
+    eng1.close()
 
 
 def _engine_with_env(env, *args, **kw):
@@ -358,10 +363,14 @@ def test_failure_statuses():
     with pytest.raises(_capi.ApmError):
         _capi.Engine(X, np.zeros(40))                       # targets must be +-1
     eng = _capi.Engine(rs.normal(size=(40, 2)), y, kernel='iso', max_chains=2, max_nimp=2)
-    with pytest.raises(_capi.ApmError):
+    with pytest.raises((_capi.ApmError, ValueError)):
         eng.estimate_full(np.zeros((3, 2)), rs.normal(size=(3, 40, 2)), [0, 1, 2])   # B > max_chains
-    with pytest.raises(_capi.ApmError):
+    with pytest.raises((_capi.ApmError, ValueError)):
         eng.estimate_full(np.zeros((1, 2)), rs.normal(size=(1, 40, 4)), [0])         # N > max_nimp
+    with pytest.raises(ValueError):
+        eng.estimate_full(np.zeros((2, 2)), rs.normal(size=(2, 39, 2)), [0, 1])      # u of the wrong shape
+    with pytest.raises(ValueError):
+        eng.estimate_full(np.zeros((2, 2)), rs.normal(size=(2, 40, 2)), [1, 1])      # duplicate slots in one batch
     th_nan = np.array([[np.nan, 0.], [0., 0.]])
     out, ops, st = eng.estimate_full(th_nan, u, [0, 1])
     assert st[0] != 0 and st[1] == 0 and np.isnan(out[0]) and np.isfinite(out[1])
