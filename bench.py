@@ -12,8 +12,12 @@ IS tail) for all chains of the rank, with fresh theta and u every step.  metric 
   value   inputs (u) already resident in HBM; timed with CUDA events, max over ranks
   e2e     the same step through the reference-facing C-ABI call with HOST buffers (pinned u, theta):
           H2D of u and theta and D2H of the results inside the timed region
-  roofline  dominant kernel family (k_chol = k_chol_dataflow / k_chol_step, fp64 DMMA) timed live with CUDA events around every launch
-            of the timed region (apm_profile); peak = fp64 DMMA issue peak measured in this run
+  roofline  dominant kernel family (k_chol = k_chol_flow, the TMA / mbarrier dataflow Cholesky, fp64 DMMA) timed live with CUDA
+            events around every launch of the timed region (apm_profile); peak = fp64 DMMA issue peak measured in this run;
+            every kernel family carries its own bound / achieved / frac
+  configs   the other BASELINE.json configurations (breast E-SS + RD-SS, N_imp sweep, PM-MH, n = 8192), chains sharded over
+            the ranks, keyed under "configs" of the same JSON line; the reference arm carries the CPU counterparts of the
+            iterations/s figures
   cpu_baseline  the oracle port (numpy/scipy/OpenBLAS + the reference's own Cython kernel module when
             oracle/_ref is present) timed on this box's host cores on a bounded sample
 """
@@ -32,7 +36,8 @@ import numpy as np  # noqa: E402
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name='pima-shaped synthetic GP probit, Laplace-IS FULL estimate', n=768, D=8, n_imp=64,
+WORKLOAD = dict(name='pima-shaped synthetic GP probit (n=768, D=8, ARD kernel, eps=1e-8), Laplace importance-sampling estimator, '
+                     'N_imp=64: FULL log-ML estimates with fresh theta and u', n=768, D=8, n_imp=64,
                 chains_per_gpu=256, kernel='ard', epsilon=1e-8)
 METRIC = 'FULL log-ML estimates/sec (GP probit n=768, N_imp=64)'
 UNIT = 'estimates/s'
@@ -109,17 +114,18 @@ def make_inputs(n, D, N, B, seed):
 
 
 # ---------------------------------------------------------------------------------------------- CPU legs
-def _oracle_estimator(X, y):
+def _oracle_estimator(X, y, kernel='ard'):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import apm_oracle as orc
     import ref_loader
     refk = ref_loader.load_ref_kernels()
+    name = 'diagonal_squared_exponential_kernel' if kernel == 'ard' else 'isotropic_squared_exponential_kernel'
     if refk is not None:      # the reference's own compiled Cython builder (oracle/_ref), scalar & GIL-bound
-        kf = lambda K, X_, th: refk.diagonal_squared_exponential_kernel(K, X_, th, WORKLOAD['epsilon'])  # noqa: E731
-        kind = 'port (numpy/scipy restatement; K build by the reference Cython module oracle/_ref)'
+        kf = lambda K, X_, th: getattr(refk, name)(K, X_, th, WORKLOAD['epsilon'])  # noqa: E731
+        kind = 'port (numpy/scipy restatement oracle/apm_oracle.py; K build by the reference Cython module oracle/_ref)'
     else:
-        kf = lambda K, X_, th: orc.diagonal_squared_exponential_kernel(K, X_, th, WORKLOAD['epsilon'])  # noqa: E731
-        kind = 'port (numpy/scipy restatement; K build by oracle/kernels_oracle.c)'
+        kf = lambda K, X_, th: getattr(orc, name)(K, X_, th, WORKLOAD['epsilon'])  # noqa: E731
+        kind = 'port (numpy/scipy restatement oracle/apm_oracle.py; K build by oracle/kernels_oracle.c)'
     return orc.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf, orc.laplace_approximation), kind
 
 
@@ -130,6 +136,7 @@ def _cpu_worker_init():
     """Per-process set-up (outside the timed region): data set, thetas, estimator."""
     w = WORKLOAD
     X, y, thetas = make_inputs(w['n'], w['D'], w['n_imp'], 64, 7)
+    _W['X'], _W['y'] = X, y
     _W['est'], _ = _oracle_estimator(X, y)
     _W['thetas'] = thetas[0]
 
@@ -145,27 +152,99 @@ def _cpu_worker(args):
     return count
 
 
-def cpu_baseline_single(budget_s=12.):
-    """cpu_baseline leg of our arm: 1 host thread, FULL estimates for about budget_s seconds."""
+def _cpu_chain_worker(args):
+    """One host process: one single-chain sampler run of the reference's algorithm (oracle/apm_oracle_samplers.py) at the
+    pima shape, N_imp = 64, ARD kernel -- the CPU counterpart of the GPU arm's lock-step chains.  Returns
+    (iterations, seconds, FULL estimates, CACHED estimates)."""
+    method, seed, iters = args
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import apm_oracle as orc
+    import apm_oracle_samplers as osm
+    from apm_b200 import synth
+    w = WORKLOAD
+    n, D, N = w['n'], w['D'], w['n_imp']
+    est = _W['est']
+    prior = synth.prior_params(D)
+    lg = orc.log_gamma_log_pdf
+    counts = [0, 0]
+
+    def log_prior(th):
+        return lg(th[0], prior['a_sigma'], prior['b_sigma']) + sum(lg(t, prior['a_tau'], prior['b_tau']) for t in th[1:])
+
+    def log_f_estimator(u, theta=None, cached=None):
+        counts[0 if cached is None else 1] += 1
+        v, c = est(u, theta, cached)
+        return v + log_prior(theta), c
+
+    prng = np.random.RandomState(seed)
+    u_sampler = lambda: prng.normal(size=(n, N))  # noqa: E731
+    scales = np.full(D + 1, 0.1)
+    prop_sampler = lambda th, s: th + s * prng.normal(size=th.shape[0])  # noqa: E731
+    log_prop_density = lambda tp, tc, s: -0.5 * np.sum(((tp - tc) / s)**2)  # noqa: E731
+
+    def dir_and_w():
+        d = prng.normal(size=D + 1)
+        return d / d.dot(d)**0.5, 1.
+
+    theta0 = _W['thetas'][seed % 64]
+    import warnings
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        if method == 'pmmh':
+            def main(th):
+                counts[0] += 1
+                return est(prng.normal(size=(n, N)), th)[0] + log_prior(th)
+            osm.pmmh_chain(main, log_prop_density, prop_sampler, scales, prng, theta0, iters + 1)
+        else:
+            osm.apm_chain(method, log_f_estimator, u_sampler, prng, theta0, iters + 1, dir_and_w_sampler=dir_and_w,
+                          log_prop_density=log_prop_density, prop_sampler=prop_sampler, prop_scales=scales)
+    return iters, time.perf_counter() - t0, counts[0], counts[1]
+
+
+def cpu_baseline_settings(budget_s=(8., 6.)):
+    """cpu_baseline leg of our arm (rank 0): FULL estimates on the host with (a) one BLAS thread and (b) all cores as BLAS
+    threads of one process (the third setting, one single-thread process per core, is the --impl reference arm)."""
     w = WORKLOAD
     X, y, thetas = make_inputs(w['n'], w['D'], w['n_imp'], 64, 99)
     est, kind = _oracle_estimator(X, y)
     rs = np.random.RandomState(5)
-    est(rs.normal(size=(w['n'], w['n_imp'])), thetas[0][0])          # warm-up
-    n_done, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s:
-        est(rs.normal(size=(w['n'], w['n_imp'])), thetas[0][(n_done + 1) % 64])
-        n_done += 1
-    dt = time.perf_counter() - t0
-    return {'value': n_done / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-            'sample': '%d FULL estimates (n=%d, D=%d, N_imp=%d) in %.1f s, OPENBLAS_NUM_THREADS=1; %s; host has %d cores'
-                      % (n_done, w['n'], w['D'], w['n_imp'], dt, kind, os.cpu_count())}
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+
+    def run(budget):
+        est(rs.normal(size=(w['n'], w['n_imp'])), thetas[0][0])          # warm-up
+        n_done, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget:
+            est(rs.normal(size=(w['n'], w['n_imp'])), thetas[0][(n_done + 1) % 64])
+            n_done += 1
+        return n_done, time.perf_counter() - t0
+
+    n1, t1 = run(budget_s[0])
+    settings = {'blas_threads_1': {'value': n1 / t1, 'cores': 1, 'sample': '%d FULL estimates in %.1f s' % (n1, t1)}}
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=cores, user_api='blas'):
+            nc, tc = run(budget_s[1])
+        settings['blas_threads_nproc'] = {'value': nc / tc, 'cores': cores, 'sample': '%d FULL estimates in %.1f s' % (nc, tc)}
+    except Exception as e:      # threadpoolctl missing / BLAS without a thread control: say so instead of guessing
+        settings['blas_threads_nproc'] = {'value': None, 'cores': cores, 'sample': 'not measured: %s' % e}
+    best = max((k for k in settings if settings[k]['value']), key=lambda k: settings[k]['value'])
+    return {'value': settings[best]['value'], 'unit': UNIT, 'cores': settings[best]['cores'], 'kind': 'port',
+            'sample': 'best of two single-process settings (%s): %s; n=%d, D=%d, N_imp=%d; %s; host has %d cores; the third SURVEY '
+                      'setting (one single-BLAS-thread process per core) is the --impl reference arm'
+                      % (best, settings[best]['sample'], w['n'], w['D'], w['n_imp'], kind, cores),
+            'settings': settings}
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's CPU algorithm (oracle port) on all host cores: one single-BLAS-thread
     process per core (the fastest setting found in the survey), each step = `per_worker` FULL estimates per
-    process."""
+    process.  After the timed steps the same pool runs one short single-chain sampler run per core (E-SS + RD-SS and
+    PM-MH, the reference's loops restated in oracle/apm_oracle_samplers.py) for the CPU iterations/s."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
@@ -178,6 +257,7 @@ def run_reference_arm(args):
     per_worker = 2
     _, kind = _oracle_estimator(*make_inputs(8, 2, 1, 1, 0)[:2])
     ctx = mp.get_context('fork')
+    chain_legs = {}
     with ctx.Pool(cores, initializer=_cpu_worker_init) as pool:
         for wstep in range(args.warmup):
             pool.map(_cpu_worker, [(1000 + wstep * cores + i, 1) for i in range(cores)])
@@ -185,6 +265,17 @@ def run_reference_arm(args):
         for step in range(args.steps):
             pool.map(_cpu_worker, [(5000 + step * cores + i, per_worker) for i in range(cores)])
         dt = time.perf_counter() - t0
+        if not args.no_configs:
+            for method, iters in (('ess+rdss', 4), ('pmmh', 6)):
+                tw = time.perf_counter()
+                res = pool.map(_cpu_chain_worker, [(method, 300 + i, iters) for i in range(cores)])
+                tw = time.perf_counter() - tw
+                chain_legs[method] = {
+                    'value': sum(r[0] for r in res) / tw, 'unit': 'chain-iterations/s', 'chains': cores, 'iterations': iters,
+                    'full_estimates_per_iter': sum(r[2] - 1 for r in res) / float(sum(r[0] for r in res)),
+                    'cached_estimates_per_iter': sum(r[3] for r in res) / float(sum(r[0] for r in res)),
+                    'method': '%s, one chain per host core (%d processes, OPENBLAS_NUM_THREADS=1), reference loops restated in '
+                              'oracle/apm_oracle_samplers.py, wall clock of the whole pool' % (method, cores)}
     total = args.steps * cores * per_worker
     value = total / dt
     w = WORKLOAD
@@ -192,19 +283,159 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': '%s; CPU arm: %d FULL estimates per step' % (w['name'], cores * per_worker),
-                   'n': w['n'], 'D': w['D'], 'n_imp': w['n_imp'], 'kernel': w['kernel']},
+        'config': {'workload': w['name'], 'n': w['n'], 'D': w['D'], 'n_imp': w['n_imp'], 'kernel': w['kernel'],
+                   'execution': 'CPU arm: %d FULL estimates per step (%d per process)' % (cores * per_worker, per_worker)},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d processes x %d FULL estimates per step, OPENBLAS_NUM_THREADS=1 each; %s'
+                         'sample': '%d processes x %d FULL estimates per step, OPENBLAS_NUM_THREADS=1 each; %s; /root/reference is '
+                                   'absent on the GPU box, so the arm runs the port (timed beside oracle/ref_loader.py in the build '
+                                   'container: the port is ~7 %% faster than the unmodified reference, identical values)'
                                    % (cores, per_worker, kind)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if chain_legs:
+        line['apm_iters_per_s'] = chain_legs['ess+rdss']
+        line['configs'] = {'pmmh': chain_legs['pmmh']}
     print(json.dumps(line))
     return 0
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+class _Dist(object):
+    """Rank plumbing: barrier + synchronize, MAX / SUM over ranks."""
+
+    def __init__(self, torch, dist, world, dev):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, value, op='max'):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == 'max' else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed(self, fn, steps):
+        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = [fn(i) for i in range(steps)]
+        e1.record()
+        self.barrier()
+        return self.reduce(e0.elapsed_time(e1)), outs
+
+    def wall(self, fn):
+        """Host wall clock of fn between barriers, max over ranks (sampler runs: Python scheduler included)."""
+        self.barrier()
+        t0 = time.perf_counter()
+        out = fn()
+        self.barrier()
+        return self.reduce(time.perf_counter() - t0), out
+
+
+def _estimator_rates(D_, eng, n, D, N, B, reps, seed, want_cached=True):
+    """FULL (and CACHED) estimates/s of one engine with device-resident u; chains of all ranks."""
+    torch = D_.torch
+    gen = torch.Generator(device=D_.dev)
+    gen.manual_seed(seed)
+    from apm_b200 import synth
+    u = [torch.randn(B, n, N, dtype=torch.float64, device=D_.dev, generator=gen) for _ in range(2)]
+    thetas = [synth.bulk_thetas(B, D, seed=seed + 11 * i) for i in range(2)]
+    slots = np.arange(B)
+    for i in range(2):
+        eng.estimate_full(thetas[i], u[i], slots)
+    eng.work_count(reset=True)
+    ms_full, outs = D_.timed(lambda i: eng.estimate_full(thetas[i % 2], u[i % 2], slots), reps)
+    units = sum(eng.work_count(reset=True)) / float(B * reps)
+    out = {'full_estimates_per_s': D_.world * B * reps / (ms_full * 1e-3), 'chains': D_.world * B,
+           'newton_iters_mean': float(np.mean([(o[1] - 3).mean() for o in outs])),
+           'failed_chains': int(D_.reduce(sum((o[2] != 0).sum() for o in outs), 'sum')),
+           'executed_n3_over_3_units_per_estimate': units}
+    if want_cached:
+        ms_c, _ = D_.timed(lambda i: eng.estimate_cached(slots, u[(i + 1) % 2]), reps)
+        out['cached_estimates_per_s'] = D_.world * B * reps / (ms_c * 1e-3)
+    return out
+
+
+def _sampler_rate(D_, eng, n, D, N, B, method, iters, seed, rank):
+    from apm_b200 import batched, synth
+    drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, method, batched.make_log_prior(D, True),
+                                    [seed + rank * B + c for c in range(B)], prop_scales=np.full(D + 1, 0.1), rng='device',
+                                    device=D_.dev, async_full=True)
+    th0 = synth.bulk_thetas(B, D, seed=seed)
+    drv.get_samples(th0, 3)          # warm-up (allocations, first-use initialisation)
+    dt, out = D_.wall(lambda: drv.get_samples(th0, iters + 1))
+    return {'value': D_.world * B * iters / dt, 'unit': 'chain-iterations/s', 'iterations': iters, 'chains': D_.world * B,
+            'method': method, 'full_estimates_per_iter': float(out['n_full'].mean() - 1) / iters,
+            'cached_estimates_per_iter': float(out['n_cached'].mean()) / iters,
+            'failed_chains': int(D_.reduce((out['failed'] != 0).sum(), 'sum')),
+            'timing': 'host wall clock between barriers, max over ranks, incl. the Python scheduler and the drain of the last '
+                      'iterations; device RNG, asynchronous FULL rounds'}
+
+
+def run_configs(D_, rank, quick):
+    """BASELINE.json configurations 2-5, chains sharded over the ranks (independent chains: no data-path collective)."""
+    from apm_b200 import _capi, synth
+    torch, world, dev = D_.torch, D_.world, D_.dev
+    out = {}
+    # ---- config 2: breast-shaped, E-SS u + RD-SS theta, 256 lock-step chains per GPU
+    n, D, N, B = 682, 9, 64, 256
+    X, y, _ = synth.make_dataset(n, D, seed=0)
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N, device=dev.index)
+    eng.use_torch_stream()
+    ent = _estimator_rates(D_, eng, n, D, N, B, 4, 3)
+    ent['apm'] = _sampler_rate(D_, eng, n, D, N, B, 'ess+rdss', 20 if quick else 40, 2000, rank)
+    ent['workload'] = 'breast-shaped synthetic (n=682, D=9, ARD), Laplace IS N_imp=64, E-SS-u + RD-SS-theta, 256 chains per GPU'
+    out['breast_ess_rdss'] = ent
+    eng.close()
+    # ---- config 3: N_imp sweep, 1024 chains sharded over the ranks (Laplace: the reference has no EP; EP = labelled extension)
+    n, D = 768, 8
+    B = max(1024 // world, 1)
+    Ns = (1, 16, 64, 1024) if quick else (1, 4, 16, 64, 256, 1024)
+    X, y, _ = synth.make_dataset(n, D, seed=0)
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=B, max_nimp=max(Ns), device=dev.index)
+    eng.use_torch_stream()
+    sweep = {}
+    for N in Ns:
+        sweep[str(N)] = _estimator_rates(D_, eng, n, D, N, B, 2, 5 + N)
+    eng.set_approximation('ep', 1e-6, 100, 1.0)
+    ep = _estimator_rates(D_, eng, n, D, 64, B, 2, 77, want_cached=False)
+    eng.close()
+    out['nimp_sweep'] = {'workload': 'pima-shaped synthetic (n=768, D=8, ARD), Laplace IS, N_imp sweep, 1024 chains sharded over '
+                                     '%d GPU(s) (%d per GPU)' % (world, B), 'n_imp': sweep,
+                         'ep_extension_n_imp_64': {'full_estimates_per_s': ep['full_estimates_per_s'], 'ep_iters_mean': ep['newton_iters_mean'],
+                                                   'failed_chains': ep['failed_chains'],
+                                                   'note': 'EP posterior approximation: not in the reference (SURVEY App. D), checked '
+                                                           'against its own restatement in oracle/'}}
+    # ---- config 4: pseudo-marginal MH, 4096 chains on 8 GPUs = 512 per GPU
+    n, D, N, B = 768, 8, 64, 512
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N, device=dev.index)
+    eng.use_torch_stream()
+    ent = _sampler_rate(D_, eng, n, D, N, B, 'pmmh', 10 if quick else 20, 3000, rank)
+    ent['workload'] = 'pima-shaped synthetic, pseudo-marginal MH (fresh u inside every estimate), 512 chains per GPU'
+    out['pmmh'] = ent
+    eng.close()
+    # ---- config 5: n = 8192, D = 16 ARD, E-SS u + RD-SS theta, 8 chains per GPU (3.5 GB of matrices per chain)
+    n, D, N, B = 8192, 16, 64, 8
+    X, y, _ = synth.make_dataset(n, D, seed=0)
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N, device=dev.index)
+    eng.use_torch_stream()
+    ent = _estimator_rates(D_, eng, n, D, N, B, 2, 9)
+    n3 = float(n)**3
+    ent['executed_tflops'] = ent['full_estimates_per_s'] * ent['executed_n3_over_3_units_per_estimate'] / 3. * n3 / 1e12
+    ent['survey_tflops'] = ent['full_estimates_per_s'] * (ent['newton_iters_mean'] / 3. + 8. / 3.) * n3 / 1e12
+    ent['apm'] = _sampler_rate(D_, eng, n, D, N, B, 'ess+rdss', 2, 4000, rank)
+    ent['workload'] = 'large synthetic GP probit (n=8192, D=16, ARD), Laplace IS N_imp=64, E-SS-u + RD-SS-theta, 8 chains per GPU'
+    out['large_n8192'] = ent
+    eng.close()
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -220,6 +451,8 @@ def run_gpu_arm(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
+    D_ = _Dist(torch, dist, world, dev)
+    barrier, timed = D_.barrier, D_.timed
 
     w = WORKLOAD
     n, D, N, B = w['n'], w['D'], w['n_imp'], args.chains or w['chains_per_gpu']
@@ -235,24 +468,6 @@ def run_gpu_arm(args):
     for h, d in zip(u_host, u_dev):
         h.copy_(d)
     torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        outs = [fn(i) for i in range(steps)]
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), outs
 
     def step_resident(i):
         return eng.estimate_full(thetas[i % 3], u_dev[i % 2], slots[i % 2])
@@ -302,18 +517,12 @@ def run_gpu_arm(args):
     # ---- APM-MCMC iterations/s: ESS-u + RD-SS-theta in lock-step over the same chains (device-resident u)
     from apm_b200 import batched
     drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, 'ess+rdss', batched.make_log_prior(D, True),
-                                    [1000 + rank * B + c for c in range(B)], rng='device', device=dev, async_full=True)
+                                    [1000 + rank * B + c for c in range(B)], prop_scales=np.full(D + 1, 0.1), rng='device',
+                                    device=dev, async_full=True)
     apm_iters = args.apm_iters
     drv.get_samples(thetas[0], 3)          # warm-up (allocations, first-use initialisation)
-    barrier()
-    t_apm = time.perf_counter()
-    apm_out = drv.get_samples(thetas[0], apm_iters + 1)
-    barrier()
-    t_apm = time.perf_counter() - t_apm
-    t_apm_t = torch.tensor([t_apm], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_apm_t, op=dist.ReduceOp.MAX)
-    t_apm = float(t_apm_t.item())
+    t_apm, apm_out = D_.wall(lambda: drv.get_samples(thetas[0], apm_iters + 1))
+    apm_failed = int(D_.reduce((apm_out['failed'] != 0).sum(), 'sum'))
 
     # ---- diagnostics gather over NCCL (per-chain log-ML of the last step): the only collective of the path
     last = torch.from_numpy(outs[-1][0]).to(dev)
@@ -323,6 +532,9 @@ def run_gpu_arm(args):
         all_logml = torch.cat(gathered).cpu().numpy()
     else:
         all_logml = last.cpu().numpy()
+    eng.close()
+
+    configs = None if args.no_configs else run_configs(D_, rank, args.quick_configs)
 
     if rank == 0:
         peak_dmma = _capi.measure_fp64_peak(0, local_rank)
@@ -331,22 +543,30 @@ def run_gpu_arm(args):
         hbm_peak, hbm_src = 6650., 'fallback (B200_PROFILING.md)'
         if os.path.isfile(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
-        n3 = float(n)**3
-        flops = {   # algorithmic flops per kernel family over the timed region (this rank)
+        n3, n2 = float(n)**3, float(n)**2
+        tri = 8. * n * (n + 64) / 2.            # bytes of the lower 64-blocks of one n x n fp64 matrix
+        flops = {   # algorithmic flops per kernel family over the roofline pass (this rank)
             # chain-Choleskys actually factored: chol(K), chol(B) per B-space Newton round, chol(M') -- the hybrid Newton
             # round makes chol(M') the last iteration's factorisation, so most chains run I + 1, not I + 2 of them
             'k_chol': chol_units * n3 / 3.,
-            # factored covariance: M' = I + Y'Y'^T is n^3/3; chol(C) itself is never formed (factored cache),
-            # so the TRSM family is only the n^2 N solve of the importance-sampling tail
-            'k_trsm_rows': chains_done * float(n)**2 * N,
-            'k_syrk_sub': syrk_units * n3 / 3.,                        # M' = I + Y'Y'^T builds executed
-            'k_gemm_tri': chains_done * float(n)**2 * N,
+            # factored covariance: chol(C) itself is never formed (factored cache), so the TRSM family is
+            # only the n^2 N solve of the importance-sampling tail
+            'k_trsm_rows': chains_done * n2 * N,
+            'k_syrk_sub': syrk_units * n3 / 3.,                        # M' = I + L_K^T W L_K builds executed (k_syrk_lk)
+            'k_gemm_tri': chains_done * n2 * N,
         }
-        hbm_bytes = {  # algorithmic bytes of the bandwidth-bound families
-            'k_build_K': chains_done * 8. * n * n,
-            # triangular mat-vecs of the M-space Newton rounds (L_K^T b and L_K mu~, lower tiles of L_K each); the B-space
-            # rounds are mat-vec-free (k_fnew_from_s reads O(n) vectors)
-            'k_matvec': syrk_units * 2. * 8. * (n * (n + 64) / 2.),
+        hbm_bytes = {  # algorithmic bytes of the bandwidth-bound families over the roofline pass
+            'k_build_K': chains_done * 8. * n2,
+            # triangular mat-vecs of the M-space Newton rounds (L_K^T b and L_K mu~) + mu~ = L_K^T a of the covariance phase
+            'k_matvec': syrk_units * 2. * tri,
+            # s = L^-T L^-1 t: the factor is read twice per Newton iteration (forward + backward substitution)
+            'k_trsv2': iters_prof * 2. * tri,
+            # k_is_logw reads F, Zf, U^T (3 x 8 n N) per chain; the log-sum-exp stage is O(N)
+            'k_is_epilogue': chains_done * 24. * n * N,
+            # u[n][N] -> U^T[Npad][np] (read + write) and the anti-transpose L' -> V of the factored cache (lower blocks, read + write)
+            'k_transpose_u': chains_done * (16. * n * N + 2. * tri),
+            # O(n) vector kernels: prep reads f, y and writes W, W^1/2, b, t; finish reads f', f and writes f (9 vectors / iteration)
+            'k_newton_vec': iters_prof * 9. * 8. * n,
         }
         kern = {}
         for name, (ms, cnt) in prof.items():
@@ -359,21 +579,32 @@ def run_gpu_arm(args):
             elif name in hbm_bytes:
                 ent.update(bound='hbm', achieved=hbm_bytes[name] / (ms * 1e-3) / 1e9, unit='GB/s')
                 ent['frac'] = ent['achieved'] / hbm_peak
+            else:       # 'misc': queue initialisation, masks, copies of O(B) integers -- launch-latency bound
+                ent.update(bound='launch', achieved=cnt / (ms * 1e-3), unit='launches/s', frac=None)
             kern[name] = ent
         dom = max((k for k in kern if k in flops), key=lambda k: kern[k]['ms_total'])
         d = kern[dom]
+        traffic, traffic_src = None, 'no ncu capture on record for this kernel / shape'
+        tfile = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+        if os.path.isfile(tfile):
+            try:
+                rec = json.load(open(tfile)).get('%s:n=%d:chains=%d' % (dom, n, B))
+                if rec:
+                    traffic, traffic_src = rec['dram_bytes_per_launch'], rec['source']
+            except Exception:
+                pass
         roofline = {
             'bound': 'tensor', 'kernel': dom, 'achieved': d['achieved'], 'peak': peak_dmma, 'unit': 'TFLOP/s',
             'frac': d['frac'],
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_chol_dataflow launch (256 chains, n = 768) from the
-            # `ncu --set full` capture summarised in profiles/r1h_ncu_top_kernels_full.md: 4.21 GB + 1.20 GB
-            'traffic': 5.41e9 if (dom == 'k_chol' and n == 768 and B == 256) else None,
-            'traffic_note': 'bytes per launch from ncu (profiles/r1h_ncu_top_kernels_full.md); minimum (read K, write L) '
-                            'is 1.28 GB, the blocked left-looking operand traffic with a working set > L2 is 4.7 GB',
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-batch launch of the dominant kernel, from the
+            # `ncu --set full` capture named in traffic_source (profiles/ncu_traffic.json; never measured under this run)
+            'traffic': traffic, 'traffic_source': traffic_src,
+            'algorithmic_bytes_per_launch': B * 2. * tri,
             'achieved_per_launch_gflop': flops[dom] / d['launches'] / 1e9,
             'avg_launch_ms': d['ms_total'] / d['launches'],
-            'measured': 'CUDA events around every launch of a second pass of the same %d steps, single lane, stream overlap off '
-                        '(%.2f ms/step; the timed `value` pass runs with lanes and overlap on and no per-launch events)' % (args.steps, ms_prof / args.steps),
+            'measured': 'CUDA events around every launch of a second pass of the same %d steps, stream overlap off '
+                        '(%.2f ms/step; the timed `value` pass runs with the chol(K) / M-space overlap on and no per-launch events)'
+                        % (args.steps, ms_prof / args.steps),
             'peak_source': 'fp64 DMMA (mma.sync m8n8k4.f64) issue peak measured in this run by apm_measure_fp64_peak; '
                            'MEASURED_PEAKS.json has no fp64 entry (bf16 only). DFMA peak %.1f TFLOP/s. HBM peak %.0f GB/s %s'
                            % (peak_dfma, hbm_peak, hbm_src),
@@ -389,17 +620,18 @@ def run_gpu_arm(args):
                                    % (work_value[0] / chains_done, work_value[1] / chains_done)},
             'kernels': kern,
         }
-        cpu = cpu_baseline_single() if not args.no_cpu_baseline else None
+        cpu = cpu_baseline_settings() if not args.no_cpu_baseline else None
         value = world * chains_done / (ms_total * 1e-3)
         e2e_val = world * chains_done / (ms_e2e * 1e-3)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': '%s; %d chains per GPU per step' % (w['name'], B), 'n': n, 'D': D, 'n_imp': N,
-                       'kernel': w['kernel'], 'chains_per_gpu': B, 'parallelism': 'independent chains sharded over %d GPU(s)' % world,
+            'config': {'workload': w['name'], 'n': n, 'D': D, 'n_imp': N,
+                       'kernel': w['kernel'], 'chains_per_gpu': B, 'parallelism': 'independent chains sharded over %d GPU(s), %d per GPU per step' % (world, B),
                        'l2_policy': 'inputs larger than L2: u 100.7 MB/step alternating between two buffers, per-chain matrices 1.2 GB each',
-                       'execution': 'apm_estimate_full splits the batch into lanes (up to 8 chain groups on their own host threads and streams); the roofline pass runs single-lane',
+                       'execution': 'one host thread per GPU; per factorisation one persistent TMA / mbarrier dataflow launch over all chains; '
+                                    'Newton rounds queued under device-side masks (one host round trip per estimate)',
                        'newton_iters_mean': iters_total / chains_done, 'failed_chains': bad},
             'e2e': {'value': e2e_val, 'unit': UNIT, 'ms_per_step': ms_e2e / args.steps,
                     'h2d_bytes_per_step': int(B * n * N * 8 + B * (D + 1) * 8), 'd2h_bytes_per_step': int(B * (8 + 4 + 4))},
@@ -412,7 +644,8 @@ def run_gpu_arm(args):
                                 'method': 'E-SS u + RD-SS theta, lock-step, %d chains/GPU, %d iterations, device RNG, asynchronous FULL rounds (worker thread + companion context for the CACHED rounds)' % (B, apm_iters),
                                 'full_estimates_per_iter': float(apm_out['n_full'].mean() - 1) / apm_iters,
                                 'cached_estimates_per_iter': float(apm_out['n_cached'].mean()) / apm_iters,
-                                'failed_chains': int((apm_out['failed'] != 0).sum()), 'timing': 'host wall clock incl. the Python scheduler and the drain of the last iterations'},
+                                'failed_chains': apm_failed, 'timing': 'host wall clock between barriers, max over ranks, incl. the Python scheduler and the drain of the last iterations'},
+            'configs': configs,
             'diagnostics_gather': {'collective': 'nccl all_gather' if world > 1 else 'none (1 GPU)',
                                    'chains': int(all_logml.shape[0]), 'mean_logml': float(np.nanmean(all_logml))},
         }
@@ -420,7 +653,6 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
     return 0
 
 
@@ -432,6 +664,8 @@ def main():
     ap.add_argument('--impl', default='apm_b200', choices=['apm_b200', 'reference'])
     ap.add_argument('--chains', type=int, default=0, help='chains per GPU (default 256)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the BASELINE configurations 2-5 (and the CPU sampler legs of the reference arm)')
+    ap.add_argument('--quick-configs', action='store_true', help='shorter sampler runs / fewer sweep points in the configurations')
     ap.add_argument('--apm-iters', type=int, default=100, help='iterations of the batched ESS+RDSS sampler leg (chains drain at the end of a run: short runs understate the steady state)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -143,3 +143,50 @@ def test_estimator_newton_iteration_counts():
         key = 't%d_' % t
         assert est.n_cubic_ops == int(g[key + 'cubic_ops']) == iters[t] + 3
         assert abs(full - g[key + 'full']) <= max(1e-10 * abs(g[key + 'full']), 10. * float(g[key + 'ulp_sens']))
+
+
+@pytest.mark.parametrize('method', ['ess+rdss', 'mi+mh', 'ess+mh', 'mi+rdss', 'pmmh'])
+def test_sampler_restatement_vs_reference_chains(method):
+    """oracle/apm_oracle_samplers.py (the chain loops timed by bench.py's reference arm) against the 1000-iteration chains
+    of the UNMODIFIED reference (tests/golden/samplers.npz): identical traces, reject counts and cubic-op counts."""
+    import apm_oracle_samplers as osm
+    from apm_b200 import synth
+    from wiring import first_divergence
+    g = load_golden('samplers')
+    X, y = g['X'], g['y']
+    N, n_iter = 4, 400
+    D = X.shape[1]
+    prior = synth.prior_params(D)
+    kf = lambda K, X_, th: orc.isotropic_squared_exponential_kernel(K, X_, th, 1e-8)  # noqa: E731
+    ml = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, kf, orc.laplace_approximation)
+    lg = orc.log_gamma_log_pdf
+    log_prior = lambda th: lg(th[0], prior['a_sigma'], prior['b_sigma']) + lg(th[1], prior['a_tau'], prior['b_tau'])  # noqa: E731
+
+    def log_f_estimator(u, theta=None, cached=None):
+        v, c = ml(u, theta, cached)
+        return v + log_prior(theta), c
+
+    prng = np.random.RandomState()
+    u_sampler = lambda: prng.normal(size=(y.shape[0], N))  # noqa: E731
+    prop_sampler = lambda th, s: np.r_[th[0] + s[0] * prng.normal(), th[1] + s[1] * prng.normal()]  # noqa: E731
+    log_prop_density = lambda tp, tc, s: -0.5 * (((tp[0] - tc[0]) / s[0])**2 + ((tp[1] - tc[1]) / s[1])**2)  # noqa: E731
+
+    def dir_and_w():
+        d = prng.normal(size=2)
+        d /= d.dot(d)**0.5
+        return d, 1.
+
+    prng.seed(1000 + N)
+    theta_init = synth.draw_theta_prior(prng, D, ard=False)
+    scales = np.array([0.5, 0.5])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        if method == 'pmmh':
+            main = lambda th: ml(prng.normal(size=(y.shape[0], N)), th)[0] + log_prior(th)  # noqa: E731
+            thetas, n_rej = osm.pmmh_chain(main, log_prop_density, prop_sampler, scales, prng, theta_init, n_iter)
+        else:
+            thetas, n_rej = osm.apm_chain(method, log_f_estimator, u_sampler, prng, theta_init, n_iter, dir_and_w_sampler=dir_and_w,
+                                          log_prop_density=log_prop_density, prop_sampler=prop_sampler, prop_scales=scales)
+    key = '%s_N%d_' % (method, N)
+    assert first_divergence(thetas, g[key + 'thetas'][:n_iter]) is None
