@@ -54,6 +54,9 @@ struct apm_ctx {
     cudaStream_t copy_stream = nullptr;   // H2D of the auxiliary normals overlaps the O(n^3) front of a FULL estimate
     cudaEvent_t copy_done = nullptr;
     bool u_staged = false;
+    // host u of the running apm_estimate_full: its upload is started by run_newton right before the first host round trip,
+    // i.e. after the whole mode search has been queued (a pageable buffer makes cudaMemcpyAsync block the host thread)
+    const double* pend_u = nullptr; int pend_N = 0, pend_B = 0;
     // chol(K) is only needed by the importance-sampling tail: it runs on aux_stream (per-step launches) as filler
     // work beside the Newton rounds, whose latency-bound kernels leave SM slots idle
     cudaStream_t aux_stream = nullptr;
@@ -683,6 +686,8 @@ struct StreamSwap {
 // reads the number of still-active chains after `newton_r0` rounds have been queued (then after every further round):
 // one host round trip per estimate on typical data (4-5 iterations) instead of one per iteration.  In a hybrid round the
 // two forms touch disjoint chains: the B-space form runs on the main stream, the M-space form beside it on the aux stream.
+static int prefetch_u(apm_ctx* c, const double* u, int u_on_device, int N, int B);
+
 static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pending = false) {
     NewtonVecs nv = make_nv(c);
     const bool hybrid = dSlots != nullptr && c->factored_cov && c->hybrid_newton;
@@ -786,6 +791,10 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
         APM_TRY(check_launch(c, "k_newton_finish"));
         if (it + 1 < c->newton_r0 && it + 1 < c->max_iters) continue;     // keep queueing: no host round trip yet
         CU_TRY(cudaMemcpyAsync(c->hNActive, c->dNActive, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (c->pend_u) {       // the GPU is busy with the queued rounds: now is the time to bring u over
+            APM_TRY(prefetch_u(c, c->pend_u, 0, c->pend_N, c->pend_B));
+            c->pend_u = nullptr;
+        }
         CU_TRY(cudaStreamSynchronize(c->stream));
         n_act = c->hNActive[0];
         c->newton_b_finisher_count = hybrid ? c->hNActive[2] : 0;   // (cumulative) finished in a B-space round: need the covariance phase
@@ -1266,12 +1275,20 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
     APM_TRY(check_B(c, B));
     if (!theta || !u || !slots || !logml_out) return APM_ERR_INVALID;
     cancel_prefetch(c);
-    APM_TRY(prefetch_u(c, u, u_on_device, N, B));
     const bool overlap = c->overlap_chol_k;
     APM_TRY(full_front(c, theta, B, slots, overlap));
+    if (N <= 0 || N > c->maxN) {
+        set_err("N (importance samples) out of range for this context");
+        return APM_ERR_INVALID;
+    }
+    c->pend_u = u_on_device ? nullptr : u;
+    c->pend_N = N; c->pend_B = B;
+    int rc_mode = (c->approx == 1) ? run_ep(c, B)                               // extension: EP behind post_approx_func
+                                   : run_newton(c, B, c->dSlotsA, overlap);     // estimators.py:207 -> lpa.py:81-102
+    c->pend_u = nullptr;
+    APM_TRY(rc_mode);
+    // u is only needed by the importance-sampling tail: a host buffer has had the whole mode search to cross the bus
     APM_TRY(stage_u(c, u, u_on_device, N, B));
-    if (c->approx == 1) APM_TRY(run_ep(c, B));                                  // extension: EP behind post_approx_func
-    else APM_TRY(run_newton(c, B, c->dSlotsA, overlap));                        // estimators.py:207 -> lpa.py:81-102
     if (c->factored_cov) {
         // chol(C) = L_K U^-T straight from chol(K) and W (lpa.py:111-112 + estimators.py:209 without forming C)
         if (overlap) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));

@@ -398,6 +398,59 @@ def test_many_blocks_n2048():
     eng.close()
 
 
+def test_large_n8192_full_and_cached_vs_oracle():
+    """BASELINE config 5 shape (n = 8192, D = 16, ARD, N_imp = 64): 128 block columns, 512 MB per matrix.  One FULL and one
+    CACHED estimate against the CPU oracle (all host cores as BLAS threads: ~1-2 min), at the north-star tolerance 1e-9."""
+    from threadpoolctl import threadpool_limits
+    n, D, N = 8192, 16, 64
+    X, y, th = synth.make_dataset(n, D, seed=0)
+    rs = np.random.RandomState(8)
+    u1, u2 = rs.normal(size=(1, n, N)), rs.normal(size=(1, n, N))
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=1, n_slots=2, max_nimp=N)
+    full, ops, st = eng.estimate_full(th[None], u1, [0])
+    cached, st2 = eng.estimate_cached([0], u2)
+    again, _ = eng.estimate_cached([0], u1)
+    assert st[0] == 0 and st2[0] == 0 and again[0] == full[0]
+    eng.close()
+    import os
+    with threadpool_limits(limits=max(1, min(16, os.cpu_count() or 1)), user_api='blas'):
+        est = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, oracle_kernel('ard', 1e-8), orc.laplace_approximation)
+        ref, cache = est(u1[0], th)
+        ref2, _ = est(u2[0], None, cache)
+    assert ops[0] == est.n_cubic_ops
+    assert abs(full[0] - ref) < 1e-9 * abs(ref), (full[0], ref)
+    assert abs(cached[0] - ref2) < 1e-9 * abs(ref2), (cached[0], ref2)
+
+
+@pytest.mark.parametrize('N', [256, 1024])
+def test_many_importance_samples_vs_oracle(N):
+    """BASELINE config 3 shapes: pima (n = 768, D = 8, ARD) with N_imp = 256 and 1024 (4 and 16 sample-row blocks in the tail
+    kernels), FULL and CACHED estimates and the per-sample log-weights against the oracle."""
+    n, D, B = 768, 8, 2
+    X, y, th = synth.make_dataset(n, D, seed=0)
+    thetas = np.stack([th, th + 0.1])
+    rs = np.random.RandomState(N)
+    u1, u2 = rs.normal(size=(B, n, N)), rs.normal(size=(B, n, N))
+    eng = _capi.Engine(X, y, kernel='ard', max_chains=B, max_nimp=N)
+    full, ops, st = eng.estimate_full(thetas, u1, [0, 1])
+    cached, st2 = eng.estimate_cached([0, 1], u2)
+    logw = eng.cached_weights([0, 1], u2)
+    assert np.all(st == 0) and np.all(st2 == 0)
+    for b in range(B):
+        est = orc.LogMarginalLikelihoodApproxPosteriorISEstimator(X, y, oracle_kernel('ard', 1e-8), orc.laplace_approximation)
+        ref, cache = est(u1[b], thetas[b])
+        ref2, _ = est(u2[b], None, cache)
+        K0 = np.empty((n, n))
+        oracle_kernel('ard', 1e-8)(K0, X, thetas[b])
+        tol = max(REL, 2e-15 * np.linalg.cond(K0))
+        assert ops[b] == est.n_cubic_ops
+        assert abs(full[b] - ref) < tol * abs(ref), (b, full[b], ref)
+        assert abs(cached[b] - ref2) < tol * abs(ref2), (b, cached[b], ref2)
+        lw_ref = orc.is_log_weights(u2[b], y, *cache)
+        assert np.max(np.abs(logw[b] - lw_ref)) < tol * np.max(np.abs(lw_ref))
+    eng.close()
+
+
 def test_ep_approximation_vs_oracle():
     """EP (extension; the reference has no EP): the CUDA parallel-EP loop against its numpy restatement -- same
     iteration count, posterior mean / covariance / site parameters to 1e-9 -- standalone and inside the IS estimator
