@@ -97,7 +97,7 @@ struct apm_ctx {
     int* dFlowCounter = nullptr;   // per queue set: [0] task queue head, [1] chains to factorise (k_chol_flow_init)
     // k_chol_flow (TMA / mbarrier dataflow Cholesky): tensor maps over the three matrix buffers it factors into, and two
     // sets of queue state + packed diagonal blocks (set 1: launches on the aux stream, which overlap the main stream's)
-    CUtensorMap tmLB, tmSlotLK, tmSlotLC, tmK;
+    CUtensorMap tmLB, tmSlotLK, tmSlotLC, tmK, tmSlotLK16;   // (16: k-major 16x16 boxes of L_K for the fused M' source)
     bool tma_ok = false;
     int *dFlow2Progress[2] = {nullptr, nullptr}, *dFlow2Skip[2] = {nullptr, nullptr};
     double* dDiagPack[2] = {nullptr, nullptr};
@@ -192,10 +192,10 @@ static int check_launch(apm_ctx* c, const char* what) {
 static int g_attr_done = 0;
 static int set_kernel_attrs() {
     if (g_attr_done) return APM_OK;
-    CU_TRY(cudaFuncSetAttribute(k_chol_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(k_syrk_lk, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_gemm_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_build_K, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -319,6 +319,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
         c->tma_ok = make_matrix_tmap(&c->tmLB, c->dLB, c->np, (long long)Bm) &&
                     make_matrix_tmap(&c->tmK, c->dK, c->np, (long long)Bm) &&
                     make_matrix_tmap(&c->tmSlotLK, c->dSlotLK, c->np, (long long)n_slots) &&
+                    make_matrix_tmap(&c->tmSlotLK16, c->dSlotLK, c->np, (long long)n_slots, 16) &&
                     make_matrix_tmap(&c->tmSlotLC, c->dSlotLC, c->np, (long long)n_slots);
         if (!c->tma_ok) {
             set_err("apm_create: cuTensorMapEncodeTiled failed (TMA descriptors of the Cholesky operands)");
@@ -327,7 +328,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
         }
         int occ = 0, sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_flow, CF_THREADS, CF_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_flow<true>, CF_THREADS, CF_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
         c->flow2_grid = occ * sms;
         if (getenv("APM_FLOW_GRID") && atoi(getenv("APM_FLOW_GRID")) > 0) c->flow2_grid = atoi(getenv("APM_FLOW_GRID"));
     }
@@ -575,7 +576,10 @@ static int build_K(apm_ctx* c, int B, int kind, double eps) {
 // work_slot >= 0: the number of chains actually factorised is added to dWork[work_slot] as well (M' factorisations).
 static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, const int* src_idx, double* dst,
                     long long dst_bs, const int* dst_idx, const double* scale, int add_identity, double* logdet_parts,
-                    const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr) {
+                    const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr,
+                    const int* syrk_slots = nullptr) {
+    // syrk_slots != null: the source is M' = P (I + L_K^T W L_K) P, accumulated on the fly from chol(K) in those slots and
+    // W (dVec[V_W]) inside the factorisation's tasks (src is ignored; see chol_flow.cuh)
     cudaStream_t st = c->launch_stream ? c->launch_stream : c->stream;
     const int set = (st == c->aux_stream) ? 1 : 0;
     const CUtensorMap *tm = nullptr, *tms = nullptr;
@@ -587,7 +591,9 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
         m0 = (int)((dst - c->dLB) / (long long)c->mat);
     }
     // source: K (Newton / chol K), the LB buffer (M' in place) or a slot's L_C buffer (explicit covariance in place)
-    if (src_idx) {
+    if (syrk_slots) {
+        tms = &c->tmK;      // (unused by the fused-source instantiation)
+    } else if (src_idx) {
         tms = (src == c->dSlotLC) ? &c->tmSlotLC : (src == c->dSlotLK ? &c->tmSlotLK : nullptr);
     } else if (src >= c->dK && src < c->dK + (size_t)c->maxB * c->mat) {
         tms = &c->tmK;
@@ -610,13 +616,16 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     q.counter = c->dFlowCounter + 2 * set; q.progress = c->dFlow2Progress[set]; q.list = c->dFlow2Skip[set];
     q.diagpack = c->dDiagPack[set];
     q.spin_ns = 64;
+    q.lk_idx = syrk_slots; q.w = c->dVec[V_W]; q.w_bs = c->np;
     const int total_tasks = B * c->nb * (c->nb + 1) / 2;
     prof_begin(c, KID_MISC);
-    k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb, c->dWork);
+    k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb, c->dWork,
+                                                             syrk_slots ? c->dWork + 1 : nullptr);
     APM_TRY(check_launch(c, "k_chol_flow_init"));
     const int grid = c->flow2_grid < total_tasks ? c->flow2_grid : total_tasks;
     prof_begin(c, KID_CHOL);
-    k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, q);
+    if (syrk_slots) k_chol_flow<true><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
+    else k_chol_flow<false><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
     return check_launch(c, "k_chol_flow");
 }
 
@@ -641,23 +650,6 @@ static NewtonVecs make_nv(apm_ctx* c) {
     nv.tol = c->tol; nv.max_iters = c->max_iters;
     nv.done_m = nullptr; nv.mask_b = nullptr; nv.mask_m = nullptr; nv.pred_factor = c->pred_factor;
     return nv;
-}
-
-// M' = P (I + L_K^T W L_K) P (lower tiles, reversed coordinates) -> dLB, for chains in `mask` (null: all), straight from
-// chol(K) in the slots (k-major operand stages: see tile_engine.cuh "Factored posterior covariance")
-static int run_build_mprime(apm_ctx* c, int B, const int* dSlots, const int* mask) {
-    prof_begin(c, KID_MISC);
-    k_count_mask<<<1, 256, 0, c->stream>>>(mask, c->dStatus, B, c->dWork + 1);
-    APM_TRY(check_launch(c, "k_count_mask"));
-    SyrkLkParams s;
-    s.LK = c->dSlotLK; s.lk_bs = (long long)c->mat; s.ldk = c->np; s.lk_idx = dSlots;
-    s.W = c->dVec[V_W]; s.w_bs = c->np;
-    s.M = c->dLB; s.m_bs = (long long)c->mat; s.ldm = c->np;
-    s.nb = c->nb; s.ntiles = c->nb * (c->nb + 1) / 2;
-    s.status = c->dStatus; s.mask = mask;
-    prof_begin(c, KID_SYRK);
-    k_syrk_lk<<<B * s.ntiles, TILE_THREADS, TILE_SMEM_BYTES, c->stream>>>(s);
-    return check_launch(c, "k_syrk_lk");
 }
 
 // Newton mode search (lpa.py:81-102) for chains 0..B-1 whose K sits in c->dK.  On exit f (V_F) is the
@@ -765,10 +757,9 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
             k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, nv.bvec, c->np,
                                                                 nv.t, c->np, nullptr, c->dStatus, maskM, 1);
             APM_TRY(check_launch(c, "k_lt_matvec"));
-            // L' = chol(M'), M' = P (I + L_K^T W L_K) P
-            APM_TRY(run_build_mprime(c, B, dSlots, maskM));
-            APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB));
+            // L' = chol(M'), M' = P (I + L_K^T W L_K) P built inside the factorisation from L_K and W (never stored)
+            APM_TRY(run_chol(c, B, nullptr, 0, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
+                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, dSlots));
             // s' = M'^-1 t'
             prof_begin(c, KID_TRSV);
             k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
@@ -908,10 +899,9 @@ static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots, const i
         todo = c->dMaskB;
     }
     if (need_cov) {
-        APM_TRY(run_build_mprime(c, B, dSlots, todo));
-        // L' = chol(M') in place (M' has eigenvalues >= 1: cannot fail for finite input)
-        APM_TRY(run_chol(c, B, c->dLB, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                         nullptr, APM_CHAIN_CHOL_C, todo, nullptr));
+        // L' = chol(M'), M' = P (I + L_K^T W L_K) P from L_K and W (M' has eigenvalues >= 1: cannot fail for finite input)
+        APM_TRY(run_chol(c, B, nullptr, 0, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
+                         nullptr, APM_CHAIN_CHOL_C, todo, nullptr, dSlots));
     }
     // V = anti-transpose of L' into the slot's L_C buffer; mu~ = L_K^T a.  The importance-sampling tail works with
     // (L_K, V, mu, mu~) directly, so the n^3/3 triangular solve for the explicit L_C = L_K V^-1 is only run if somebody

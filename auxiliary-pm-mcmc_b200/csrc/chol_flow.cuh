@@ -44,7 +44,7 @@ constexpr int CF_STAGES = APM_CF_STAGES;
 constexpr int DP_LBLOCKS = 36;                         // lower 8x8 blocks (q >= p) of a 64x64 triangle, block (q,p) at q(q+1)/2 + p
 constexpr int DP_DOUBLES = (DP_LBLOCKS + 8) * 64;      // + inverses of the 8 diagonal 8x8 blocks
 constexpr int DP_BYTES = DP_DOUBLES * 8;               // 22528
-constexpr int CF_CTRL_BYTES = 512;
+constexpr int CF_CTRL_BYTES = 1024;
 constexpr int CF_SMEM_BYTES = 1024 + CF_STAGES * 2 * CF_CHUNK_BYTES + DP_BYTES + CF_CTRL_BYTES;   // 1024: manual alignment slack
 
 __device__ __forceinline__ int dp_block(int q, int p) { return (q * (q + 1) / 2 + p) * 64; }
@@ -122,6 +122,9 @@ struct CholFlowParams {
     int src_m0;                  // same for the source tensor map when src_idx == null
     int np;                      // rows per matrix in the tensor maps (n padded)
     int zero;                    // always 0, but only known at run time (see cf_release_stage)
+    // k_chol_flow<true>: the source matrix is M' = P (I + L_K^T W L_K) P and is never stored: its tiles are accumulated on the
+    // fly from k-major 16x16 boxes of L_K (tensor map tml) scaled by W before the factorisation's own k-loop (src unused)
+    const int* lk_idx; const double* w; long long w_bs;
     const double* scale; long long scale_bs;
     int add_identity;
     int nb;
@@ -141,7 +144,7 @@ struct CholFlowParams {
 // Newton mask) into an ordered list: a launch for a few straggler chains enumerates only their tasks.  One launch instead
 // of two memsets + a snapshot kernel; block 0 / warp 0 does the (ballot) compaction.
 __global__ void k_chol_flow_init(int* counter, int* progress, int* list, const int* status, const int* active, int nchains, int nb,
-                                 unsigned long long* work) {
+                                 unsigned long long* work, unsigned long long* work2) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nchains * nb) progress[e] = 0;
     if (blockIdx.x == 0 && threadIdx.x < 32) {
@@ -157,6 +160,7 @@ __global__ void k_chol_flow_init(int* counter, int* progress, int* list, const i
             counter[0] = 0;
             counter[1] = count;
             if (work && count) atomicAdd(work, (unsigned long long)count);   // chain-Choleskys executed (work accounting)
+            if (work2 && count) atomicAdd(work2, (unsigned long long)count); // ... and M' builds, when the source is the fused SYRK
         }
     }
 }
@@ -232,6 +236,44 @@ __device__ __forceinline__ void cf_gemm_chunk(CfAcc& acc, const unsigned char* s
 #pragma unroll
         for (int nt = 0; nt < 8; nt++)
             if (!DIAG || nt <= 2 * warp + 1) b[nt] = *reinterpret_cast<const double*>(b_base + nt * 1024 + lo);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+            if (!DIAG || nt <= 2 * warp + 1) {
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+                    if (!DIAG || nt <= 2 * warp + mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            }
+    }
+}
+
+// Source tiles of M' = P (I + L_K^T W L_K) P on the fly ("TN" chunk: sum over ROWS r of the row-major L_K).  Tile (i, k) of M'
+// is tile (I, K) = (nb-1-i, nb-1-k) of M with both index orders reversed:
+//   S[m'][n'] = [i == k][m' == n'] + sum_{r >= 64 K} W_r L_K[r][64 I + 63 - m'] L_K[r][64 K + 63 - n'].
+// A stage holds 16 rows r as eight 16x16 boxes (k-major: row r at r*128 bytes inside a box, 16-byte segment c at c ^ (r & 7)):
+// boxes 0..3 = column block I (A operand), 4..7 = column block K (B operand), plus W_r of the 16 rows.  This warp's output
+// rows m' = 16 warp + 8 mt + g read source column 63 - m' = box 3 - warp, in-box column 15 - 8 mt - g; DMMA kk contracts the
+// rows {2t + (kk & 1) + 8 (kk >> 1)}: their (r & 7) in {0,2,4,6} (+1) spreads the 16 lanes of a half-warp over 16 bank pairs.
+template <bool DIAG>
+__device__ __forceinline__ void cf_gemm_chunk_tn(CfAcc& acc, const unsigned char* sA, const unsigned char* sB, const double* sW,
+                                                 int warp, int g, int t) {
+    const unsigned char* a_box = sA + (3 - warp) * 2048;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        const int kr = 8 * (kk >> 1) + 2 * t + (kk & 1);
+        const double wk = sW[kr];
+        const uint32_t row = (uint32_t)kr * 128u, x = (uint32_t)(kr & 7);
+        double a[2], b[8];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            const uint32_t mm = (uint32_t)(15 - 8 * mt - g);
+            a[mt] = wk * *reinterpret_cast<const double*>(a_box + row + (((mm >> 1) ^ x) << 4) + ((mm & 1) << 3));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+            if (!DIAG || nt <= 2 * warp + 1) {
+                const uint32_t mm = (uint32_t)(15 - 8 * (nt & 1) - g);
+                b[nt] = *reinterpret_cast<const double*>(sB + (3 - (nt >> 1)) * 2048 + row + (((mm >> 1) ^ x) << 4) + ((mm & 1) << 3));
+            }
 #pragma unroll
         for (int nt = 0; nt < 8; nt++)
             if (!DIAG || nt <= 2 * warp + 1) {
@@ -361,7 +403,10 @@ __device__ __forceinline__ void cf_potrf_regs(CfAcc& acc, double* dp, int warp, 
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tms, CholFlowParams p) {
+// SYRK: the source is the fused M' = P (I + L_K^T W L_K) P (two instantiations keep the plain path free of its registers)
+template <bool SYRK>
+__global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tms, const __grid_constant__ CUtensorMap tml,
+                                                                           CholFlowParams p) {
     extern __shared__ unsigned char cf_smem_raw[];
     const uint32_t raw = smem_u32(cf_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -376,7 +421,9 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
     const uint32_t bar_dp_full = bar_tq_empty + 16, bar_dp_empty = bar_dp_full + 8;
     volatile CfTask* tq = reinterpret_cast<volatile CfTask*>(ctrl + 16 * CF_STAGES + 48);       // 2 descriptors
     double* red = reinterpret_cast<double*>(ctrl + 16 * CF_STAGES + 48 + 2 * sizeof(CfTask));   // 4 partial log-dets
-    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= CF_CTRL_BYTES, "control block too small");
+    double* wst = reinterpret_cast<double*>(ctrl + 512);                                         // W_r of a TN stage: [stage][16]
+    const uint32_t wst_u = ctrl_u + 512;
+    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= 512 && 512 + CF_STAGES * 128 <= CF_CTRL_BYTES, "control block too small");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -423,7 +470,8 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
             if (type < 0) break;
             const int m = p.dst_idx ? p.dst_idx[b] : p.dst_m0 + b;
             const int row0 = m * p.np;
-            {
+            const int* prog = p.progress + (size_t)b * nb;
+            if (!SYRK) {
                 // source tile (i, k): four boxes in two stages.  No dependency: nobody writes this tile before this task does.
                 const int srow = (p.src_idx ? p.src_idx[b] : p.src_m0 + b) * p.np + i * TB;
                 for (int h = 0; h < 2; h++, it++) {
@@ -433,8 +481,24 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                     tma_load_2d(ring_u + s * 2 * CF_CHUNK_BYTES, &tms, k * TB + 32 * h, srow, bar_full + 8 * s);
                     tma_load_2d(ring_u + s * 2 * CF_CHUNK_BYTES + CF_CHUNK_BYTES, &tms, k * TB + 32 * h + 16, srow, bar_full + 8 * s);
                 }
+            } else {
+                // source tile of M' from L_K: 4 (k + 1) stages of 16 rows, column blocks I = nb-1-i (A) and K = nb-1-k (B)
+                const int I = nb - 1 - i, K = nb - 1 - k;
+                const int lrow = p.lk_idx[b] * p.np + K * TB;
+                const double* wsrc = p.w + (long long)b * p.w_bs + K * TB;
+                const bool dg = type != 0;
+                for (int c = 0; c < 4 * (k + 1); c++, it++) {
+                    const uint32_t s = it % CF_STAGES;
+                    mbar_wait(bar_empty + 8 * s, ((it / CF_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(bar_full + 8 * s, (dg ? CF_CHUNK_BYTES : 2 * CF_CHUNK_BYTES) + 128);
+                    const uint32_t st = ring_u + s * 2 * CF_CHUNK_BYTES;
+                    for (int j = 0; j < 4; j++) {
+                        tma_load_2d(st + CF_CHUNK_BYTES + j * 2048, &tml, K * TB + 16 * j, lrow + 16 * c, bar_full + 8 * s);
+                        if (!dg) tma_load_2d(st + j * 2048, &tml, I * TB + 16 * j, lrow + 16 * c, bar_full + 8 * s);
+                    }
+                    bulk_load_1d(wst_u + s * 128, wsrc + 16 * c, 128, bar_full + 8 * s);
+                }
             }
-            const int* prog = p.progress + (size_t)b * nb;
             if (type == 0) {
                 if (k > 0) {
                     while (cf_ld_relaxed(prog + i) < k) __nanosleep(p.spin_ns);
@@ -493,8 +557,8 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
         int* prog = p.progress + (size_t)b * nb;
         const bool diag = type != 0;
         CfAcc acc;
-        // ---- source tile A_ik (two stages of the ring)
-        {
+        if (!SYRK) {
+            // ---- source tile A_ik (two stages of the ring)
             const double* rs = sc ? sc + i * TB : nullptr;
             const double* cs = sc ? sc + k * TB : nullptr;
             const bool ident = diag && p.add_identity != 0;
@@ -509,6 +573,24 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
 #pragma unroll
                     for (int q = 0; q < 4; q++) dep |= (uint32_t)__double2hiint(acc[mt][4 * h + q][1]);
                 cf_release_stage(bar_empty + 8 * s, dep, p.zero, lane);
+            }
+        } else {
+            // ---- source tile of M' = P (I + L_K^T W L_K) P accumulated from L_K (never stored)
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+                    const bool dtile = diag && nt == 2 * warp + mt;
+                    acc[mt][nt][0] = (dtile && g == 2 * t) ? 1.0 : 0.0;
+                    acc[mt][nt][1] = (dtile && g == 2 * t + 1) ? 1.0 : 0.0;
+                }
+            for (int c = 0; c < 4 * (k + 1); c++, it++) {
+                const uint32_t s = it % CF_STAGES;
+                mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
+                const unsigned char* st = ring + s * 2 * CF_CHUNK_BYTES;
+                if (diag) cf_gemm_chunk_tn<true>(acc, st + CF_CHUNK_BYTES, st + CF_CHUNK_BYTES, wst + s * 16, warp, g, t);
+                else cf_gemm_chunk_tn<false>(acc, st, st + CF_CHUNK_BYTES, wst + s * 16, warp, g, t);
+                cf_release_stage(bar_empty + 8 * s, cf_acc_dep(acc), p.zero, lane);
             }
         }
         if (!diag) {

@@ -25,17 +25,18 @@ inline PFN_apm_encodeTiled tmap_encode_fn() {
 }
 
 // 2-D view of `nmat` stacked row-major fp64 matrices [nmat][np][np]: dim0 = column, dim1 = stacked row (m * np + r).
-// Box = 16 columns (one 128-byte swizzle row) x 64 rows, SWIZZLE_128B: the operand stages of k_chol_flow.
-inline bool make_matrix_tmap(CUtensorMap* out, const double* base, int np, long long nmat) {
+// Box = 16 columns (one 128-byte swizzle row) x box_rows rows, SWIZZLE_128B: the operand stages of k_chol_flow (64 rows: row-major
+// operands with k contiguous; 16 rows: k-major 16x16 boxes of L_K for the fused M' = I + L_K^T W L_K source).
+inline bool make_matrix_tmap(CUtensorMap* out, const double* base, int np, long long nmat, int box_rows = 64) {
     PFN_apm_encodeTiled enc = tmap_encode_fn();
     if (!enc) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)np, (cuuint64_t)np * (cuuint64_t)nmat};
     const cuuint64_t strides[1] = {(cuuint64_t)np * sizeof(double)};
-    const cuuint32_t box[2] = {16, 64};
+    const cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-               getenv("APM_TMAP_NOPROMO") ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

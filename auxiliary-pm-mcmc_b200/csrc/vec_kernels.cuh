@@ -521,18 +521,6 @@ __global__ void k_newton_init(int* active, int* mask_b, int* mask_m, int* done_m
     if (b == 0) { n_active[0] = B; n_active[1] = 0; n_active[2] = 0; }
 }
 
-// *out += number of chains with status == 0 inside mask (null: all) -- work accounting of the masked launches
-__global__ void k_count_mask(const int* mask, const int* status, int B, unsigned long long* out) {
-    __shared__ int cnt;
-    if (threadIdx.x == 0) cnt = 0;
-    __syncthreads();
-    int c = 0;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) c += (status[b] == 0) && (!mask || mask[b]);
-    if (c) atomicAdd(&cnt, c);
-    __syncthreads();
-    if (threadIdx.x == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
-}
-
 // diff = mean((fnew - f)^2); f <- fnew; iteration bookkeeping (lpa.py:96-102)
 __global__ void __launch_bounds__(256) k_newton_finish(NewtonVecs nv) {
     __shared__ double red[8];

@@ -548,11 +548,11 @@ def run_gpu_arm(args):
         flops = {   # algorithmic flops per kernel family over the roofline pass (this rank)
             # chain-Choleskys actually factored: chol(K), chol(B) per B-space Newton round, chol(M') -- the hybrid Newton
             # round makes chol(M') the last iteration's factorisation, so most chains run I + 1, not I + 2 of them
-            'k_chol': chol_units * n3 / 3.,
+            # ... and the M' = I + L_K^T W L_K builds (n^3/3 each) that k_chol_flow<true> accumulates inside the factorisation
+            'k_chol': (chol_units + syrk_units) * n3 / 3.,
             # factored covariance: chol(C) itself is never formed (factored cache), so the TRSM family is
             # only the n^2 N solve of the importance-sampling tail
             'k_trsm_rows': chains_done * n2 * N,
-            'k_syrk_sub': syrk_units * n3 / 3.,                        # M' = I + L_K^T W L_K builds executed (k_syrk_lk)
             'k_gemm_tri': chains_done * n2 * N,
         }
         hbm_bytes = {  # algorithmic bytes of the bandwidth-bound families over the roofline pass

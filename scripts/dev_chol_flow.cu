@@ -58,10 +58,13 @@ int main(int argc, char** argv) {
     for (auto& v : hX) { double s = 0; for (int q = 0; q < 12; q++) s += rand() / (double)RAND_MAX; v = s - 6.0; }
     for (int b = 0; b < B; b++) { hpar[2 * b] = exp(0.5 + 0.3 * (rand() / (double)RAND_MAX - 0.5)); hpar[2 * b + 1] = 2.0 * exp(0.3 * (rand() / (double)RAND_MAX - 0.5)); }
     for (auto& v : hscale) v = 0.3 + 0.6 * rand() / (double)RAND_MAX;
-    double *dX, *dpar, *dK, *dL0, *dL1, *dscale, *dinv0, *dinv1, *dld0, *dld1, *ddp;
+    double *dX, *dpar, *dK, *dL0, *dL1, *dLK, *dscale, *dinv0, *dinv1, *dld0, *dld1, *ddp;
+    int* dident;
     int *dstatus, *dactive, *dcounter, *dprogress, *dskip;
     CK(cudaMalloc(&dX, hX.size() * 8)); CK(cudaMalloc(&dpar, hpar.size() * 8)); CK(cudaMalloc(&dscale, hscale.size() * 8));
-    CK(cudaMalloc(&dK, B * mat * 8)); CK(cudaMalloc(&dL0, B * mat * 8)); CK(cudaMalloc(&dL1, B * mat * 8));
+    CK(cudaMalloc(&dK, B * mat * 8)); CK(cudaMalloc(&dL0, B * mat * 8)); CK(cudaMalloc(&dL1, B * mat * 8)); CK(cudaMalloc(&dLK, B * mat * 8));
+    CK(cudaMalloc(&dident, B * 4));
+    { std::vector<int> id(B); for (int b = 0; b < B; b++) id[b] = b; CK(cudaMemcpy(dident, id.data(), B * 4, cudaMemcpyHostToDevice)); }
     CK(cudaMalloc(&dinv0, (size_t)B * nb * 4096 * 8)); CK(cudaMalloc(&dinv1, (size_t)B * nb * 4096 * 8));
     CK(cudaMalloc(&dld0, (size_t)B * nb * 8)); CK(cudaMalloc(&dld1, (size_t)B * nb * 8));
     CK(cudaMalloc(&ddp, (size_t)B * nb * DP_BYTES));
@@ -74,21 +77,25 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
 
     CK(cudaFuncSetAttribute(k_chol_dataflow, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(k_chol_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_syrk_lk, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_chol_flow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_chol_flow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
     int occ_old = 0, occ_new = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_old, k_chol_dataflow, TILE_THREADS, TILE_SMEM_BYTES));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_new, k_chol_flow, CF_THREADS, CF_SMEM_BYTES));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_new, k_chol_flow<false>, CF_THREADS, CF_SMEM_BYTES));
     printf("occupancy: old %d CTAs/SM, new %d CTAs/SM, %d SMs\n", occ_old, occ_new, sms);
-    CUtensorMap tmK, tm1;
-    if (!make_matrix_tmap(&tm1, dL1, np, B) || !make_matrix_tmap(&tmK, dK, np, B)) { printf("tensor map creation failed\n"); return 2; }
+    CUtensorMap tmK, tm1, tmLK16;
+    if (!make_matrix_tmap(&tm1, dL1, np, B) || !make_matrix_tmap(&tmK, dK, np, B) || !make_matrix_tmap(&tmLK16, dLK, np, B, 16)) { printf("tensor map creation failed\n"); return 2; }
 
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     std::vector<double> h0(B * mat), h1(B * mat);
 
-    for (int variant = 0; variant < 3; variant++) {
+    for (int variant = 0; variant < 4; variant++) {
         // 0: chol(K) -> L;  1: chol(I + S K S) with inverse diagonal blocks;  2: as 1, in place, every 3rd chain inactive
-        const bool scaled = variant >= 1, inplace = variant == 2;
+        // 3: chol(M'), M' = P (I + L_K^T W L_K) P: round-1 k_syrk_lk + in-place Cholesky against the fused source of k_chol_flow
+        const bool syrk = variant == 3;
+        const bool scaled = variant == 1 || variant == 2, inplace = variant == 2;
         std::vector<int> hact(B, 1);
         if (variant == 2) for (int b = 0; b < B; b += 3) hact[b] = 0;
         CK(cudaMemcpy(dactive, hact.data(), B * 4, cudaMemcpyHostToDevice));
@@ -97,11 +104,11 @@ int main(int argc, char** argv) {
         // ---- round-1 kernel
         {
             CholParams p;
-            p.src = inplace ? dL0 : dK; p.src_bs = (long long)mat; p.lds = np; p.src_idx = nullptr;
+            p.src = (inplace || syrk) ? dL0 : dK; p.src_bs = (long long)mat; p.lds = np; p.src_idx = nullptr;
             p.dst = dL0; p.dst_bs = (long long)mat; p.ldd = np; p.dst_idx = nullptr;
             p.scale = scaled ? dscale : nullptr; p.scale_bs = np; p.add_identity = scaled;
             p.nb = nb; p.logdet_parts = dld0; p.logdet_stride = nb; p.logdet_idx = nullptr;
-            p.inv_out = scaled ? dinv0 : nullptr; p.inv_bs = (long long)nb * 4096;
+            p.inv_out = (scaled || syrk) ? dinv0 : nullptr; p.inv_bs = (long long)nb * 4096;
             p.status = dstatus; p.fail_code = 5; p.active = variant == 2 ? dactive : nullptr; p.nchains = B;
             p.sm_sem = nullptr; p.sem_limit = 0;
             CholFlow f;
@@ -112,6 +119,13 @@ int main(int argc, char** argv) {
                 if (inplace) CK(cudaMemcpy(dL0, dK, B * mat * 8, cudaMemcpyDeviceToDevice));
                 if (r == 1) CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(dstatus, 0, B * 4));
+                if (syrk) {
+                    SyrkLkParams sp;
+                    sp.LK = dLK; sp.lk_bs = (long long)mat; sp.ldk = np; sp.lk_idx = dident;
+                    sp.W = dscale; sp.w_bs = np; sp.M = dL0; sp.m_bs = (long long)mat; sp.ldm = np;
+                    sp.nb = nb; sp.ntiles = nb * (nb + 1) / 2; sp.status = dstatus; sp.mask = nullptr;
+                    k_syrk_lk<<<B * sp.ntiles, TILE_THREADS, TILE_SMEM_BYTES>>>(sp);
+                }
                 CK(cudaMemsetAsync(dcounter, 0, 4));
                 CK(cudaMemsetAsync(dprogress, 0, (size_t)B * nb * 4));
                 k_chol_skip_snapshot<<<(B + 255) / 256, 256>>>(dstatus, p.active, dskip, B);
@@ -125,11 +139,12 @@ int main(int argc, char** argv) {
         // ---- new kernel
         {
             CholFlowParams p;
-            p.src = inplace ? dL1 : dK; p.src_bs = (long long)mat; p.lds = np; p.src_idx = nullptr;
+            p.src = inplace ? dL1 : dK; p.src_bs = (long long)mat;
+            p.lk_idx = dident; p.w = dscale; p.w_bs = np; p.lds = np; p.src_idx = nullptr;
             p.dst = dL1; p.dst_bs = (long long)mat; p.ldd = np; p.dst_idx = nullptr; p.dst_m0 = 0; p.src_m0 = 0; p.zero = 0; p.np = np;
             p.scale = scaled ? dscale : nullptr; p.scale_bs = np; p.add_identity = scaled;
             p.nb = nb; p.logdet_parts = dld1; p.logdet_stride = nb; p.logdet_idx = nullptr;
-            p.inv_out = scaled ? dinv1 : nullptr; p.inv_bs = (long long)nb * 4096;
+            p.inv_out = (scaled || syrk) ? dinv1 : nullptr; p.inv_bs = (long long)nb * 4096;
             p.status = dstatus; p.fail_code = 5; p.active = variant == 2 ? dactive : nullptr; p.nchains = B;
             p.counter = dcounter + 4; p.progress = dprogress; p.list = dskip; p.diagpack = ddp;
             p.spin_ns = 64;
@@ -140,8 +155,9 @@ int main(int argc, char** argv) {
                 if (inplace) CK(cudaMemcpy(dL1, dK, B * mat * 8, cudaMemcpyDeviceToDevice));
                 if (r == 1) CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(dstatus, 0, B * 4));
-                k_chol_flow_init<<<(B * nb + 255) / 256, 256>>>(p.counter, p.progress, p.list, dstatus, p.active, B, nb, nullptr);
-                k_chol_flow<<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, inplace ? tm1 : tmK, p);
+                k_chol_flow_init<<<(B * nb + 255) / 256, 256>>>(p.counter, p.progress, p.list, dstatus, p.active, B, nb, nullptr, nullptr);
+                if (syrk) k_chol_flow<true><<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, tmK, tmLK16, p);
+                else k_chol_flow<false><<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, inplace ? tm1 : tmK, tmLK16, p);
                 if (inplace && r >= 1) break;
             }
             CK(cudaEventRecord(e1));
@@ -159,6 +175,7 @@ int main(int argc, char** argv) {
             }
 #endif
         }
+        if (variant == 0) CK(cudaMemcpy(dLK, dL1, B * mat * 8, cudaMemcpyDeviceToDevice));   // L_K of the M' variant
         CK(cudaMemcpy(h0.data(), dL0, B * mat * 8, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(h1.data(), dL1, B * mat * 8, cudaMemcpyDeviceToHost));
         if (variant == 2)   // inactive chains keep the copied source: identical in both
@@ -194,8 +211,9 @@ int main(int argc, char** argv) {
             for (int i = 0; i < np; i++) for (int j = i + 1; j < (i / 64 + 1) * 64; j++) upper = std::max(upper, fabs(h1[c * mat + (size_t)i * np + j]));
         }
         // host reconstruction of chain 1: || L L^T - A ||_max / ||A||_max
-        double rec = 0, an = 0;
-        {
+        double rec = 0, an = 1;
+        if (!syrk) {
+            an = 0;
             const int c = 1 % B;
             std::vector<double> hK(mat);
             CK(cudaMemcpy(hK.data(), dK + c * mat, mat * 8, cudaMemcpyDeviceToHost));
@@ -216,7 +234,7 @@ int main(int argc, char** argv) {
         double ldd = 0;
         for (int c = 0; c < B; c++) { if (variant == 2 && c % 3 == 0) continue; for (int k = 0; k < nb; k++) ldd = std::max(ldd, fabs(l0[c * nb + k] - l1[c * nb + k])); }
         double invd = 0, invref = 0;
-        if (scaled) {
+        if (scaled || syrk) {
             std::vector<double> i0((size_t)B * nb * 4096), i1((size_t)B * nb * 4096);
             CK(cudaMemcpy(i0.data(), dinv0, i0.size() * 8, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(i1.data(), dinv1, i1.size() * 8, cudaMemcpyDeviceToHost));
@@ -226,7 +244,7 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(hst.data(), dstatus, B * 4, cudaMemcpyDeviceToHost));
         int nfail = 0; for (int v : hst) nfail += v != 0;
         const double nact = variant == 2 ? B - (B + 2) / 3 : B;
-        const double gflop = nact * (double)np * np * np / 3.0 / 1e9;
+        const double gflop = (syrk ? 2.0 : 1.0) * nact * (double)np * np * np / 3.0 / 1e9;
         printf("variant %d: new vs old max rel %.3e (abs %.3e)  upper %.1e  recon %.3e  logdet diff %.2e  inv diff %.2e (max %.2e)  failed %d\n",
                variant, rel, wabs, upper, rec / an, ldd, invd, invref, nfail);
         printf("           old %.3f ms (%.2f TFLOP/s)   new %.3f ms (%.2f TFLOP/s)   speed-up %.2fx\n", ms_old, gflop / ms_old, ms_new,

@@ -1,5 +1,5 @@
-// r1_chol_engine.cuh -- DEV ONLY (not part of the product): the round-1 cp.async / mma.sync dataflow Cholesky, kept as the
-// A/B baseline of scripts/dev_chol_flow.cu (profiles/: "old" timings).  The product uses csrc/chol_flow.cuh.
+// r1_chol_engine.cuh -- DEV ONLY (not part of the product): the round-1 cp.async / mma.sync dataflow Cholesky and the separate
+// M' = I + L_K^T W L_K SYRK kernel (k_syrk_lk; the product accumulates M' inside k_chol_flow<true>), kept as the A/B baseline of scripts/dev_chol_flow.cu (profiles/: "old" timings).  The product uses csrc/chol_flow.cuh.
 #pragma once
 #include "../auxiliary-pm-mcmc_b200/csrc/tile_engine.cuh"
 #define APM_SKEL 0
@@ -421,6 +421,121 @@ __global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_chol_dataflow(CholPa
 __global__ void k_chol_skip_snapshot(const int* status, const int* active, int* skip, int n) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < n) skip[b] = (status[b] != 0) || (active && !active[b]);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// M' straight from L_K ("TN" operands): M = I + L_K^T W L_K is a sum of outer products of ROWS of the row-major L_K,
+//   M[i][j] = [i == j] + sum_{k >= max(i,j)} W_k L_K[k][i] L_K[k][j],
+// so the k-chunks are staged k-major ([KC][64] per operand, row stride 68: the fragment reads a = S[k = t][m = g] are two-way
+// = minimal for 8-byte accesses) and W_k scales the A fragment.  No transposed, scaled copy Y' of L_K (k_make_Y) and no
+// second read of it.  The CTA of lower tile (i', j') of M' = P M P computes tile (I, J) = (nb-1-i', nb-1-j') of M (I <= J: its
+// k-range starts at block J) and stores it index-reversed.
+// ------------------------------------------------------------------------------------------------
+constexpr int TNS = 68;
+constexpr int TN_STAGE_DOUBLES = 2 * KC * TNS + KC;   // A chunk, B chunk, W chunk
+static_assert(STAGES * TN_STAGE_DOUBLES * 8 <= TILE_SMEM_BYTES, "k-major stages exceed the shared memory of a CTA");
+
+__device__ __forceinline__ void gemm_tn_load_stage(double* st, const double* __restrict__ A, const double* __restrict__ Bm, int ld,
+                                                   const double* __restrict__ w, int k0, int tid) {
+    // 16 rows x 32 16-byte segments per operand = 512 segments, 4 per thread
+#pragma unroll
+    for (int q = 0; q < (KC * 32) / TILE_THREADS; q++) {
+        const int seg = tid + q * TILE_THREADS;
+        const int r = seg >> 5, c = (seg & 31) * 2;
+        cp_async16(st + r * TNS + c, A + (size_t)(k0 + r) * ld + c);
+        cp_async16(st + KC * TNS + r * TNS + c, Bm + (size_t)(k0 + r) * ld + c);
+    }
+    if (tid < KC / 2) cp_async16(st + 2 * KC * TNS + tid * 2, w + k0 + tid * 2);
+}
+
+// acc += sum_{k < kdepth} w[k] * A[k][0..63] (x) Bm[k][0..63]   (A, Bm: pointers to row k = 0 of the two column blocks)
+__device__ __forceinline__ void gemm_tn_64x64_w(Acc& acc, const double* __restrict__ A, const double* __restrict__ Bm, int ld,
+                                                const double* __restrict__ w, int kdepth, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int nchunks = kdepth / KC;
+    if (nchunks == 0) return;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nchunks) gemm_tn_load_stage(smem + s * TN_STAGE_DOUBLES, A, Bm, ld, w, s * KC, tid);
+        cp_async_commit();
+    }
+    for (int kc = 0; kc < nchunks; kc++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nk = kc + STAGES - 1;
+            if (nk < nchunks) gemm_tn_load_stage(smem + (nk % STAGES) * TN_STAGE_DOUBLES, A, Bm, ld, w, nk * KC, tid);
+            cp_async_commit();
+        }
+        const double* st = smem + (kc % STAGES) * TN_STAGE_DOUBLES;
+        const double* a_s = st + t * TNS + wm * 32 + g;
+        const double* b_s = st + KC * TNS + t * TNS + wn * 32 + g;
+        const double* w_s = st + 2 * KC * TNS + t;
+#pragma unroll
+        for (int kk = 0; kk < KC / 4; kk++) {
+            const double wk = w_s[kk * 4];
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = a_s[kk * 4 * TNS + mi * 8] * wk;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) b[ni] = b_s[kk * 4 * TNS + ni * 8];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc.v[mi][ni][0], acc.v[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+}
+
+struct SyrkLkParams {
+    const double* LK; long long lk_bs; int ldk; const int* lk_idx;   // chol(K) (slot)
+    const double* W; long long w_bs;                                  // Newton / EP weights, [chain][np] (0 in the padding)
+    double* M; long long m_bs; int ldm;                               // M' (lower tiles, full diagonal tiles)
+    int nb; int ntiles;
+    const int* status; const int* mask;
+};
+
+__global__ void __launch_bounds__(TILE_THREADS, MIN_CTAS) k_syrk_lk(SyrkLkParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.x / p.ntiles;
+    const int tix = p.ntiles - 1 - (int)(blockIdx.x % p.ntiles);   // deepest tiles first
+    if (p.status[b] != 0 || (p.mask && !p.mask[b])) return;
+    int i = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= tix) i++;
+    while (i * (i + 1) / 2 > tix) i--;
+    const int j = tix - i * (i + 1) / 2;                           // lower tile (i, j) of M'
+    const int I = p.nb - 1 - i, J = p.nb - 1 - j;                  // tile (I, J) of M, I <= J
+    const double* L = p.LK + chain_index(p.lk_idx, b) * p.lk_bs;
+    const double* W = p.W + (long long)b * p.w_bs;
+    double* M = p.M + (long long)b * p.m_bs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3, wm = warp >> 1, wn = warp & 1;
+    Acc acc;
+    acc.zero();
+    if (i == j && wm == wn) {
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {   // identity on the diagonal of the 32x32 warp block
+            if (g == 2 * t) acc.v[mi][mi][0] = 1.0;
+            if (g == 2 * t + 1) acc.v[mi][mi][1] = 1.0;
+        }
+    }
+    const int kstart = J * TB;
+    gemm_tn_64x64_w(acc, L + (size_t)kstart * p.ldk + I * TB, L + (size_t)kstart * p.ldk + J * TB, p.ldk, W + kstart,
+                    (p.nb - J) * TB, smem);
+    // M'[i*64 + 63 - m][j*64 + 63 - n] = M[I*64 + m][J*64 + n]
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int m = wm * 32 + mi * 8 + g, n = wn * 32 + ni * 8 + 2 * t;
+            *reinterpret_cast<double2*>(M + (size_t)(i * TB + 63 - m) * p.ldm + j * TB + 62 - n) =
+                make_double2(acc.v[mi][ni][1], acc.v[mi][ni][0]);
+        }
 }
 
 
