@@ -15,6 +15,7 @@ EXPORTS = [
     'apm_set_overlap', 'apm_set_newton', 'apm_set_approximation', 'apm_ep', 'apm_get_info', 'apm_kernel_build', 'apm_kernel_grad', 'apm_laplace', 'apm_estimate_full',
     'apm_estimate_cached', 'apm_estimate_cached_weights', 'apm_laplace_lml', 'apm_estimate_prior_mc',
     'apm_slot_export', 'apm_slot_import', 'apm_slot_factor', 'apm_slot_copy', 'apm_profile', 'apm_profile_read', 'apm_launch_count', 'apm_work_count', 'apm_create_companion', 'apm_dev_chol_bench', 'apm_measure_fp64_peak',
+    'apm_sampler_create', 'apm_sampler_run', 'apm_sampler_stats', 'apm_sampler_destroy',
 ]
 
 KERNEL_ISO, KERNEL_ARD = 0, 1
@@ -70,6 +71,10 @@ def lib():
     L.apm_work_count.argtypes = [vp, ct.POINTER(ct.c_int64), ct.c_int]
     L.apm_dev_chol_bench.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, dp]
     L.apm_measure_fp64_peak.argtypes = [ct.c_int, ct.c_int, dp]
+    L.apm_sampler_create.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, vp, vp, vp, ct.c_double, ct.c_int, ct.POINTER(vp)]
+    L.apm_sampler_run.argtypes = [vp, vp, ct.c_int, vp, vp]
+    L.apm_sampler_stats.argtypes = [vp, vp]
+    L.apm_sampler_destroy.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is ct.c_int and name not in ('apm_version', 'apm_last_error', 'apm_launch_count'):
@@ -395,3 +400,53 @@ class Engine(object):
     def slot_copy(self, src, dst):
         s, d = i32(np.atleast_1d(src)), i32(np.atleast_1d(dst))
         check(self._L.apm_slot_copy(self._h, _ptr(s), _ptr(d), s.shape[0]))
+
+
+METHODS = {'mi+mh': 0, 'ess+mh': 1, 'mi+rdss': 2, 'ess+rdss': 3, 'pmmh': 4}
+
+
+class NativeSampler(object):
+    """apm_sampler of include/apm_b200.h: B chains of a composite sampler advanced natively on `engine` (device RNG,
+    host C++ chain state machines).  prior_ab: (n_theta, 2) shape / rate of the log-Gamma prior of every theta component."""
+
+    def __init__(self, engine, method, seeds, n_imp, prior_ab, prop_scales=None, slice_width=1., max_slice_iters=1000):
+        self._L = lib()
+        self.engine = engine
+        self.B = len(seeds)
+        self.P = engine.n_theta
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        prior_ab = f64(prior_ab)
+        if prior_ab.shape != (self.P, 2):
+            raise ValueError('prior_ab must be (n_theta, 2)')
+        ps = None if prop_scales is None else f64(np.broadcast_to(np.asarray(prop_scales, dtype=np.float64), (self.P,)))
+        h = ct.c_void_p()
+        check(self._L.apm_sampler_create(engine._h, METHODS[method], self.B, int(n_imp), _ptr(seeds), _ptr(prior_ab),
+                                         None if ps is None else _ptr(ps), float(slice_width), int(max_slice_iters),
+                                         ct.byref(h)))
+        self._h = h
+
+    def run(self, theta_init, n_sample):
+        theta_init = f64(theta_init)
+        if theta_init.shape != (self.B, self.P):
+            raise ValueError('theta_init must be (n_chains, n_theta)')
+        thetas = np.empty((self.B, int(n_sample), self.P))
+        counts = np.zeros((self.B, 6), dtype=np.int64)
+        check(self._L.apm_sampler_run(self._h, _ptr(theta_init), int(n_sample), _ptr(thetas), _ptr(counts)))
+        return thetas, counts
+
+    def stats(self):
+        out = np.zeros(8)
+        check(self._L.apm_sampler_stats(self._h, _ptr(out)))
+        return dict(full_calls=int(out[0]), full_chains=int(out[1]), cached_calls=int(out[2]), cached_chains=int(out[3]),
+                    t_flight=float(out[4]), t_total=float(out[5]), rounds=int(out[6]))
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.apm_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

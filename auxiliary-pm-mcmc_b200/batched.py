@@ -16,6 +16,12 @@ drawn on the host) chain c reproduces the single-chain / reference trace for the
 how many chains share the batch or how they are sharded over GPUs.  `rng='device'` keeps u in HBM
 (torch CUDA generator, not stream-identical to numpy) for throughput runs.
 
+`rng='native'` hands the whole run to the native sampler of the C ABI (`apm_sampler_*`, csrc/sampler.cuh): the same chain
+logic as a C++ state machine per chain, Philox normals generated on the device straight into the estimator's layout, the
+asynchronous FULL / CACHED schedule without the interpreter.  `rng='philox'` runs THIS module's generators on the same
+Philox streams (apm_b200.philox, numpy on the host), so the native sampler can be checked draw for draw against the
+chain logic that is pinned to the reference.
+
 Chain groups: given a LIST of backends (one engine context each) the chains are split into that many contiguous
 groups, each scheduled by its own host thread on its own CUDA stream.  A FULL round of one group (GPU-bound, the GIL
 is released inside the C-ABI call) then overlaps the Python scheduling, the torch tensor work and the cheap CACHED
@@ -63,10 +69,14 @@ class _Chain(object):
     """State of one chain + its generator.  `local` = position inside its chain group (slot numbering of the
     group's engine context)."""
 
-    def __init__(self, index, seed, theta_init, local=None):
+    def __init__(self, index, seed, theta_init, local=None, philox_streams=False):
         self.index = index
         local = index if local is None else local
-        self.prng = np.random.RandomState(seed)
+        if philox_streams:
+            from .philox import PhiloxStream
+            self.prng = PhiloxStream(seed)
+        else:
+            self.prng = np.random.RandomState(seed)
         self.theta = np.array(theta_init, dtype=np.float64)
         self.u = None
         self.log_f = None
@@ -94,8 +104,8 @@ class BatchedAPMSampler(object):
                  async_batch_frac=0.5):
         if method not in ('mi+mh', 'ess+mh', 'mi+rdss', 'ess+rdss', 'pmmh'):
             raise ValueError('unknown method %r' % method)
-        if rng not in ('parity', 'device'):
-            raise ValueError("rng must be 'parity' or 'device'")
+        if rng not in ('parity', 'device', 'philox', 'native'):
+            raise ValueError("rng must be 'parity', 'philox', 'device' or 'native'")
         self.backends = list(backend) if isinstance(backend, (list, tuple)) else [backend]
         self.backend = self.backends[0]
         self.n, self.N, self.P = int(n_data), int(n_imp), int(n_theta)
@@ -128,12 +138,12 @@ class BatchedAPMSampler(object):
     # ---- random draws -----------------------------------------------------------------------------
     def _draw_u(self, ch):
         """u_sampler(): n*N standard normals, row-major (nb cell 12: prng.normal(size=(n, N)))."""
-        if self.rng == 'parity':
+        if self.rng in ('parity', 'philox'):
             return ch.prng.normal(size=(self.n, self.N))
         return self._torch.randn(self.n, self.N, dtype=self._torch.float64, device=self.device, generator=self._gen)
 
     def _ellipse(self, u, v, phi):
-        if self.rng == 'parity':
+        if self.rng in ('parity', 'philox'):
             return u * np.cos(phi) + v * np.sin(phi)              # mu.py:382
         return u * float(np.cos(phi)) + v * float(np.sin(phi))
 
@@ -606,19 +616,24 @@ class BatchedAPMSampler(object):
         (B, n_sample, P), n_reject (B, 2), n_cubic_ops (B,), n_full (B,), n_cached (B,), failed (B,) status
         codes, rounds)."""
         B = self.B
+        if self.rng == 'native':
+            return self._get_samples_native(theta_init, n_sample, theta_init_sampler)
         G = max(1, min(len(self.backends), B))
         bounds = [(g * B) // G for g in range(G + 1)]            # contiguous chain groups, one per backend
         local = {}
         for g in range(G):
             for c in range(bounds[g], bounds[g + 1]):
                 local[c] = c - bounds[g]
+        px = self.rng == 'philox'
+        if px and theta_init is None:
+            raise ValueError("rng='philox' needs explicit theta_init (the Philox streams have no Gamma sampler)")
         if theta_init is None:
-            chains = [_Chain(c, self.seeds[c], np.zeros(self.P), local[c]) for c in range(B)]
+            chains = [_Chain(c, self.seeds[c], np.zeros(self.P), local[c], px) for c in range(B)]
             for ch in chains:
                 ch.theta = np.array(theta_init_sampler(ch.prng), dtype=np.float64)
         else:
             theta_init = np.asarray(theta_init, dtype=np.float64)
-            chains = [_Chain(c, self.seeds[c], theta_init[c], local[c]) for c in range(B)]
+            chains = [_Chain(c, self.seeds[c], theta_init[c], local[c], px) for c in range(B)]
         traces = np.full((B, n_sample, self.P), np.nan)
         schedule = self._schedule_parity
         if self.rng == 'device':
@@ -631,6 +646,26 @@ class BatchedAPMSampler(object):
                     n_cubic_ops=np.array([ch.n_cubic_ops for ch in chains]),
                     n_full=np.array([ch.n_full for ch in chains]), n_cached=np.array([ch.n_cached for ch in chains]),
                     failed=np.array([0 if ch.failed is None else ch.failed for ch in chains]), rounds=rounds)
+
+
+    def _get_samples_native(self, theta_init, n_sample, theta_init_sampler=None):
+        """The whole run inside the C ABI (apm_sampler_run).  The log prior must be the notebooks' log-Gamma prior
+        (`make_log_prior`: its hyper-parameters are handed to the native code)."""
+        from . import _capi
+        prior_ab = getattr(self.log_prior, 'prior_ab', None)
+        if prior_ab is None:
+            raise ValueError("rng='native' needs a log prior made by make_log_prior (log-Gamma hyper-parameters)")
+        if theta_init is None:
+            raise ValueError("rng='native' needs explicit theta_init (the Philox streams have no Gamma sampler)")
+        ns = getattr(self, '_native', None)
+        if ns is None:
+            ns = _capi.NativeSampler(self.backend.engine, self.method, self.seeds, self.N, prior_ab, self.prop_scales,
+                                     self.slice_width, self.max_slice_iters)
+            self._native = ns
+        thetas, counts = ns.run(np.asarray(theta_init, dtype=np.float64), n_sample)
+        self.async_stats = ns.stats()
+        return dict(thetas=thetas, n_reject=counts[:, 0:2].copy(), n_cubic_ops=counts[:, 2].copy(), n_full=counts[:, 3].copy(),
+                    n_cached=counts[:, 4].copy(), failed=counts[:, 5].copy(), rounds=self.async_stats['rounds'])
 
 
 def make_log_prior(D, ard):
@@ -650,4 +685,6 @@ def make_log_prior(D, ard):
             v = v + utils.log_gamma_log_pdf(thetas[:, k], p['a_tau'], p['b_tau'])
         return v
     log_prior.many = many
+    # shape / rate per theta component, for the native sampler
+    log_prior.prior_ab = np.array([[p['a_sigma'], p['b_sigma']]] + [[p['a_tau'], p['b_tau']]] * (D if ard else 1))
     return log_prior

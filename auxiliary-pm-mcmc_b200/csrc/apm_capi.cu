@@ -1259,11 +1259,22 @@ static int full_front(apm_ctx* c, const double* theta, int B, const int* slots, 
     return rc;
 }
 
+// ut_ready: the transposed auxiliary normals of chains 0..B-1 already sit in c->dUT (written there by the native sampler,
+// sampler.cuh); u is ignored
+static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
+                              const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status, bool ut_ready);
+
 extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
                                  const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status) {
+    if (!u) return APM_ERR_INVALID;
+    return estimate_full_impl(c, theta, u, u_on_device, N, B, slots, logml_out, cubic_ops_out, chain_status, false);
+}
+
+static int estimate_full_impl(apm_ctx* c, const double* theta, const double* u, int u_on_device, int N, int B,
+                              const int* slots, double* logml_out, int* cubic_ops_out, int* chain_status, bool ut_ready) {
     APM_TRY(not_companion(c));
     APM_TRY(check_B(c, B));
-    if (!theta || !u || !slots || !logml_out) return APM_ERR_INVALID;
+    if (!theta || !slots || !logml_out) return APM_ERR_INVALID;
     cancel_prefetch(c);
     const bool overlap = c->overlap_chol_k;
     APM_TRY(full_front(c, theta, B, slots, overlap));
@@ -1271,14 +1282,14 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
         set_err("N (importance samples) out of range for this context");
         return APM_ERR_INVALID;
     }
-    c->pend_u = u_on_device ? nullptr : u;
+    c->pend_u = (u_on_device || ut_ready) ? nullptr : u;
     c->pend_N = N; c->pend_B = B;
     int rc_mode = (c->approx == 1) ? run_ep(c, B)                               // extension: EP behind post_approx_func
                                    : run_newton(c, B, c->dSlotsA, overlap);     // estimators.py:207 -> lpa.py:81-102
     c->pend_u = nullptr;
     APM_TRY(rc_mode);
     // u is only needed by the importance-sampling tail: a host buffer has had the whole mode search to cross the bus
-    APM_TRY(stage_u(c, u, u_on_device, N, B));
+    if (!ut_ready) APM_TRY(stage_u(c, u, u_on_device, N, B));
     if (c->factored_cov) {
         // chol(C) = L_K U^-T straight from chol(K) and W (lpa.py:111-112 + estimators.py:209 without forming C)
         if (overlap) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
@@ -1307,9 +1318,13 @@ extern "C" int apm_estimate_full(apm_ctx* c, const double* theta, const double* 
 }
 
 static int cached_common(apm_ctx* c, const int* slots, const double* u, int u_on_device, int N, int B, double* logml_out,
-                         double* logw_out, int* chain_status) {
+                         double* logw_out, int* chain_status, bool ut_ready = false) {
     APM_TRY(check_B(c, B));
-    if (!slots || !u) return APM_ERR_INVALID;
+    if (!slots || (!u && !ut_ready)) return APM_ERR_INVALID;
+    if (N <= 0 || N > c->maxN) {
+        set_err("N (importance samples) out of range for this context");
+        return APM_ERR_INVALID;
+    }
     cancel_prefetch(c);
     APM_TRY(reset_status(c, B));
     APM_TRY(upload_slots(c, slots, B, c->dSlotsA, true));
@@ -1327,7 +1342,7 @@ static int cached_common(apm_ctx* c, const int* slots, const double* u, int u_on
         for (int b = 0; b < B; b++) APM_TRY(slot_make_explicit(c, slots[b]));
         n_fact = 0;
     }
-    APM_TRY(stage_u(c, u, u_on_device, N, B));
+    if (!ut_ready) APM_TRY(stage_u(c, u, u_on_device, N, B));
     APM_TRY(run_is_tail(c, N, B, c->dSlotsA, c->dOut, logw_out ? c->dLogw : nullptr, 0, n_fact == B));
     if (logw_out) CU_TRY(cudaMemcpyAsync(logw_out, c->dLogw, sizeof(double) * (size_t)B * N, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaMemsetAsync(c->dIters, 0, sizeof(int) * B, c->stream));
@@ -1666,3 +1681,5 @@ extern "C" int apm_measure_fp64_peak(int device, int kind, double* tflops) {
     *tflops = best;
     return APM_OK;
 }
+
+#include "sampler.cuh"

@@ -152,11 +152,9 @@ int apm_ep(apm_ctx* ctx, const double* K, int K_on_device, int B, int calc_cov, 
  *   logml_out HOST [B]; cubic_ops_out HOST [B] = newton iters + 1 + 2 (est.py:217), may be NULL;
  *   chain_status HOST [B].
  * Chains with a non-zero status get logml = NaN and leave their slot invalid.
- * Execution: batches of >= 128 chains are split into up to 8 contiguous chain groups ("lanes"), each driven by
- * its own host thread on its own CUDA streams, so the latency-bound Newton kernels, host round trips and H2D
- * copies of one group overlap the tensor-pipe kernels of the others; the call returns when all lanes are done.
- * Results do not depend on the split (bit-identical to the single-lane path).  Environment overrides:
- * APM_LANES (1 disables), APM_LANE_MIN_CHAINS, APM_LANE_MIN_BATCH.
+ * Execution: one host thread; the Newton rounds are queued under device-side masks (one host round trip per call on
+ * typical data), chol(K) and the upload of a host u overlap the mode search on auxiliary streams.  A chain's result
+ * does not depend on the other chains of the batch.
  */
 int apm_estimate_full(apm_ctx* ctx, const double* theta, const double* u, int u_on_device, int N,
                       int B, const int* slots, double* logml_out, int* cubic_ops_out,
@@ -231,6 +229,35 @@ int apm_work_count(apm_ctx* ctx, int64_t* out, int reset);
 /* Tuning aid: average milliseconds of one batched Cholesky of the context's current K matrices (B chains,
  * after apm_kernel_build) into slots 0..B-1.  mode 0 = default path, 1 = per-step launches. */
 int apm_dev_chol_bench(apm_ctx* ctx, int B, int reps, int mode, double* ms_out);
+
+/*
+ * Native batched sampler -- the lock-step drivers of SURVEY.md section 8 f-1: B independent chains of one of the
+ * reference's composite samplers (auxpm/samplers.py: APM MI+MH :346-418, APM ESS+MH :515-587, APM MI+RDSS :658-730,
+ * APM ESS+RDSS :800-841, PM-MH :223-262; updates of auxpm/mcmc_updates.py :117-160, :284-303, :373-400, :481-519) advanced
+ * together on the engine `ctx`.  The auxiliary normals are generated on the device (Philox4x32-10 keyed by the chain's
+ * seed) directly in the layout the estimator reads and never leave it; proposals, the ellipse u cos(phi) + v sin(phi)
+ * and the accepted state are device buffers; the per-chain scalars (theta, brackets, accept / reject) are host state.
+ * The log prior added to every estimate is the notebooks' log-Gamma prior (gpdemo/utils.py:39-59, nb cell 12):
+ * prior_ab HOST [n_theta][2] = shape a and rate b of every theta component.
+ *   method       0 MI+MH, 1 ESS+MH, 2 MI+RDSS, 3 ESS+RDSS, 4 PM-MH
+ *   seeds        HOST [n_chains]: a chain's trace depends on its seed only (not on the batch, the schedule or the GPU count)
+ *   prop_scales  HOST [n_theta] random-walk scales of the MH theta-update (methods 0, 1, 4), else NULL
+ *   slice_width  w of the random-direction slice update (methods 2, 3; max_steps_out = 0 as in the notebooks)
+ * ctx must have max_chains >= n_chains, n_slots >= 2 n_chains (current / proposed cache per chain) and max_nimp >= n_imp;
+ * it must not be used by other calls while apm_sampler_run is running.
+ */
+typedef struct apm_sampler apm_sampler;
+int apm_sampler_create(apm_ctx* ctx, int method, int n_chains, int n_imp, const uint64_t* seeds, const double* prior_ab,
+                       const double* prop_scales, double slice_width, int max_slice_iters, apm_sampler** out);
+/* n_sample states per chain (the first is theta_init, as get_samples of the reference returns them).
+ * theta_init HOST [n_chains][n_theta]; thetas_out HOST [n_chains][n_sample][n_theta] (NaN after a chain failed);
+ * counts_out HOST [n_chains][6]: rejected u-updates, rejected theta-updates, n_cubic_ops, FULL estimates, CACHED
+ * estimates, failure status (0 = ok, else the chain_status code that stopped the chain). */
+int apm_sampler_run(apm_sampler* s, const double* theta_init, int n_sample, double* thetas_out, int64_t* counts_out);
+/* Scheduling diagnostics of the last run: out8 = FULL calls, chains in them, CACHED calls, chains in them, seconds with a
+ * FULL call in flight, seconds in total, scheduler rounds, 0. */
+int apm_sampler_stats(apm_sampler* s, double* out8);
+int apm_sampler_destroy(apm_sampler* s);
 
 /* Micro-benchmarks used by bench.py to measure the fp64 roofline denominators on the box:
  * kind 0: DMMA m8n8k4 issue peak, 1: DFMA peak.  Returns TFLOP/s in *tflops. */
