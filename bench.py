@@ -362,20 +362,33 @@ def _estimator_rates(D_, eng, n, D, N, B, reps, seed, want_cached=True):
     return out
 
 
-def _sampler_rate(D_, eng, n, D, N, B, method, iters, seed, rank):
+SAMPLER_NOTE = {
+    'native': 'native sampler of the C ABI (apm_sampler_run, csrc/sampler.cuh): C++ chain state machines, Philox normals and the '
+              'ellipse generated on the device in the estimator\'s layout, asynchronous FULL / CACHED schedule',
+    'device': 'Python generator scheduler (apm_b200.batched), torch device RNG, asynchronous FULL rounds (worker thread + companion '
+              'context for the CACHED rounds)'}
+
+
+def _sampler_rate(D_, eng, n, D, N, B, method, iters, seed, rank, rng='native', th0=None):
+    """chain-iterations/s of B lock-step chains per GPU on `eng`: host wall clock of one get_samples call between barriers (max
+    over ranks), which includes the scheduler and the drain of the last iterations."""
     from apm_b200 import batched, synth
     drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, method, batched.make_log_prior(D, True),
-                                    [seed + rank * B + c for c in range(B)], prop_scales=np.full(D + 1, 0.1), rng='device',
+                                    [seed + rank * B + c for c in range(B)], prop_scales=np.full(D + 1, 0.1), rng=rng,
                                     device=D_.dev, async_full=True)
-    th0 = synth.bulk_thetas(B, D, seed=seed)
+    if th0 is None:
+        th0 = synth.bulk_thetas(B, D, seed=seed)
     drv.get_samples(th0, 3)          # warm-up (allocations, first-use initialisation)
     dt, out = D_.wall(lambda: drv.get_samples(th0, iters + 1))
+    if getattr(drv, '_native', None) is not None:
+        drv._native.close()
     return {'value': D_.world * B * iters / dt, 'unit': 'chain-iterations/s', 'iterations': iters, 'chains': D_.world * B,
             'method': method, 'full_estimates_per_iter': float(out['n_full'].mean() - 1) / iters,
             'cached_estimates_per_iter': float(out['n_cached'].mean()) / iters,
             'failed_chains': int(D_.reduce((out['failed'] != 0).sum(), 'sum')),
-            'timing': 'host wall clock between barriers, max over ranks, incl. the Python scheduler and the drain of the last '
-                      'iterations; device RNG, asynchronous FULL rounds'}
+            'scheduler': SAMPLER_NOTE[rng],
+            'timing': 'host wall clock of the whole run between barriers, max over ranks, incl. the scheduler and the drain of the '
+                      'last iterations'}
 
 
 def run_configs(D_, rank, quick):
@@ -515,14 +528,9 @@ def run_gpu_arm(args):
     ms_cached, _ = timed(step_cached, max(args.steps, 3))
 
     # ---- APM-MCMC iterations/s: ESS-u + RD-SS-theta in lock-step over the same chains (device-resident u)
-    from apm_b200 import batched
-    drv = batched.BatchedAPMSampler(batched.EngineBackend(eng), n, N, D + 1, 'ess+rdss', batched.make_log_prior(D, True),
-                                    [1000 + rank * B + c for c in range(B)], prop_scales=np.full(D + 1, 0.1), rng='device',
-                                    device=dev, async_full=True)
     apm_iters = args.apm_iters
-    drv.get_samples(thetas[0], 3)          # warm-up (allocations, first-use initialisation)
-    t_apm, apm_out = D_.wall(lambda: drv.get_samples(thetas[0], apm_iters + 1))
-    apm_failed = int(D_.reduce((apm_out['failed'] != 0).sum(), 'sum'))
+    apm = _sampler_rate(D_, eng, n, D, N, B, 'ess+rdss', apm_iters, 1000, rank, 'native', thetas[0])
+    apm_py = None if args.no_configs else _sampler_rate(D_, eng, n, D, N, B, 'ess+rdss', min(apm_iters, 40), 1000, rank, 'device', thetas[0])
 
     # ---- diagnostics gather over NCCL (per-chain log-ML of the last step): the only collective of the path
     last = torch.from_numpy(outs[-1][0]).to(dev)
@@ -640,11 +648,9 @@ def run_gpu_arm(args):
             'roofline': roofline,
             'cpu_baseline': cpu,
             'cached_estimates_per_s': world * B * max(args.steps, 3) / (ms_cached * 1e-3),
-            'apm_iters_per_s': {'value': world * B * apm_iters / t_apm, 'unit': 'chain-iterations/s',
-                                'method': 'E-SS u + RD-SS theta, lock-step, %d chains/GPU, %d iterations, device RNG, asynchronous FULL rounds (worker thread + companion context for the CACHED rounds)' % (B, apm_iters),
-                                'full_estimates_per_iter': float(apm_out['n_full'].mean() - 1) / apm_iters,
-                                'cached_estimates_per_iter': float(apm_out['n_cached'].mean()) / apm_iters,
-                                'failed_chains': apm_failed, 'timing': 'host wall clock between barriers, max over ranks, incl. the Python scheduler and the drain of the last iterations'},
+            # E-SS u + RD-SS theta (smp.py:800-841), lock-step chains on the engine of the timed steps
+            'apm_iters_per_s': apm,
+            'apm_iters_per_s_python_scheduler': apm_py,
             'configs': configs,
             'diagnostics_gather': {'collective': 'nccl all_gather' if world > 1 else 'none (1 GPU)',
                                    'chains': int(all_logml.shape[0]), 'mean_logml': float(np.nanmean(all_logml))},
