@@ -79,6 +79,7 @@ struct apm_ctx {
     // Cholesky factor is exactly what the factored covariance needs, so the converged chain skips the separate
     // SYRK + Cholesky of M' (and the chol(B) of that iteration).  APM_NO_HYBRID_NEWTON=1 disables it.
     bool hybrid_newton = true;
+    bool fused_vt = true;               // k_chol_flow<true> also stores V = anti-transpose of L' (APM_NO_FUSED_VT=1: separate k_antitranspose)
     double pred_factor = 0.15;   // measured optimum 0.1-0.2 (profiles/): a missed prediction costs a latency-bound covariance phase
     int *dMaskM = nullptr, *dMaskB = nullptr, *dDoneM = nullptr;
     // f_new = s / W^1/2 instead of the second mat-vec of a B-space Newton step (k_fnew_from_s); APM_FNEW_THR=0 disables it
@@ -335,6 +336,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
     c->hybrid_newton = getenv("APM_NO_HYBRID_NEWTON") == nullptr;
+    c->fused_vt = getenv("APM_NO_FUSED_VT") == nullptr;
     if (getenv("APM_NEWTON_R0") && atoi(getenv("APM_NEWTON_R0")) > 0) c->newton_r0 = atoi(getenv("APM_NEWTON_R0"));
     if (getenv("APM_FNEW_THR")) c->fnew_thr = atof(getenv("APM_FNEW_THR"));
     if (getenv("APM_PRED_FACTOR") && atof(getenv("APM_PRED_FACTOR")) > 0) c->pred_factor = atof(getenv("APM_PRED_FACTOR"));
@@ -617,6 +619,8 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     q.diagpack = c->dDiagPack[set];
     q.spin_ns = 64;
     q.lk_idx = syrk_slots; q.w = c->dVec[V_W]; q.w_bs = c->np;
+    // the M' factorisations also leave V = anti-transpose of L' in the slot's L_C buffer (what the importance-sampling tail reads)
+    q.vt_out = (syrk_slots && c->fused_vt) ? c->dSlotLC : nullptr; q.vt_bs = (long long)c->mat;
     const int total_tasks = B * c->nb * (c->nb + 1) / 2;
     prof_begin(c, KID_MISC);
     k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb, c->dWork,
@@ -903,14 +907,16 @@ static int run_covariance_factored(apm_ctx* c, int B, const int* dSlots, const i
         APM_TRY(run_chol(c, B, nullptr, 0, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
                          nullptr, APM_CHAIN_CHOL_C, todo, nullptr, dSlots));
     }
-    // V = anti-transpose of L' into the slot's L_C buffer; mu~ = L_K^T a.  The importance-sampling tail works with
-    // (L_K, V, mu, mu~) directly, so the n^3/3 triangular solve for the explicit L_C = L_K V^-1 is only run if somebody
-    // asks for C_chol (slot_make_explicit).
-    dim3 ag(c->np / 32, c->np / 32, B), ab(32, 8);
-    prof_begin(c, KID_TRANSPOSE);
-    k_antitranspose<<<ag, ab, 0, c->stream>>>(c->dLB, (long long)c->mat, nullptr, c->dSlotLC, (long long)c->mat, dSlots, c->np,
-                                             c->dStatus);
-    APM_TRY(check_launch(c, "k_antitranspose"));
+    // V = anti-transpose of L' is already in the slot's L_C buffer: every M' factorisation (k_chol_flow<true>) stores its tiles
+    // a second time in that form.  mu~ = L_K^T a.  The importance-sampling tail works with (L_K, V, mu, mu~) directly, so the
+    // n^3/3 triangular solve for the explicit L_C = L_K V^-1 is only run if somebody asks for C_chol (slot_make_explicit).
+    if (!c->fused_vt) {
+        dim3 ag(c->np / 32, c->np / 32, B), ab(32, 8);
+        prof_begin(c, KID_TRANSPOSE);
+        k_antitranspose<<<ag, ab, 0, c->stream>>>(c->dLB, (long long)c->mat, nullptr, c->dSlotLC, (long long)c->mat, dSlots, c->np,
+                                                 c->dStatus);
+        APM_TRY(check_launch(c, "k_antitranspose"));
+    }
     if (need_cov) {
         prof_begin(c, KID_MATVEC);
         k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, c->dVec[V_A], c->np,

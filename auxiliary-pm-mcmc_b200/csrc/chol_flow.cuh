@@ -125,6 +125,9 @@ struct CholFlowParams {
     // k_chol_flow<true>: the source matrix is M' = P (I + L_K^T W L_K) P and is never stored: its tiles are accumulated on the
     // fly from k-major 16x16 boxes of L_K (tensor map tml) scaled by W before the factorisation's own k-loop (src unused)
     const int* lk_idx; const double* w; long long w_bs;
+    // k_chol_flow<true> only: optional second copy of the factor, anti-transposed (vt[np-1-c][np-1-r] = L'[r][c]) into matrix
+    // lk_idx[b] of vt_out -- V = U^T of M = U U^T, the operand the importance-sampling tail solves with (no transpose kernel)
+    double* vt_out; long long vt_bs;
     const double* scale; long long scale_bs;
     int add_identity;
     int nb;
@@ -402,6 +405,25 @@ __device__ __forceinline__ void cf_potrf_regs(CfAcc& acc, double* dp, int warp, 
     }
 }
 
+// Anti-transposed copy of a finished tile: element (R, C) of L' goes to vt[np-1-C][np-1-R].  For a fixed (mt, nt, j) the 8
+// lanes g of a quad column write 8 consecutive doubles (64 bytes) of one row; plain stores, nobody in this launch reads them.
+__device__ __forceinline__ void cf_store_antitransposed(const CfAcc& acc, double* vt, int np, int ldd, int row0, int col0, int warp,
+                                                        int g, int t, bool diag) {
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        const int R = row0 + warp * 16 + mt * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const bool lower = !diag || nt <= 2 * warp + mt;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int C = col0 + nt * 8 + 2 * t + j;
+                vt[(size_t)(np - 1 - C) * ldd + (np - 1 - R)] = lower ? acc[mt][nt][j] : 0.0;
+            }
+        }
+    }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------------------------
 // SYRK: the source is the fused M' = P (I + L_K^T W L_K) P (two instantiations keep the plain path free of its registers)
 template <bool SYRK>
@@ -619,6 +641,8 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
             } else {
                 cf_publish_arrive(n & 1);
             }
+            if (SYRK && p.vt_out)
+                cf_store_antitransposed(acc, p.vt_out + (long long)p.lk_idx[b] * p.vt_bs, p.np, p.ldd, i * TB, k * TB, warp, g, t, false);
         } else {
             // ---- diag(k): D = A_kk - L_k,0..k-1 L_k,0..k-1^T (tiles on / below the diagonal) ; L_kk = chol(D)
             for (int c = 0; c < 4 * k; c++, it++) {
@@ -657,6 +681,8 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                 fence_proxy_async_global();
                 cf_st_release(prog + k, k + 1);
             }
+            if (SYRK && p.vt_out)
+                cf_store_antitransposed(acc, p.vt_out + (long long)p.lk_idx[b] * p.vt_bs, p.np, p.ldd, k * TB, k * TB, warp, g, t, true);
             if (p.inv_out) {
                 // (L_kk^{-1})^T = I * L_kk^{-T} for the single right-hand-side solves of the Newton step (k_trsv2)
 #pragma unroll

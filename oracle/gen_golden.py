@@ -304,6 +304,26 @@ def gen_utils(ref):
         adapt=np.array([ref.utils.adapt_factor_func(b, 20) for b in range(20)]))
 
 
+def gen_run_artefacts(ref):
+    """Files written by the reference's own save_run / save_adaptive_run (gpdemo/utils.py:108-208) for fixed arguments; the
+    time stamp prefix of the file names is stripped.  tests/test_samplers_host.py compares the product's files with them."""
+    import glob
+    import shutil
+    import tempfile
+    out = os.path.join(OUT, 'run_artefacts')
+    os.makedirs(out, exist_ok=True)
+    thetas = np.arange(12.).reshape(6, 2)
+    with tempfile.TemporaryDirectory() as tmp:
+        ref.utils.save_run(tmp, 'apm_test', thetas, (3, 4), 77, 1.5, {'n_imp': 4, 'a': [1, 2], 'tag': 'x'})
+        ref.utils.save_run(tmp, 'pmmh_test', thetas, 5, 9, 2.5, {'seed': 1})
+        ref.utils.save_adaptive_run(tmp, 'ad_test', thetas, thetas[:3], np.ones(3) * 0.25, thetas + 1, (1, 2), 9, 2.5,
+                                    {'n_batch': 3, 'batch_size': 2})
+        for f in sorted(glob.glob(os.path.join(tmp, '*'))):
+            name = os.path.basename(f)[len('YYYY_mm_dd_HH_MM_SS_'):]
+            shutil.copy(f, os.path.join(out, 'ref_' + name))
+    print('run artefacts:', sorted(os.listdir(out)))
+
+
 if __name__ == '__main__':
     if os.environ.get('OPENBLAS_NUM_THREADS') != '1':
         print('warning: run with OPENBLAS_NUM_THREADS=1 for a deterministic oracle', file=sys.stderr)
@@ -313,6 +333,7 @@ if __name__ == '__main__':
         globals()['gen_' + sys.argv[2]](ref, *sys.argv[3:])
         sys.exit(0)
     gen_utils(ref)
+    gen_run_artefacts(ref)
     gen_kernels(ref)
     gen_laplace(ref)
     gen_estimator(ref, 'small_ard', 100, 4, 'ard', (1, 8), 3, 31, True)

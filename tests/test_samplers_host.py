@@ -82,6 +82,30 @@ def test_run_artefacts_have_the_reference_file_format(tmp_path):
     assert np.array_equal(z['n_reject_n_cubic_ops_comp_time'], [5, 9, 2.5])
 
 
+def test_run_artefacts_match_files_written_by_the_reference(tmp_path):
+    """tests/golden/run_artefacts/ref_* were written by the unmodified gpdemo.utils.save_run / save_adaptive_run
+    (oracle/gen_golden.py:gen_run_artefacts): same npz members (names, dtypes, shapes, values) and byte-identical JSON."""
+    import os
+    gdir = os.path.join(os.path.dirname(__file__), 'golden', 'run_artefacts')
+    thetas = np.arange(12.).reshape(6, 2)
+    made = {
+        'apm_test': utils.save_run(str(tmp_path), 'apm_test', thetas, (3, 4), 77, 1.5, {'n_imp': 4, 'a': [1, 2], 'tag': 'x'}),
+        'pmmh_test': utils.save_run(str(tmp_path), 'pmmh_test', thetas, 5, 9, 2.5, {'seed': 1}),
+        'ad_test': utils.save_adaptive_run(str(tmp_path), 'ad_test', thetas, thetas[:3], np.ones(3) * 0.25, thetas + 1, (1, 2), 9,
+                                           2.5, {'n_batch': 3, 'batch_size': 2}),
+    }
+    for tag, (res, par) in made.items():
+        ref = np.load(os.path.join(gdir, 'ref_%s_results.npz' % tag))
+        ours = np.load(res)
+        assert sorted(ours.files) == sorted(ref.files)
+        for k in ref.files:
+            assert ours[k].dtype == ref[k].dtype and ours[k].shape == ref[k].shape and np.array_equal(ours[k], ref[k]), (tag, k)
+        assert open(par).read() == open(os.path.join(gdir, 'ref_%s_params.json' % tag)).read()
+        # <time stamp><tag>_results.npz / _params.json with the reference's stamp format
+        base = os.path.basename(res)
+        assert base.endswith(tag + '_results.npz') and len(base) == len('YYYY_mm_dd_HH_MM_SS_') + len(tag + '_results.npz')
+
+
 def test_chain_diagnostics():
     rs = np.random.RandomState(3)
     n = 20000
