@@ -438,7 +438,7 @@ class NativeSampler(object):
         out = np.zeros(8)
         check(self._L.apm_sampler_stats(self._h, _ptr(out)))
         return dict(full_calls=int(out[0]), full_chains=int(out[1]), cached_calls=int(out[2]), cached_chains=int(out[3]),
-                    t_flight=float(out[4]), t_total=float(out[5]), rounds=int(out[6]))
+                    t_flight=float(out[4]), t_total=float(out[5]), rounds=int(out[6]), t_busy=float(out[7]))
 
     def close(self):
         if getattr(self, '_h', None):

@@ -79,6 +79,7 @@ struct apm_ctx {
     // Cholesky factor is exactly what the factored covariance needs, so the converged chain skips the separate
     // SYRK + Cholesky of M' (and the chol(B) of that iteration).  APM_NO_HYBRID_NEWTON=1 disables it.
     bool hybrid_newton = true;
+    bool fused_fwd = true;              // forward substitution of the Newton solves inside k_chol_flow's diagonal tasks (APM_NO_FUSED_FWD=1: k_trsv2 does both halves)
     bool fused_vt = true;               // k_chol_flow<true> also stores V = anti-transpose of L' (APM_NO_FUSED_VT=1: separate k_antitranspose)
     double pred_factor = 0.15;   // measured optimum 0.1-0.2 (profiles/): a missed prediction costs a latency-bound covariance phase
     int *dMaskM = nullptr, *dMaskB = nullptr, *dDoneM = nullptr;
@@ -100,7 +101,7 @@ struct apm_ctx {
     // sets of queue state + packed diagonal blocks (set 1: launches on the aux stream, which overlap the main stream's)
     CUtensorMap tmLB, tmSlotLK, tmSlotLC, tmK, tmSlotLK16;   // (16: k-major 16x16 boxes of L_K for the fused M' source)
     bool tma_ok = false;
-    int *dFlow2Progress[2] = {nullptr, nullptr}, *dFlow2Skip[2] = {nullptr, nullptr};
+    int *dFlow2Progress[2] = {nullptr, nullptr}, *dFlow2Skip[2] = {nullptr, nullptr}, *dFlowYProg[2] = {nullptr, nullptr};
     double* dDiagPack[2] = {nullptr, nullptr};
     int flow2_grid = 0;           // resident CTAs of k_chol_flow on the whole GPU
     unsigned long long* dWork = nullptr;   // [0] chain-Choleskys, [1] M' builds executed (counted on the device: the masks are only known there)
@@ -193,15 +194,18 @@ static int check_launch(apm_ctx* c, const char* what) {
 static int g_attr_done = 0;
 static int set_kernel_attrs() {
     if (g_attr_done) return APM_OK;
-    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_gemm_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_build_K, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU_TRY(cudaFuncSetAttribute(k_build_dK, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CU_TRY(cudaFuncSetAttribute(k_trsv2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU_TRY(cudaFuncSetAttribute(k_trsv2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU_TRY(cudaFuncSetAttribute(k_trsv2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU_TRY(cudaFuncSetAttribute(k_is_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     g_attr_done = 1;
     return APM_OK;
@@ -214,8 +218,10 @@ extern "C" int apm_destroy(apm_ctx* c);
 
 // parent != null: companion context -- its cache slots ARE the parent's (no slot storage of its own) and its per-chain
 // matrix workspaces are sized for one chain (it only runs the O(n^2 N) cached estimates)
+// full_ws (companions only): matrix workspaces for every chain, so that the companion can run FULL estimates into the parent's
+// slots as well (second FULL job of the native sampler)
 static int create_impl(const double* X, const double* y, int n, int D, int kernel_kind, double epsilon, int max_chains,
-                       int n_slots, int max_nimp, int device, apm_ctx* parent, apm_ctx** out) {
+                       int n_slots, int max_nimp, int device, apm_ctx* parent, apm_ctx** out, bool full_ws = false) {
     if (!X || !y || !out || n <= 0 || D <= 0 || max_chains <= 0 || n_slots <= 0 || max_nimp <= 0 ||
         (kernel_kind != APM_KERNEL_ISO && kernel_kind != APM_KERNEL_ARD)) {
         set_err("apm_create: invalid argument");
@@ -250,9 +256,9 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->slot_mode.assign(n_slots, 0);
     c->slot_valid.assign(n_slots, 0);
     const size_t B = max_chains, np = c->np;
-    const size_t Bm = parent ? 1 : B;      // chains with full matrix workspaces
+    const size_t Bm = (parent && !full_ws) ? 1 : B;      // chains with full matrix workspaces
     const size_t own_slots = parent ? 0 : (size_t)n_slots;
-    c->cached_only = parent != nullptr;
+    c->cached_only = parent != nullptr && !full_ws;
     int rc = APM_OK;
     auto A = [&](int r) { if (rc == APM_OK) rc = r; };
     A(dev_alloc(c, &c->dX, np * D));
@@ -300,6 +306,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     for (int q = 0; q < 2; q++) {
         A(dev_alloc(c, &c->dFlow2Progress[q], B * (size_t)c->nb));
         A(dev_alloc(c, &c->dFlow2Skip[q], B));
+        A(dev_alloc(c, &c->dFlowYProg[q], B));
         A(dev_alloc(c, &c->dDiagPack[q], Bm * (size_t)c->nb * DP_DOUBLES));
     }
     if (rc == APM_OK) cudaMemset(c->dWork, 0, 4 * sizeof(unsigned long long));
@@ -329,7 +336,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
         }
         int occ = 0, sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_flow<true>, CF_THREADS, CF_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_flow<true, true>, CF_THREADS, CF_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
         c->flow2_grid = occ * sms;
         if (getenv("APM_FLOW_GRID") && atoi(getenv("APM_FLOW_GRID")) > 0) c->flow2_grid = atoi(getenv("APM_FLOW_GRID"));
     }
@@ -337,6 +344,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
     c->hybrid_newton = getenv("APM_NO_HYBRID_NEWTON") == nullptr;
     c->fused_vt = getenv("APM_NO_FUSED_VT") == nullptr;
+    c->fused_fwd = getenv("APM_NO_FUSED_FWD") == nullptr;
     if (getenv("APM_NEWTON_R0") && atoi(getenv("APM_NEWTON_R0")) > 0) c->newton_r0 = atoi(getenv("APM_NEWTON_R0"));
     if (getenv("APM_FNEW_THR")) c->fnew_thr = atof(getenv("APM_FNEW_THR"));
     if (getenv("APM_PRED_FACTOR") && atof(getenv("APM_PRED_FACTOR")) > 0) c->pred_factor = atof(getenv("APM_PRED_FACTOR"));
@@ -394,6 +402,21 @@ extern "C" int apm_create_companion(apm_ctx* parent, int max_chains, int max_nim
     CU_TRY(cudaMemcpy(yp.data(), parent->dy, sizeof(double) * yp.size(), cudaMemcpyDeviceToHost));
     return create_impl(Xp.data(), yp.data(), parent->n, parent->D, parent->kind, parent->eps, max_chains, parent->nslots,
                        max_nimp, parent->device, parent, out);
+}
+
+// internal: companion with full workspaces (see create_impl)
+static int create_full_companion(apm_ctx* parent, int max_chains, int max_nimp, apm_ctx** out) {
+    if (!parent || !out || parent->root != nullptr) return APM_ERR_INVALID;
+    CU_TRY(cudaSetDevice(parent->device));
+    std::vector<double> Xp((size_t)parent->np * parent->D), yp(parent->np);
+    CU_TRY(cudaMemcpy(Xp.data(), parent->dX, sizeof(double) * Xp.size(), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(yp.data(), parent->dy, sizeof(double) * yp.size(), cudaMemcpyDeviceToHost));
+    APM_TRY(create_impl(Xp.data(), yp.data(), parent->n, parent->D, parent->kind, parent->eps, max_chains, parent->nslots,
+                        max_nimp, parent->device, parent, out, true));
+    apm_ctx* c = *out;     // same algorithmic settings as the parent
+    c->tol = parent->tol; c->max_iters = parent->max_iters; c->approx = parent->approx;
+    c->ep_tol = parent->ep_tol; c->ep_max_iters = parent->ep_max_iters; c->ep_damping = parent->ep_damping;
+    return APM_OK;
 }
 
 static int not_companion(apm_ctx* c) {
@@ -579,7 +602,9 @@ static int build_K(apm_ctx* c, int B, int kind, double eps) {
 static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, const int* src_idx, double* dst,
                     long long dst_bs, const int* dst_idx, const double* scale, int add_identity, double* logdet_parts,
                     const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr,
-                    const int* syrk_slots = nullptr) {
+                    const int* syrk_slots = nullptr, bool fwd = false) {
+    // fwd: the factorisation also solves L y = t for the right-hand side in dVec[V_T] (y -> dVec[V_S]): the forward half of
+    // the Newton step's triangular solves, fused into the diagonal tasks
     // syrk_slots != null: the source is M' = P (I + L_K^T W L_K) P, accumulated on the fly from chol(K) in those slots and
     // W (dVec[V_W]) inside the factorisation's tasks (src is ignored; see chol_flow.cuh)
     cudaStream_t st = c->launch_stream ? c->launch_stream : c->stream;
@@ -621,15 +646,21 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     q.lk_idx = syrk_slots; q.w = c->dVec[V_W]; q.w_bs = c->np;
     // the M' factorisations also leave V = anti-transpose of L' in the slot's L_C buffer (what the importance-sampling tail reads)
     q.vt_out = (syrk_slots && c->fused_vt) ? c->dSlotLC : nullptr; q.vt_bs = (long long)c->mat;
+    q.fwd_t = fwd ? c->dVec[V_T] : nullptr; q.fwd_y = c->dVec[V_S]; q.fwd_bs = c->np; q.yprog = c->dFlowYProg[set];
     const int total_tasks = B * c->nb * (c->nb + 1) / 2;
     prof_begin(c, KID_MISC);
     k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb, c->dWork,
-                                                             syrk_slots ? c->dWork + 1 : nullptr);
+                                                             syrk_slots ? c->dWork + 1 : nullptr, fwd ? q.yprog : nullptr);
     APM_TRY(check_launch(c, "k_chol_flow_init"));
     const int grid = c->flow2_grid < total_tasks ? c->flow2_grid : total_tasks;
     prof_begin(c, KID_CHOL);
-    if (syrk_slots) k_chol_flow<true><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
-    else k_chol_flow<false><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
+    if (syrk_slots) {
+        if (fwd) k_chol_flow<true, true><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
+        else k_chol_flow<true, false><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
+    } else {
+        if (fwd) k_chol_flow<false, true><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
+        else k_chol_flow<false, false><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
+    }
     return check_launch(c, "k_chol_flow");
 }
 
@@ -735,11 +766,15 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
             if (!matfree) APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t, maskB));
             // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
             APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB));
+                             nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB, nullptr, c->fused_fwd));
             // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
             prof_begin(c, KID_TRSV);
-            k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
-                                                      (long long)c->nb * TB * TB, nvB);
+            if (c->fused_fwd)
+                k_trsv2<true><<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                                (long long)c->nb * TB * TB, nvB);
+            else
+                k_trsv2<false><<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                                 (long long)c->nb * TB * TB, nvB);
             APM_TRY(check_launch(c, "k_trsv2"));
             // f_new = K a                                              (lpa.py:95)
             if (matfree) {
@@ -763,11 +798,15 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
             APM_TRY(check_launch(c, "k_lt_matvec"));
             // L' = chol(M'), M' = P (I + L_K^T W L_K) P built inside the factorisation from L_K and W (never stored)
             APM_TRY(run_chol(c, B, nullptr, 0, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, dSlots));
+                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, dSlots, c->fused_fwd));
             // s' = M'^-1 t'
             prof_begin(c, KID_TRSV);
-            k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
-                                                      (long long)c->nb * TB * TB, nvM);
+            if (c->fused_fwd)
+                k_trsv2<true><<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                                (long long)c->nb * TB * TB, nvM);
+            else
+                k_trsv2<false><<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                                 (long long)c->nb * TB * TB, nvM);
             APM_TRY(check_launch(c, "k_trsv2"));
             // mu~ = reversed s' (-> slot), f_new = L_K mu~
             prof_begin(c, KID_MATVEC);
@@ -849,8 +888,8 @@ static int run_ep(apm_ctx* c, int B) {
         APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
                          nullptr, APM_CHAIN_CHOL_B, c->dActive, c->dInvB));
         prof_begin(c, KID_TRSV);
-        k_trsv2<<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
-                                                  (long long)c->nb * TB * TB, nv);   // a = nu~ - S^1/2 B^-1 t
+        k_trsv2<false><<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                         (long long)c->nb * TB * TB, nv);   // a = nu~ - S^1/2 B^-1 t
         APM_TRY(check_launch(c, "k_trsv2"));
         APM_TRY(run_symv(c, B, nv.a, nullptr, nv.fnew));                         // mu = K a
         APM_TRY(run_trsm_z(c, B, c->dActive));

@@ -44,7 +44,7 @@ constexpr int CF_STAGES = APM_CF_STAGES;
 constexpr int DP_LBLOCKS = 36;                         // lower 8x8 blocks (q >= p) of a 64x64 triangle, block (q,p) at q(q+1)/2 + p
 constexpr int DP_DOUBLES = (DP_LBLOCKS + 8) * 64;      // + inverses of the 8 diagonal 8x8 blocks
 constexpr int DP_BYTES = DP_DOUBLES * 8;               // 22528
-constexpr int CF_CTRL_BYTES = 1024;
+constexpr int CF_CTRL_BYTES = 2048;                  // barriers / task slots / W or y of a stage (first KB) + two right-hand-side blocks
 constexpr int CF_SMEM_BYTES = 1024 + CF_STAGES * 2 * CF_CHUNK_BYTES + DP_BYTES + CF_CTRL_BYTES;   // 1024: manual alignment slack
 
 __device__ __forceinline__ int dp_block(int q, int p) { return (q * (q + 1) / 2 + p) * 64; }
@@ -128,6 +128,10 @@ struct CholFlowParams {
     // k_chol_flow<true> only: optional second copy of the factor, anti-transposed (vt[np-1-c][np-1-r] = L'[r][c]) into matrix
     // lk_idx[b] of vt_out -- V = U^T of M = U U^T, the operand the importance-sampling tail solves with (no transpose kernel)
     double* vt_out; long long vt_bs;
+    // Optional fused forward substitution y = L^-1 t (the first half of the Newton step's cho_solve, lpa.py:94): diag(k) adds
+    // up L_k,0..k-1 y_0..k-1 from the operand chunks it streams anyway and solves its 64 rows with the packed L_kk once the
+    // factor is published.  fwd_t: right-hand side, fwd_y: result (both [chain][np], stride fwd_bs), yprog[chain]: finished blocks.
+    const double* fwd_t; double* fwd_y; long long fwd_bs; int* yprog;
     const double* scale; long long scale_bs;
     int add_identity;
     int nb;
@@ -147,9 +151,10 @@ struct CholFlowParams {
 // Newton mask) into an ordered list: a launch for a few straggler chains enumerates only their tasks.  One launch instead
 // of two memsets + a snapshot kernel; block 0 / warp 0 does the (ballot) compaction.
 __global__ void k_chol_flow_init(int* counter, int* progress, int* list, const int* status, const int* active, int nchains, int nb,
-                                 unsigned long long* work, unsigned long long* work2) {
+                                 unsigned long long* work, unsigned long long* work2, int* yprog = nullptr) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nchains * nb) progress[e] = 0;
+    if (yprog && e < nchains) yprog[e] = 0;
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         int count = 0;
         for (int b0 = 0; b0 < nchains; b0 += 32) {
@@ -225,8 +230,11 @@ __device__ __forceinline__ uint32_t cf_acc_dep(const CfAcc& acc) {
 // acc -= A(rows of this warp) * B(all 64 rows)^T over one 16-deep chunk.  Stage layout: row r at r*128 bytes, its 16-byte
 // segment c at position c ^ (r & 7) (TMA SWIZZLE_128B).  DMMA kk contracts the columns {2kk, 2kk+1, 2kk+8, 2kk+9}: lane t
 // reads segment kk ^ 4(t>>1), half t&1 -- the 16 lanes of a half-warp then hit 16 distinct 8-byte bank pairs.
-template <bool DIAG>
-__device__ __forceinline__ void cf_gemm_chunk(CfAcc& acc, const unsigned char* sA, const unsigned char* sB, int warp, int g, int t) {
+// FWD: ys[mt] -= (row of A) . y over this lane's four columns of the chunk (ych: the 16 entries of y that go with the chunk);
+// the A fragment of DMMA kk is column 2 kk + (t & 1) + 8 (t >> 1) of the chunk.
+template <bool DIAG, bool FWD = false>
+__device__ __forceinline__ void cf_gemm_chunk(CfAcc& acc, const unsigned char* sA, const unsigned char* sB, int warp, int g, int t,
+                                              const double* ych = nullptr, double* ys = nullptr) {
     const uint32_t lo0 = (uint32_t)(((((t >> 1) << 2) ^ g) << 4) | ((t & 1) << 3));
     const unsigned char* a_base = sA + (warp * 16 + g) * 128;
     const unsigned char* b_base = sB + g * 128;
@@ -236,6 +244,11 @@ __device__ __forceinline__ void cf_gemm_chunk(CfAcc& acc, const unsigned char* s
         double a[2], b[8];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) a[mt] = -*reinterpret_cast<const double*>(a_base + mt * 1024 + lo);
+        if (FWD) {
+            const double yv = ych[2 * kk + (t & 1) + 8 * (t >> 1)];
+            ys[0] = fma(a[0], yv, ys[0]);
+            ys[1] = fma(a[1], yv, ys[1]);
+        }
 #pragma unroll
         for (int nt = 0; nt < 8; nt++)
             if (!DIAG || nt <= 2 * warp + 1) b[nt] = *reinterpret_cast<const double*>(b_base + nt * 1024 + lo);
@@ -405,6 +418,41 @@ __device__ __forceinline__ void cf_potrf_regs(CfAcc& acc, double* dp, int warp, 
     }
 }
 
+// y = L_kk^-1 rhs for one 64-row block, by one warp, from the packed diagonal block (36 lower 8x8 blocks + the inverses of
+// the 8 diagonal ones): eight dependent 8x8 steps  v = rhs_p - sum_{q<p} L_pq y_q,  y_p = inv(L_pp) v.  Lane (g, t) works on
+// row g and the column pair (2t, 2t+1) of every 8x8 block; sums over t by quad shuffles.  Result: yout[8 p + g].
+// One copy of the code (noinline, like cf_chol8_inv8): its registers stay out of the kernel's GEMM loops.  tk: the block's
+// entries of the right-hand side t; rhs: -(L_k,0..k-1 y) collected by the GEMM.
+__device__ __noinline__ void cf_forward_block(const double* dp, const double* rhs, const double* tk, double* yout, int g, int t) {
+    const unsigned FULL = 0xffffffffu;
+    const int off = g * 8 + 2 * t;
+    double tv[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) tv[p] = tk[p * 8 + g];
+    double y0[8], y1[8];      // y_q[2t], y_q[2t+1] of the finished blocks
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < p; q++) {
+            const double2 l = *reinterpret_cast<const double2*>(dp + dp_block(p, q) + off);
+            acc = fma(l.x, y0[q], acc);
+            acc = fma(l.y, y1[q], acc);
+        }
+        acc += __shfl_xor_sync(FULL, acc, 1);
+        acc += __shfl_xor_sync(FULL, acc, 2);
+        const double v = (tv[p] + rhs[p * 8 + g]) - acc;                // v[g], the same in the four lanes of a quad
+        const double v0 = __shfl_sync(FULL, v, (2 * t) * 4), v1 = __shfl_sync(FULL, v, (2 * t + 1) * 4);
+        const double2 iv = *reinterpret_cast<const double2*>(dp + dp_inv(p) + off);
+        double yp = fma(iv.x, v0, iv.y * v1);
+        yp += __shfl_xor_sync(FULL, yp, 1);
+        yp += __shfl_xor_sync(FULL, yp, 2);                            // y_p[g]
+        y0[p] = __shfl_sync(FULL, yp, (2 * t) * 4);
+        y1[p] = __shfl_sync(FULL, yp, (2 * t + 1) * 4);
+        if (t == 0) yout[p * 8 + g] = yp;
+    }
+}
+
 // Anti-transposed copy of a finished tile: element (R, C) of L' goes to vt[np-1-C][np-1-R].  For a fixed (mt, nt, j) the 8
 // lanes g of a quad column write 8 consecutive doubles (64 bytes) of one row; plain stores, nobody in this launch reads them.
 __device__ __forceinline__ void cf_store_antitransposed(const CfAcc& acc, double* vt, int np, int ldd, int row0, int col0, int warp,
@@ -426,7 +474,8 @@ __device__ __forceinline__ void cf_store_antitransposed(const CfAcc& acc, double
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------
 // SYRK: the source is the fused M' = P (I + L_K^T W L_K) P (two instantiations keep the plain path free of its registers)
-template <bool SYRK>
+// FWD: fused forward substitution (p.fwd_*); separate instantiations keep the plain factorisation free of its registers
+template <bool SYRK, bool FWD = false>
 __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tms, const __grid_constant__ CUtensorMap tml,
                                                                            CholFlowParams p) {
     extern __shared__ unsigned char cf_smem_raw[];
@@ -445,7 +494,9 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
     double* red = reinterpret_cast<double*>(ctrl + 16 * CF_STAGES + 48 + 2 * sizeof(CfTask));   // 4 partial log-dets
     double* wst = reinterpret_cast<double*>(ctrl + 512);                                         // W_r of a TN stage: [stage][16]
     const uint32_t wst_u = ctrl_u + 512;
-    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= 512 && 512 + CF_STAGES * 128 <= CF_CTRL_BYTES, "control block too small");
+    double* fw_rhs = reinterpret_cast<double*>(ctrl + 1024);                                     // [2][64]: right-hand side block of a diag task (by task parity)
+    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= 512 && 512 + CF_STAGES * 128 <= 1024 && 1024 + 2 * 64 * 8 <= CF_CTRL_BYTES,
+                  "control block too small");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -542,18 +593,23 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                 mbar_expect_tx(bar_dp_full, DP_BYTES);
                 bulk_load_1d(dp_u, p.diagpack + ((size_t)b * nb + k) * DP_DOUBLES, DP_BYTES, bar_dp_full);
             } else {
-                int known = 0;
+                int known = 0, yknown = 0;
+                const bool fwd = FWD;
+                const double* ysrc = fwd ? p.fwd_y + (long long)b * p.fwd_bs : nullptr;
                 for (int j = 0; j < k; j++) {
-                    if (known < j + 1) {
+                    if (known < j + 1 || (fwd && yknown < j + 1)) {
                         while ((known = cf_ld_relaxed(prog + k)) < j + 1) __nanosleep(p.spin_ns);
+                        if (fwd)
+                            while ((yknown = cf_ld_relaxed(p.yprog + b)) < j + 1) __nanosleep(p.spin_ns);
                         __threadfence();
                         fence_proxy_async_global();
                     }
                     for (int c = 4 * j; c < 4 * j + 4; c++, it++) {
                         const uint32_t s = it % CF_STAGES;
                         mbar_wait(bar_empty + 8 * s, ((it / CF_STAGES) & 1) ^ 1);
-                        mbar_expect_tx(bar_full + 8 * s, CF_CHUNK_BYTES);
+                        mbar_expect_tx(bar_full + 8 * s, CF_CHUNK_BYTES + (fwd ? 128 : 0));
                         tma_load_2d(ring_u + s * 2 * CF_CHUNK_BYTES, &tm, c * CF_KC, row0 + k * TB, bar_full + 8 * s);
+                        if (fwd) bulk_load_1d(wst_u + s * 128, ysrc + 16 * c, 128, bar_full + 8 * s);   // y entries of the chunk's columns
                     }
                 }
                 if (n > 0) mbar_wait(bar_dp_empty, (n - 1) & 1);   // keeps the producer within one task of the consumers
@@ -645,11 +701,32 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                 cf_store_antitransposed(acc, p.vt_out + (long long)p.lk_idx[b] * p.vt_bs, p.np, p.ldd, i * TB, k * TB, warp, g, t, false);
         } else {
             // ---- diag(k): D = A_kk - L_k,0..k-1 L_k,0..k-1^T (tiles on / below the diagonal) ; L_kk = chol(D)
-            for (int c = 0; c < 4 * k; c++, it++) {
-                const uint32_t s = it % CF_STAGES;
-                mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
-                cf_gemm_chunk<true>(acc, ring + s * 2 * CF_CHUNK_BYTES, ring + s * 2 * CF_CHUNK_BYTES, warp, g, t);
-                cf_release_stage(bar_empty + 8 * s, cf_acc_dep(acc), p.zero, lane);
+            const bool fwd = FWD;
+            if (fwd) {
+                // fused forward substitution: rhs_k = t_k - sum_j L_kj y_j, collected from the A fragments of the GEMM
+                double ys[2] = {0.0, 0.0};
+                for (int c = 0; c < 4 * k; c++, it++) {
+                    const uint32_t s = it % CF_STAGES;
+                    mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
+                    cf_gemm_chunk<true, true>(acc, ring + s * 2 * CF_CHUNK_BYTES, ring + s * 2 * CF_CHUNK_BYTES, warp, g, t, wst + s * 16, ys);
+                    cf_release_stage(bar_empty + 8 * s, cf_acc_dep(acc) | (uint32_t)__double2hiint(ys[0]) | (uint32_t)__double2hiint(ys[1]), p.zero, lane);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    ys[mt] += __shfl_xor_sync(0xffffffffu, ys[mt], 1);
+                    ys[mt] += __shfl_xor_sync(0xffffffffu, ys[mt], 2);
+                }
+                if (t == 0) {
+                    fw_rhs[(n & 1) * 64 + warp * 16 + g] = ys[0];
+                    fw_rhs[(n & 1) * 64 + warp * 16 + 8 + g] = ys[1];
+                }
+            } else {
+                for (int c = 0; c < 4 * k; c++, it++) {
+                    const uint32_t s = it % CF_STAGES;
+                    mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
+                    cf_gemm_chunk<true>(acc, ring + s * 2 * CF_CHUNK_BYTES, ring + s * 2 * CF_CHUNK_BYTES, warp, g, t);
+                    cf_release_stage(bar_empty + 8 * s, cf_acc_dep(acc), p.zero, lane);
+                }
             }
             bool bad = false;
             double dg0 = 1.0, dg1 = 1.0;
@@ -701,6 +778,14 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                     for (int nt = 0; nt < 8; nt++)
                         *reinterpret_cast<double2*>(io + (warp * 16 + mt * 8 + g) * TB + nt * 8 + 2 * t) =
                             make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            }
+            if (fwd && warp == 0) {
+                // y_k = L_kk^-1 rhs_k: off the factorisation's critical path (L_kk is already published); the next diagonal
+                // task of this chain waits for yprog before it streams y_k
+                cf_forward_block(dp, fw_rhs + (n & 1) * 64, p.fwd_t + (long long)b * p.fwd_bs + k * TB, p.fwd_y + (long long)b * p.fwd_bs + k * TB, g, t);
+                fence_proxy_async_global();         // read by other CTAs' bulk copies
+                __syncwarp();
+                if (lane == 0) cf_st_release(p.yprog + b, k + 1);
             }
         }
         __syncwarp();

@@ -104,7 +104,8 @@ enum { APM_METHOD_MI_MH = 0, APM_METHOD_ESS_MH = 1, APM_METHOD_MI_RDSS = 2, APM_
 
 namespace {
 
-enum { IDX_MI = 0, IDX_V, IDX_ELL, IDX_ACC, IDX_FULL_NEW, IDX_FULL_GATHER, IDX_SETS };
+// FULL_NEW / FULL_GATHER exist once per FULL job slot (+ 2 w): a slot's lists are rewritten only after its previous job finished
+enum { IDX_MI = 0, IDX_V, IDX_ELL, IDX_ACC, IDX_FULL_NEW, IDX_FULL_GATHER, IDX_SETS = 8 };
 enum { REQ_NONE = 0, REQ_FULL, REQ_FULL_NEWU, REQ_CACHED_NEW, REQ_CACHED_ELL };
 enum { ST_START = 0, ST_U_MI, ST_U_ESS, ST_TH_MH, ST_TH_RDSS, ST_PMMH, ST_DONE };
 const double S_TWO_PI = 2.0 * 3.14159265358979323846;
@@ -135,6 +136,9 @@ struct FullJob {
 struct apm_sampler {
     apm_ctx* eng = nullptr;
     apm_ctx* comp = nullptr;
+    apm_ctx* eng2 = nullptr;           // second FULL job: companion with full workspaces on the same cache slots (n_jobs == 2)
+    int n_jobs = 1;
+    int min_second = 0;                // a second job is only started with at least this many chains
     int method = 0, B = 0, N = 0, Npad = 0, P = 0, n = 0, np = 0, device = 0;
     long long ubs = 0;
     std::vector<uint64_t> seeds;
@@ -148,17 +152,17 @@ struct apm_sampler {
     int* dIdx = nullptr;
     int* hIdx = nullptr;
     double* hCS = nullptr;
-    cudaStream_t s_main = nullptr, s_full = nullptr;
-    cudaEvent_t ev_full_ready = nullptr;
+    cudaStream_t s_main = nullptr, s_full[2] = {nullptr, nullptr};
+    cudaEvent_t ev_full_ready[2] = {nullptr, nullptr};
     std::vector<SChain> chains;
     double* trace = nullptr;
     int n_sample = 0;
     // FULL worker
-    std::thread worker;
+    std::thread worker[2];
     std::mutex mu;
     std::condition_variable cv;
-    FullJob job;
-    bool job_posted = false, job_done = false, quit = false;
+    FullJob job[2];
+    bool job_posted[2] = {false, false}, job_done[2] = {false, false}, quit = false;
     // scheduling diagnostics of the last run
     double stats[8] = {0};
 };
@@ -342,24 +346,26 @@ void s_resume(apm_sampler* s, SChain& ch, double val) {
     }
 }
 
-void s_worker(apm_sampler* s) {
+inline apm_ctx* s_engine(apm_sampler* s, int w) { return w == 0 ? s->eng : s->eng2; }
+
+void s_worker(apm_sampler* s, int w) {
     cudaSetDevice(s->device);
     for (;;) {
         std::unique_lock<std::mutex> lk(s->mu);
-        s->cv.wait(lk, [s] { return s->job_posted || s->quit; });
+        s->cv.wait(lk, [s, w] { return s->job_posted[w] || s->quit; });
         if (s->quit) return;
-        s->job_posted = false;
+        s->job_posted[w] = false;
         lk.unlock();
-        FullJob& j = s->job;
+        FullJob& j = s->job[w];
         const int m = (int)j.chains.size();
-        int rc = (cudaStreamWaitEvent(s->s_full, s->ev_full_ready, 0) == cudaSuccess) ? APM_OK : APM_ERR_CUDA;
+        int rc = (cudaStreamWaitEvent(s->s_full[w], s->ev_full_ready[w], 0) == cudaSuccess) ? APM_OK : APM_ERR_CUDA;
         if (rc == APM_OK)
-            rc = estimate_full_impl(s->eng, j.thetas.data(), nullptr, 1, s->N, m, j.slots.data(), j.vals.data(), j.ops.data(),
+            rc = estimate_full_impl(s_engine(s, w), j.thetas.data(), nullptr, 1, s->N, m, j.slots.data(), j.vals.data(), j.ops.data(),
                                     j.st.data(), true);
         j.rc = rc;
         if (rc != APM_OK) j.err = g_err;
         lk.lock();
-        s->job_done = true;
+        s->job_done[w] = true;
         lk.unlock();
         s->cv.notify_all();
     }
@@ -403,34 +409,34 @@ int s_copy(apm_sampler* s, int set, int cnt, double* dst, const double* src) {
 }
 
 // gather the chains of the next FULL call (fresh normals first where the request asks for them) and hand it to the worker
-int s_submit_full(apm_sampler* s, const std::vector<int>& full) {
+int s_submit_full(apm_sampler* s, const std::vector<int>& full, int w) {
     const int m = (int)full.size();
-    FullJob& j = s->job;
+    FullJob& j = s->job[w];
     j.chains = full;
     j.thetas.resize((size_t)m * s->P); j.slots.resize(m); j.vals.resize(m); j.ops.resize(m); j.st.resize(m);
     int n_new = 0;
     for (int q = 0; q < m; q++) {
         SChain& ch = s->chains[full[q]];
         if (ch.req == REQ_FULL_NEWU) {
-            s_hidx(s, IDX_FULL_NEW, 0)[n_new] = full[q];      // fresh u of the chain (PM-MH: every estimate; APM: the first)
-            s_hidx(s, IDX_FULL_NEW, 1)[n_new] = full[q];
-            s_hidx(s, IDX_FULL_NEW, 2)[n_new] = (int)ch.draw;
+            s_hidx(s, IDX_FULL_NEW + 2 * w, 0)[n_new] = full[q];      // fresh u of the chain (PM-MH: every estimate; APM: the first)
+            s_hidx(s, IDX_FULL_NEW + 2 * w, 1)[n_new] = full[q];
+            s_hidx(s, IDX_FULL_NEW + 2 * w, 2)[n_new] = (int)ch.draw;
             n_new++;
         }
         memcpy(&j.thetas[(size_t)q * s->P], ch.theta_req.data(), sizeof(double) * s->P);
         j.slots[q] = ch.prop;                                   // written into the proposal slot
     }
-    APM_TRY(s_normals(s, IDX_FULL_NEW, n_new, s->dU, s->ubs));
+    APM_TRY(s_normals(s, IDX_FULL_NEW + 2 * w, n_new, s->dU, s->ubs));
     for (int q = 0; q < m; q++) {
-        s_hidx(s, IDX_FULL_GATHER, 0)[q] = q;
-        s_hidx(s, IDX_FULL_GATHER, 1)[q] = full[q];
+        s_hidx(s, IDX_FULL_GATHER + 2 * w, 0)[q] = q;
+        s_hidx(s, IDX_FULL_GATHER + 2 * w, 1)[q] = full[q];
     }
-    APM_TRY(s_copy(s, IDX_FULL_GATHER, m, s->eng->dUT, s->dU));
-    S_CU(cudaEventRecord(s->ev_full_ready, s->s_main));
+    APM_TRY(s_copy(s, IDX_FULL_GATHER + 2 * w, m, s_engine(s, w)->dUT, s->dU));
+    S_CU(cudaEventRecord(s->ev_full_ready[w], s->s_main));
     {
         std::lock_guard<std::mutex> lk(s->mu);
-        s->job_done = false;
-        s->job_posted = true;
+        s->job_done[w] = false;
+        s->job_posted[w] = true;
     }
     s->cv.notify_all();
     return APM_OK;
@@ -456,23 +462,34 @@ int s_run(apm_sampler* s, const double* theta_init, int n_sample, double* thetas
         ch.state = ST_START;
         n_pending++;
     }
-    // the engine runs the FULL calls on the worker's stream, the companion the CACHED calls on this thread's
+    // the engines run the FULL calls on their workers' streams, the companion the CACHED calls on this thread's
+    const int J = s->n_jobs;
     const cudaStream_t eng_stream = s->eng->stream;
     S_CU(cudaStreamSynchronize(eng_stream));
-    s->eng->stream = s->s_full;
+    s->eng->stream = s->s_full[0];
     s->comp->stream = s->s_main;
-    bool inflight = false;
-    struct Restore {     // also on error returns: wait for a FULL call still in flight before handing the engine back
+    if (s->eng2) {      // the second engine follows the settings of the first
+        apm_ctx *a = s->eng, *b2 = s->eng2;
+        b2->stream = s->s_full[1];
+        b2->tol = a->tol; b2->max_iters = a->max_iters; b2->approx = a->approx;
+        b2->ep_tol = a->ep_tol; b2->ep_max_iters = a->ep_max_iters; b2->ep_damping = a->ep_damping;
+        b2->overlap_chol_k = a->overlap_chol_k;
+    }
+    bool inflight[2] = {false, false};
+    struct Restore {     // also on error returns: wait for the FULL calls still in flight before handing the engine back
         apm_sampler* s; cudaStream_t st; bool* inflight;
         ~Restore() {
-            if (*inflight) { std::unique_lock<std::mutex> lk(s->mu); s->cv.wait(lk, [this] { return s->job_done; }); }
-            cudaStreamSynchronize(s->s_full); cudaStreamSynchronize(s->s_main);
+            for (int w = 0; w < 2; w++) {
+                if (inflight[w]) { std::unique_lock<std::mutex> lk(s->mu); s->cv.wait(lk, [this, w] { return s->job_done[w]; }); }
+                if (s->s_full[w]) cudaStreamSynchronize(s->s_full[w]);
+            }
+            cudaStreamSynchronize(s->s_main);
             s->eng->stream = st;
         }
-    } restore{s, eng_stream, &inflight};
+    } restore{s, eng_stream, inflight};
     const auto t_start = std::chrono::steady_clock::now();
     auto now_s = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
-    double t_submit = 0.0, t_flight = 0.0;
+    double t_submit[2] = {0.0, 0.0}, t_flight = 0.0, t_busy = 0.0, t_busy_from = 0.0;
     int64_t full_calls = 0, full_chains = 0, cached_calls = 0, cached_chains = 0, rounds = 0;
     std::vector<int> full, cached, slots, st;
     std::vector<double> vals;
@@ -481,20 +498,31 @@ int s_run(apm_sampler* s, const double* theta_init, int n_sample, double* thetas
         for (const SChain& ch : s->chains) k += ch.req != REQ_NONE;
         return k;
     };
-    while (n_pending > 0 || inflight) {
+    auto any_inflight = [&] { return inflight[0] || inflight[1]; };
+    while (n_pending > 0 || any_inflight()) {
         rounds++;
-        int n_cached_req = 0;
-        for (const SChain& ch : s->chains) n_cached_req += (ch.req == REQ_CACHED_NEW || ch.req == REQ_CACHED_ELL);
-        // ---- a finished FULL call is harvested as soon as it is seen (with no CACHED work left: wait for it); its chains are
-        // resumed at once so that those which need another FULL estimate join the next call
-        if (inflight) {
+        int n_cached_req = 0, n_full_req = 0;
+        for (const SChain& ch : s->chains) {
+            n_cached_req += (ch.req == REQ_CACHED_NEW || ch.req == REQ_CACHED_ELL);
+            n_full_req += (ch.req == REQ_FULL || ch.req == REQ_FULL_NEWU);
+        }
+        // ---- finished FULL calls are harvested as soon as they are seen; their chains are resumed at once so that those
+        // which need another FULL estimate join the next call.  With nothing else to do (no CACHED work, and no FULL call
+        // that could be submitted now) the thread sleeps until a call finishes.
+        if (any_inflight()) {
+            const bool free_slot = (J > 1) && !(inflight[0] && inflight[1]);
+            const bool can_submit = free_slot && n_full_req >= std::max(1, s->min_second) && n_full_req >= s->batch_frac * n_pending;
             std::unique_lock<std::mutex> lk(s->mu);
-            if (n_cached_req == 0) s->cv.wait(lk, [s] { return s->job_done; });
-            if (s->job_done) {
-                lk.unlock();
-                inflight = false;
-                t_flight += now_s() - t_submit;
-                FullJob& j = s->job;
+            if (n_cached_req == 0 && !can_submit)
+                s->cv.wait(lk, [&] { return (inflight[0] && s->job_done[0]) || (inflight[1] && s->job_done[1]); });
+            bool done[2] = {inflight[0] && s->job_done[0], inflight[1] && s->job_done[1]};
+            lk.unlock();
+            for (int w = 0; w < 2; w++) {
+                if (!done[w]) continue;
+                inflight[w] = false;
+                t_flight += now_s() - t_submit[w];
+                if (!any_inflight()) t_busy += now_s() - t_busy_from;
+                FullJob& j = s->job[w];
                 if (j.rc != APM_OK) { set_err("FULL call: " + j.err); return j.rc; }
                 for (size_t q = 0; q < j.chains.size(); q++) {
                     SChain& ch = s->chains[j.chains[q]];
@@ -505,22 +533,31 @@ int s_run(apm_sampler* s, const double* theta_init, int n_sample, double* thetas
                 }
             }
         }
-        // ---- submit the next FULL call: enough chains are waiting for one, or nobody has CACHED work left
-        if (!inflight) {
-            full.clear();
-            int n_pend = 0;
-            for (int c = 0; c < B; c++) {
-                const int r = s->chains[c].req;
-                n_pend += r != REQ_NONE;
-                if (r == REQ_FULL || r == REQ_FULL_NEWU) full.push_back(c);
-            }
-            if (!full.empty() && ((double)full.size() >= s->batch_frac * n_pend || (int)full.size() == n_pend)) {
-                APM_TRY(s_submit_full(s, full));
-                for (int c : full) s->chains[c].req = REQ_NONE;     // in flight: not pending
-                inflight = true;
-                t_submit = now_s();
-                full_calls++;
-                full_chains += (int64_t)full.size();
+        // ---- submit the next FULL call to a free job slot: enough chains are waiting for one, or nobody has CACHED work left.
+        // A second call beside one in flight is only worth its fixed cost with at least min_second chains.
+        {
+            int w = -1;
+            for (int q = 0; q < J; q++)
+                if (!inflight[q]) { w = q; break; }
+            if (w >= 0) {
+                full.clear();
+                int n_pend = 0;
+                for (int c = 0; c < B; c++) {
+                    const int r = s->chains[c].req;
+                    n_pend += r != REQ_NONE;
+                    if (r == REQ_FULL || r == REQ_FULL_NEWU) full.push_back(c);
+                }
+                const bool alone = !any_inflight();
+                const bool enough = (double)full.size() >= s->batch_frac * n_pend || (int)full.size() == n_pend;
+                if (!full.empty() && enough && (alone || (int)full.size() >= s->min_second)) {
+                    APM_TRY(s_submit_full(s, full, w));
+                    for (int c : full) s->chains[c].req = REQ_NONE;     // in flight: not pending
+                    if (alone) t_busy_from = now_s();
+                    inflight[w] = true;
+                    t_submit[w] = now_s();
+                    full_calls++;
+                    full_chains += (int64_t)full.size();
+                }
             }
         }
         // ---- CACHED requests of the chains that are not in flight
@@ -590,6 +627,7 @@ int s_run(apm_sampler* s, const double* theta_init, int n_sample, double* thetas
     }
     s->stats[0] = (double)full_calls; s->stats[1] = (double)full_chains; s->stats[2] = (double)cached_calls;
     s->stats[3] = (double)cached_chains; s->stats[4] = t_flight; s->stats[5] = now_s(); s->stats[6] = (double)rounds;
+    s->stats[7] = t_busy;      // time with at least one FULL call in flight (stats[4] sums the calls' own durations)
     return APM_OK;
 }
 
@@ -598,17 +636,18 @@ int s_run(apm_sampler* s, const double* theta_init, int n_sample, double* thetas
 extern "C" int apm_sampler_destroy(apm_sampler* s) {
     if (!s) return APM_OK;
     cudaSetDevice(s->device);
-    if (s->worker.joinable()) {
-        {
-            std::lock_guard<std::mutex> lk(s->mu);
-            s->quit = true;
-        }
-        s->cv.notify_all();
-        s->worker.join();
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->quit = true;
     }
+    s->cv.notify_all();
+    for (int w = 0; w < 2; w++)
+        if (s->worker[w].joinable()) s->worker[w].join();
     if (s->s_main) cudaStreamSynchronize(s->s_main);
-    if (s->s_full) cudaStreamSynchronize(s->s_full);
+    for (int w = 0; w < 2; w++)
+        if (s->s_full[w]) cudaStreamSynchronize(s->s_full[w]);
     if (s->comp) apm_destroy(s->comp);
+    if (s->eng2) apm_destroy(s->eng2);
     if (s->dU) cudaFree(s->dU);
     if (s->dV) cudaFree(s->dV);
     if (s->dCS) cudaFree(s->dCS);
@@ -616,9 +655,11 @@ extern "C" int apm_sampler_destroy(apm_sampler* s) {
     if (s->dIdx) cudaFree(s->dIdx);
     if (s->hIdx) cudaFreeHost(s->hIdx);
     if (s->hCS) cudaFreeHost(s->hCS);
-    if (s->ev_full_ready) cudaEventDestroy(s->ev_full_ready);
+    for (int w = 0; w < 2; w++) {
+        if (s->ev_full_ready[w]) cudaEventDestroy(s->ev_full_ready[w]);
+        if (s->s_full[w]) cudaStreamDestroy(s->s_full[w]);
+    }
     if (s->s_main) cudaStreamDestroy(s->s_main);
-    if (s->s_full) cudaStreamDestroy(s->s_full);
     delete s;
     return APM_OK;
 }
@@ -655,6 +696,11 @@ extern "C" int apm_sampler_create(apm_ctx* ctx, int method, int n_chains, int n_
     s->slice_width = slice_width;
     s->max_slice_iters = max_slice_iters > 0 ? max_slice_iters : 1000;
     if (getenv("APM_SAMPLER_BATCH_FRAC") && atof(getenv("APM_SAMPLER_BATCH_FRAC")) > 0) s->batch_frac = atof(getenv("APM_SAMPLER_BATCH_FRAC"));
+    // FULL calls in flight at once (1 or 2) and the smallest call worth starting beside another one
+    // (default 1: two persistent factorisations in flight do not share the SMs' CTA slots elastically -- measured +-2 %)
+    s->n_jobs = (getenv("APM_SAMPLER_JOBS") && atoi(getenv("APM_SAMPLER_JOBS")) == 2) ? 2 : 1;
+    s->min_second = std::max(8, n_chains / 5);
+    if (getenv("APM_SAMPLER_MIN_SECOND") && atoi(getenv("APM_SAMPLER_MIN_SECOND")) > 0) s->min_second = atoi(getenv("APM_SAMPLER_MIN_SECOND"));
     const size_t B = n_chains;
     const bool ess = method == APM_METHOD_ESS_MH || method == APM_METHOD_ESS_RDSS;
     bool ok = cudaMalloc(&s->dU, sizeof(double) * B * s->ubs) == cudaSuccess &&
@@ -665,8 +711,10 @@ extern "C" int apm_sampler_create(apm_ctx* ctx, int method, int n_chains, int n_
               cudaMallocHost(&s->hIdx, sizeof(int) * IDX_SETS * 4 * B) == cudaSuccess &&
               cudaMallocHost(&s->hCS, sizeof(double) * 2 * B) == cudaSuccess &&
               cudaStreamCreateWithFlags(&s->s_main, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&s->s_full, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&s->ev_full_ready, cudaEventDisableTiming) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->s_full[0], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->s_full[1], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->ev_full_ready[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->ev_full_ready[1], cudaEventDisableTiming) == cudaSuccess &&
               cudaMemcpy(s->dSeeds, seeds, sizeof(unsigned long long) * B, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         set_err(std::string("apm_sampler_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -678,7 +726,14 @@ extern "C" int apm_sampler_create(apm_ctx* ctx, int method, int n_chains, int n_
         apm_sampler_destroy(s);
         return rc;
     }
-    s->worker = std::thread(s_worker, s);
+    if (s->n_jobs > 1) {
+        rc = create_full_companion(ctx, n_chains, n_imp, &s->eng2);
+        if (rc != APM_OK) {
+            apm_sampler_destroy(s);
+            return rc;
+        }
+    }
+    for (int w = 0; w < s->n_jobs; w++) s->worker[w] = std::thread(s_worker, s, w);
     *out = s;
     return APM_OK;
 }

@@ -409,6 +409,9 @@ __global__ void k_symv_reduce(const double* __restrict__ direct, const double* _
 // explicit (L_kk^{-1})^T blocks written by k_chol_step (B = I + W^1/2 K W^1/2 has eigenvalues >= 1, so its
 // diagonal blocks are well conditioned), which turns every step into coalesced, fully parallel mat-vecs.
 // dynamic smem: w[np] + rhs[64] + part[4][64]
+// skip_forward: w = L^-1 t is already in nv.s (forward substitution fused into the factorisation, chol_flow.cuh): only the
+// backward half runs (L is read once instead of twice).
+template <bool SKIP_FWD>
 __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, long long l_bs, int ld, int nb,
                                                const double* __restrict__ LinvT, long long inv_bs, NewtonVecs nv) {
     extern __shared__ __align__(16) double smem[];
@@ -422,9 +425,10 @@ __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, lon
     const double* Ib = LinvT + (long long)b * inv_bs;
     const long long o = (long long)b * nv.vs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < np; i += 256) w[i] = nv.t[o + i];
+    for (int i = tid; i < np; i += 256) w[i] = SKIP_FWD ? nv.s[o + i] : nv.t[o + i];
     __syncthreads();
     // ---- forward: L w = t
+    if (!SKIP_FWD)
     for (int kb = 0; kb < nb; kb++) {
         // rhs = t_k - L[k, 0:k] w[0:k]; warp handles 8 rows at once (independent loads in flight)
         const int kcols = kb * 64;
@@ -468,12 +472,28 @@ __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, lon
             double a0 = 0.0, a1 = 0.0;
             const int r_end = np;
             const double* col = Lb + kb * 64 + cg * 2;
+            if (SKIP_FWD) {
+                // backward-only variant: a pure latency chain of 12 column-block reads -- the 8 rows a thread reads of every
+                // 64-row block are issued together (the trip count is a multiple of 8 by construction)
+                for (int ib = kb + 1; ib < nb; ib++) {
+                    double2 m[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) m[q] = *reinterpret_cast<const double2*>(col + (size_t)(ib * 64 + q * 8 + rg) * ld);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const double sr = w[ib * 64 + q * 8 + rg];
+                        a0 = fma(m[q].x, sr, a0);
+                        a1 = fma(m[q].y, sr, a1);
+                    }
+                }
+            } else {
 #pragma unroll 4
-            for (int r = (kb + 1) * 64 + rg; r < r_end; r += 8) {
-                const double2 m = *reinterpret_cast<const double2*>(col + (size_t)r * ld);
-                const double sr = w[r];
-                a0 = fma(m.x, sr, a0);
-                a1 = fma(m.y, sr, a1);
+                for (int r = (kb + 1) * 64 + rg; r < r_end; r += 8) {
+                    const double2 m = *reinterpret_cast<const double2*>(col + (size_t)r * ld);
+                    const double sr = w[r];
+                    a0 = fma(m.x, sr, a0);
+                    a1 = fma(m.y, sr, a1);
+                }
             }
             part[rg * 64 + cg * 2] = a0;
             part[rg * 64 + cg * 2 + 1] = a1;

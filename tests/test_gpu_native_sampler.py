@@ -71,6 +71,23 @@ def test_native_sampler_trace_depends_on_the_seed_only():
     assert np.std(full['thetas'][:, -1, 0]) > 0
 
 
+def test_native_sampler_two_full_calls_in_flight_give_the_same_chains(monkeypatch):
+    """APM_SAMPLER_JOBS=2: a second FULL call (companion context with full workspaces on the same cache slots) may start
+    while one is in flight.  Scheduling only: every chain's trace, counters and operation counts are unchanged."""
+    X, y, th = synth.make_dataset(96, 3, seed=2)
+    seeds = [300 + c for c in range(20)]
+    theta_init = np.tile(th, (20, 1)) + 0.2 * np.random.RandomState(3).normal(size=(20, 4))
+    one, s1 = _run(X, y, 'ard', 4, 'ess+rdss', seeds, 8, theta_init, 40, 'native')
+    monkeypatch.setenv('APM_SAMPLER_JOBS', '2')
+    monkeypatch.setenv('APM_SAMPLER_MIN_SECOND', '2')
+    two, s2 = _run(X, y, 'ard', 4, 'ess+rdss', seeds, 8, theta_init, 40, 'native')
+    assert np.all(two['failed'] == 0)
+    assert np.array_equal(one['thetas'], two['thetas'])
+    for k in ('n_reject', 'n_full', 'n_cached', 'n_cubic_ops'):
+        assert np.array_equal(one[k], two[k]), k
+    assert s2['full_chains'] == s1['full_chains'] and s2['full_calls'] >= s1['full_calls']
+
+
 def test_native_sampler_headline_shape_runs():
     X, y, th = synth.make_dataset(768, 8, seed=0)
     B, N = 48, 64

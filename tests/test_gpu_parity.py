@@ -299,6 +299,39 @@ def test_hybrid_newton_matches_reference_form_and_is_batch_independent():
     ref_eng.close()
 
 
+def test_fused_forward_substitution_and_fused_transpose_match_the_separate_kernels():
+    """k_chol_flow's diagonal tasks also run the forward half of the Newton step's cho_solve (lpa.py:94) and the M'
+    factorisations also store V (the anti-transposed factor the importance-sampling tail reads).  Both are the same
+    arithmetic as the separate kernels they replace (k_trsv2's forward half, k_antitranspose) up to the summation order of
+    the 64-column partial sums: same iteration counts, estimates and caches; V itself is bit-identical."""
+    n, D, N, B = 330, 5, 9, 24                     # n not a multiple of 64: padded rows in the last block
+    X, y, th = synth.make_dataset(n, D, seed=4)
+    rs = np.random.RandomState(8)
+    thetas = th[None] + 0.7 * rs.normal(size=(B, D + 1))
+    u = rs.normal(size=(B, n, N))
+    u2 = rs.normal(size=(B, n, N))
+    kw = dict(kernel='ard', max_chains=B, n_slots=B, max_nimp=N)
+    out = {}
+    for name, env in (('default', {}), ('no_fwd', {'APM_NO_FUSED_FWD': '1'}), ('no_vt', {'APM_NO_FUSED_VT': '1'}),
+                      ('neither', {'APM_NO_FUSED_FWD': '1', 'APM_NO_FUSED_VT': '1'})):
+        eng = _engine_with_env(env, X, y, **kw)
+        val, ops, st = eng.estimate_full(thetas, u, np.arange(B))
+        cval, _ = eng.estimate_cached(np.arange(B), u2)
+        out[name] = (val, ops, st, cval, eng.slot_export(5))
+        eng.close()
+    val, ops, st, cval, (Kc, Cc, f, ld) = out['default']
+    assert np.all(st == 0) and len(set(ops.tolist())) > 1
+    for name in ('no_fwd', 'no_vt', 'neither'):
+        v2, o2, s2, c2, (K2, C2, f2, ld2) = out[name]
+        assert np.array_equal(o2, ops) and np.all(s2 == 0), name
+        assert np.max(np.abs(v2 - val) / np.abs(val)) < 1e-12, name
+        assert np.max(np.abs(c2 - cval) / np.abs(cval)) < 1e-12, name
+        assert np.max(np.abs(C2 - Cc)) < 1e-11 * np.max(np.abs(Cc)) and np.max(np.abs(f2 - f)) < 1e-11, name
+    # the transposed store changes no arithmetic at all
+    assert np.array_equal(out['no_vt'][0], val) and np.array_equal(out['no_vt'][3], cval)
+    assert np.array_equal(out['neither'][0], out['no_fwd'][0])
+
+
 def test_device_resident_u_and_slot_roundtrip():
     import torch
     X, y, th = synth.make_dataset(150, 4, seed=9)
