@@ -540,6 +540,11 @@ def run_gpu_arm(args):
         all_logml = torch.cat(gathered).cpu().numpy()
     else:
         all_logml = last.cpu().numpy()
+
+    # ---- one full-batch launch of the plain factorisation, timed alone (chol(K) of the current K matrices): the kernel without
+    # the Newton-round extras (fused forward substitution, M' accumulation, V store) that the k_chol family's average includes
+    plain_ms = eng.dev_chol_bench(B, reps=5, mode=0) if rank == 0 else None
+    fused_fwd = os.environ.get('APM_NO_FUSED_FWD') is None
     eng.close()
 
     configs = None if args.no_configs else run_configs(D_, rank, args.quick_configs)
@@ -567,12 +572,13 @@ def run_gpu_arm(args):
             'k_build_K': chains_done * 8. * n2,
             # triangular mat-vecs of the M-space Newton rounds (L_K^T b and L_K mu~) + mu~ = L_K^T a of the covariance phase
             'k_matvec': syrk_units * 2. * tri,
-            # s = L^-T L^-1 t: the factor is read twice per Newton iteration (forward + backward substitution)
-            'k_trsv2': iters_prof * 2. * tri,
+            # s = L^-T L^-1 t: the forward substitution runs inside k_chol_flow's diagonal tasks, k_trsv2 reads the factor once
+            # (backward substitution) plus the nb explicit 64 x 64 inverse diagonal blocks
+            'k_trsv2': iters_prof * (tri + (n + 63) // 64 * 64. * 64. * 8.) * (1. if fused_fwd else 2.),
             # k_is_logw reads F, Zf, U^T (3 x 8 n N) per chain; the log-sum-exp stage is O(N)
             'k_is_epilogue': chains_done * 24. * n * N,
-            # u[n][N] -> U^T[Npad][np] (read + write) and the anti-transpose L' -> V of the factored cache (lower blocks, read + write)
-            'k_transpose_u': chains_done * (16. * n * N + 2. * tri),
+            # u[n][N] -> U^T[Npad][np] (read + write); the anti-transposed factor V of the cache is written by k_chol_flow<true> itself
+            'k_transpose_u': chains_done * 16. * n * N,
             # O(n) vector kernels: prep reads f, y and writes W, W^1/2, b, t; finish reads f', f and writes f (9 vectors / iteration)
             'k_newton_vec': iters_prof * 9. * 8. * n,
         }
@@ -609,6 +615,12 @@ def run_gpu_arm(args):
             'traffic': traffic, 'traffic_source': traffic_src,
             'algorithmic_bytes_per_launch': B * 2. * tri,
             'achieved_per_launch_gflop': flops[dom] / d['launches'] / 1e9,
+            # the same kernel as ONE plain full-batch factorisation (chol K of all chains) timed alone with CUDA events, 5 repetitions
+            'plain_full_batch_launch': {'ms': plain_ms, 'achieved': B * n3 / 3. / (plain_ms * 1e-3) / 1e12, 'unit': 'TFLOP/s',
+                                        'frac': B * n3 / 3. / (plain_ms * 1e-3) / 1e12 / peak_dmma,
+                                        'note': 'the family figure above averages every k_chol_flow launch of the step: Newton rounds with the fused '
+                                                'forward substitution and inverse diagonal blocks, the M\' rounds (accumulation from L_K + second, '
+                                                'anti-transposed store), straggler rounds of a few chains and empty launches'},
             'avg_launch_ms': d['ms_total'] / d['launches'],
             'measured': 'CUDA events around every launch of a second pass of the same %d steps, stream overlap off '
                         '(%.2f ms/step; the timed `value` pass runs with the chol(K) / M-space overlap on and no per-launch events)'

@@ -221,8 +221,8 @@ int apm_profile_read(apm_ctx* ctx, int max_entries, char* names, double* ms, int
 int64_t apm_launch_count(apm_ctx* ctx, int reset);
 
 /* Work the DMMA kernel families actually executed since creation / the last reset, in units of n^3/3 flops per chain:
- * out[0] = chain-Choleskys factored by k_chol_* (masked-out chains and the factorisations the hybrid Newton
- * iteration skips are not counted), out[1] = M' = I + Y'Y'^T builds by k_syrk_rev.  bench.py's per-kernel roofline
+ * out[0] = chain-Choleskys factored by k_chol_flow (masked-out chains and the factorisations the hybrid Newton
+ * iteration skips are not counted), out[1] = M' = I + L_K^T W L_K builds accumulated inside k_chol_flow<true>.  bench.py's per-kernel roofline
  * uses these instead of the reference's nominal operation count (lpa.py:92, 111-112; est.py:206, 209). */
 int apm_work_count(apm_ctx* ctx, int64_t* out, int reset);
 
@@ -254,8 +254,11 @@ int apm_sampler_create(apm_ctx* ctx, int method, int n_chains, int n_imp, const 
  * counts_out HOST [n_chains][6]: rejected u-updates, rejected theta-updates, n_cubic_ops, FULL estimates, CACHED
  * estimates, failure status (0 = ok, else the chain_status code that stopped the chain). */
 int apm_sampler_run(apm_sampler* s, const double* theta_init, int n_sample, double* thetas_out, int64_t* counts_out);
-/* Scheduling diagnostics of the last run: out8 = FULL calls, chains in them, CACHED calls, chains in them, seconds with a
- * FULL call in flight, seconds in total, scheduler rounds, 0. */
+/* Scheduling diagnostics of the last run: out8 = FULL calls, chains in them, CACHED calls, chains in them, summed
+ * durations of the FULL calls [s], seconds in total, scheduler rounds, seconds with at least one FULL call in flight.
+ * Environment (read by apm_sampler_create): APM_SAMPLER_BATCH_FRAC (share of the waiting chains that must ask for a FULL
+ * estimate before a call is started, 0.5), APM_SAMPLER_JOBS=2 (a second FULL call may start beside one in flight),
+ * APM_SAMPLER_MIN_SECOND (smallest such second call). */
 int apm_sampler_stats(apm_sampler* s, double* out8);
 int apm_sampler_destroy(apm_sampler* s);
 

@@ -13,6 +13,6 @@ SHORT="python bench.py --steps 2 --warmup 1 --no-configs --no-cpu-baseline --apm
 $SHORT > $O/short_$TAG.json 2> $O/short_$TAG.err || { echo "short bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/launches_$TAG.csv $SHORT > $O/ncu1_$TAG.log 2>&1
 # the Cholesky launches of one FULL step (skip the warm-up step's): chol(K), Newton rounds, chol(M')
-ncu --set full --clock-control none --import-source on -k regex:k_chol_flow -s 12 -c 6 -o $O/prof_${TAG}_full -f $SHORT > $O/ncu2_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:^k_chol_flow$ -s 10 -c 10 -o $O/prof_${TAG}_full -f $SHORT > $O/ncu2_$TAG.log 2>&1
 ncu -i $O/prof_${TAG}_full.ncu-rep --page raw --csv > $O/prof_${TAG}_full_raw.csv 2>/dev/null
 ls -la $O | tail -12
