@@ -647,6 +647,7 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     // the M' factorisations also leave V = anti-transpose of L' in the slot's L_C buffer (what the importance-sampling tail reads)
     q.vt_out = (syrk_slots && c->fused_vt) ? c->dSlotLC : nullptr; q.vt_bs = (long long)c->mat;
     q.fwd_t = fwd ? c->dVec[V_T] : nullptr; q.fwd_y = c->dVec[V_S]; q.fwd_bs = c->np; q.yprog = c->dFlowYProg[set];
+    q.lt_b = c->dVec[V_B];        // <true, true>: the diagonal tasks build t' = P L_K^T b themselves
     const int total_tasks = B * c->nb * (c->nb + 1) / 2;
     prof_begin(c, KID_MISC);
     k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb, c->dWork,
@@ -791,11 +792,14 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
                 CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_lk_done, 0));
                 lk_pending = false;
             }
-            // t' = reversed L_K^T b
-            prof_begin(c, KID_MATVEC);
-            k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, nv.bvec, c->np,
-                                                                nv.t, c->np, nullptr, c->dStatus, maskM, 1);
-            APM_TRY(check_launch(c, "k_lt_matvec"));
+            // t' = reversed L_K^T b: with the fused forward substitution the factorisation's diagonal tasks accumulate it from the
+            // L_K boxes they stream for M'; otherwise by its own kernel
+            if (!c->fused_fwd) {
+                prof_begin(c, KID_MATVEC);
+                k_lt_matvec<<<dim3(c->nb, B), 256, 0, c->stream>>>(c->dSlotLK, (long long)c->mat, dSlots, c->np, c->nb, nv.bvec, c->np,
+                                                                    nv.t, c->np, nullptr, c->dStatus, maskM, 1);
+                APM_TRY(check_launch(c, "k_lt_matvec"));
+            }
             // L' = chol(M'), M' = P (I + L_K^T W L_K) P built inside the factorisation from L_K and W (never stored)
             APM_TRY(run_chol(c, B, nullptr, 0, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
                              nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, dSlots, c->fused_fwd));

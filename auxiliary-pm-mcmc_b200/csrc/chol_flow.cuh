@@ -44,7 +44,7 @@ constexpr int CF_STAGES = APM_CF_STAGES;
 constexpr int DP_LBLOCKS = 36;                         // lower 8x8 blocks (q >= p) of a 64x64 triangle, block (q,p) at q(q+1)/2 + p
 constexpr int DP_DOUBLES = (DP_LBLOCKS + 8) * 64;      // + inverses of the 8 diagonal 8x8 blocks
 constexpr int DP_BYTES = DP_DOUBLES * 8;               // 22528
-constexpr int CF_CTRL_BYTES = 2048;                  // barriers / task slots / W or y of a stage (first KB) + two right-hand-side blocks
+constexpr int CF_CTRL_BYTES = 2560;                  // barriers / task slots / W or y of a stage (first KB) + two right-hand-side blocks
 constexpr int CF_SMEM_BYTES = 1024 + CF_STAGES * 2 * CF_CHUNK_BYTES + DP_BYTES + CF_CTRL_BYTES;   // 1024: manual alignment slack
 
 __device__ __forceinline__ int dp_block(int q, int p) { return (q * (q + 1) / 2 + p) * 64; }
@@ -132,6 +132,9 @@ struct CholFlowParams {
     // up L_k,0..k-1 y_0..k-1 from the operand chunks it streams anyway and solves its 64 rows with the packed L_kk once the
     // factor is published.  fwd_t: right-hand side, fwd_y: result (both [chain][np], stride fwd_bs), yprog[chain]: finished blocks.
     const double* fwd_t; double* fwd_y; long long fwd_bs; int* yprog;
+    // k_chol_flow<true, true> only: fwd_t is not read -- the right-hand side t' = P L_K^T b is accumulated by the diagonal tasks
+    // from L_K (which they stream for M' anyway) and b = lt_b [chain][np] (stride fwd_bs)
+    const double* lt_b;
     const double* scale; long long scale_bs;
     int add_identity;
     int nb;
@@ -269,9 +272,12 @@ __device__ __forceinline__ void cf_gemm_chunk(CfAcc& acc, const unsigned char* s
 // boxes 0..3 = column block I (A operand), 4..7 = column block K (B operand), plus W_r of the 16 rows.  This warp's output
 // rows m' = 16 warp + 8 mt + g read source column 63 - m' = box 3 - warp, in-box column 15 - 8 mt - g; DMMA kk contracts the
 // rows {2t + (kk & 1) + 8 (kk >> 1)}: their (r & 7) in {0,2,4,6} (+1) spreads the 16 lanes of a half-warp over 16 bank pairs.
-template <bool DIAG>
+// LT (diagonal tasks of a Newton M-space round): the A fragment of a diagonal task is L_K[r][64 K + 63 - n'] for this lane's
+// output index n' = 16 warp + 8 mt + g -- exactly the terms of t'[64 k + n'] = sum_r L_K[r][.] b_r (the reversed L_K^T b, right-hand
+// side of the round's solve): tq[mt] collects them with b_r from sBv (the 16 rows' entries of b), k_lt_matvec is not launched.
+template <bool DIAG, bool LT = false>
 __device__ __forceinline__ void cf_gemm_chunk_tn(CfAcc& acc, const unsigned char* sA, const unsigned char* sB, const double* sW,
-                                                 int warp, int g, int t) {
+                                                 int warp, int g, int t, const double* sBv = nullptr, double* tq = nullptr) {
     const unsigned char* a_box = sA + (3 - warp) * 2048;
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
@@ -282,7 +288,9 @@ __device__ __forceinline__ void cf_gemm_chunk_tn(CfAcc& acc, const unsigned char
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
             const uint32_t mm = (uint32_t)(15 - 8 * mt - g);
-            a[mt] = wk * *reinterpret_cast<const double*>(a_box + row + (((mm >> 1) ^ x) << 4) + ((mm & 1) << 3));
+            const double raw = *reinterpret_cast<const double*>(a_box + row + (((mm >> 1) ^ x) << 4) + ((mm & 1) << 3));
+            a[mt] = wk * raw;
+            if (LT) tq[mt] = fma(raw, sBv[kr], tq[mt]);
         }
 #pragma unroll
         for (int nt = 0; nt < 8; nt++)
@@ -428,7 +436,7 @@ __device__ __noinline__ void cf_forward_block(const double* dp, const double* rh
     const int off = g * 8 + 2 * t;
     double tv[8];
 #pragma unroll
-    for (int p = 0; p < 8; p++) tv[p] = tk[p * 8 + g];
+    for (int p = 0; p < 8; p++) tv[p] = tk ? tk[p * 8 + g] : 0.0;
     double y0[8], y1[8];      // y_q[2t], y_q[2t+1] of the finished blocks
 #pragma unroll
     for (int p = 0; p < 8; p++) {
@@ -494,9 +502,11 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
     double* red = reinterpret_cast<double*>(ctrl + 16 * CF_STAGES + 48 + 2 * sizeof(CfTask));   // 4 partial log-dets
     double* wst = reinterpret_cast<double*>(ctrl + 512);                                         // W_r of a TN stage: [stage][16]
     const uint32_t wst_u = ctrl_u + 512;
-    double* fw_rhs = reinterpret_cast<double*>(ctrl + 1024);                                     // [2][64]: right-hand side block of a diag task (by task parity)
-    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= 512 && 512 + CF_STAGES * 128 <= 1024 && 1024 + 2 * 64 * 8 <= CF_CTRL_BYTES,
-                  "control block too small");
+    double* bst = reinterpret_cast<double*>(ctrl + 1024);                                        // b_r of a TN stage: [stage][16]
+    const uint32_t bst_u = ctrl_u + 1024;
+    double* fw_rhs = reinterpret_cast<double*>(ctrl + 1536);                                     // [2][64]: right-hand side block of a diag task (by task parity)
+    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= 512 && 512 + CF_STAGES * 128 <= 1024 && 1024 + CF_STAGES * 128 <= 1536 &&
+                  1536 + 2 * 64 * 8 <= CF_CTRL_BYTES, "control block too small");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -563,13 +573,15 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                 for (int c = 0; c < 4 * (k + 1); c++, it++) {
                     const uint32_t s = it % CF_STAGES;
                     mbar_wait(bar_empty + 8 * s, ((it / CF_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(bar_full + 8 * s, (dg ? CF_CHUNK_BYTES : 2 * CF_CHUNK_BYTES) + 128);
+                    const bool lt = FWD && dg;
+                    mbar_expect_tx(bar_full + 8 * s, (dg ? CF_CHUNK_BYTES : 2 * CF_CHUNK_BYTES) + 128 + (lt ? 128 : 0));
                     const uint32_t st = ring_u + s * 2 * CF_CHUNK_BYTES;
                     for (int j = 0; j < 4; j++) {
                         tma_load_2d(st + CF_CHUNK_BYTES + j * 2048, &tml, K * TB + 16 * j, lrow + 16 * c, bar_full + 8 * s);
                         if (!dg) tma_load_2d(st + j * 2048, &tml, I * TB + 16 * j, lrow + 16 * c, bar_full + 8 * s);
                     }
                     bulk_load_1d(wst_u + s * 128, wsrc + 16 * c, 128, bar_full + 8 * s);
+                    if (lt) bulk_load_1d(bst_u + s * 128, p.lt_b + (long long)b * p.fwd_bs + K * TB + 16 * c, 128, bar_full + 8 * s);
                 }
             }
             if (type == 0) {
@@ -635,6 +647,7 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
         int* prog = p.progress + (size_t)b * nb;
         const bool diag = type != 0;
         CfAcc acc;
+        double tq[2] = {0.0, 0.0};       // <true, true>: this lane's share of t'[64 k + 16 warp + 8 mt + g]
         if (!SYRK) {
             // ---- source tile A_ik (two stages of the ring)
             const double* rs = sc ? sc + i * TB : nullptr;
@@ -666,9 +679,14 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                 const uint32_t s = it % CF_STAGES;
                 mbar_wait(bar_full + 8 * s, (it / CF_STAGES) & 1);
                 const unsigned char* st = ring + s * 2 * CF_CHUNK_BYTES;
-                if (diag) cf_gemm_chunk_tn<true>(acc, st + CF_CHUNK_BYTES, st + CF_CHUNK_BYTES, wst + s * 16, warp, g, t);
-                else cf_gemm_chunk_tn<false>(acc, st, st + CF_CHUNK_BYTES, wst + s * 16, warp, g, t);
-                cf_release_stage(bar_empty + 8 * s, cf_acc_dep(acc), p.zero, lane);
+                uint32_t dep = 0;
+                if (diag) {
+                    cf_gemm_chunk_tn<true, FWD>(acc, st + CF_CHUNK_BYTES, st + CF_CHUNK_BYTES, wst + s * 16, warp, g, t, bst + s * 16, tq);
+                    if (FWD) dep = (uint32_t)__double2hiint(tq[0]) | (uint32_t)__double2hiint(tq[1]);
+                } else {
+                    cf_gemm_chunk_tn<false>(acc, st, st + CF_CHUNK_BYTES, wst + s * 16, warp, g, t);
+                }
+                cf_release_stage(bar_empty + 8 * s, cf_acc_dep(acc) | dep, p.zero, lane);
             }
         }
         if (!diag) {
@@ -713,6 +731,7 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
                 }
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++) {
+                    if (SYRK) ys[mt] += tq[mt];      // right-hand side entries accumulated with M' (same index as the row)
                     ys[mt] += __shfl_xor_sync(0xffffffffu, ys[mt], 1);
                     ys[mt] += __shfl_xor_sync(0xffffffffu, ys[mt], 2);
                 }
@@ -782,7 +801,8 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
             if (fwd && warp == 0) {
                 // y_k = L_kk^-1 rhs_k: off the factorisation's critical path (L_kk is already published); the next diagonal
                 // task of this chain waits for yprog before it streams y_k
-                cf_forward_block(dp, fw_rhs + (n & 1) * 64, p.fwd_t + (long long)b * p.fwd_bs + k * TB, p.fwd_y + (long long)b * p.fwd_bs + k * TB, g, t);
+                cf_forward_block(dp, fw_rhs + (n & 1) * 64, SYRK ? nullptr : p.fwd_t + (long long)b * p.fwd_bs + k * TB,
+                                 p.fwd_y + (long long)b * p.fwd_bs + k * TB, g, t);
                 fence_proxy_async_global();         // read by other CTAs' bulk copies
                 __syncwarp();
                 if (lane == 0) cf_st_release(p.yprog + b, k + 1);

@@ -703,6 +703,9 @@ extern "C" int apm_sampler_create(apm_ctx* ctx, int method, int n_chains, int n_
     if (getenv("APM_SAMPLER_MIN_SECOND") && atoi(getenv("APM_SAMPLER_MIN_SECOND")) > 0) s->min_second = atoi(getenv("APM_SAMPLER_MIN_SECOND"));
     const size_t B = n_chains;
     const bool ess = method == APM_METHOD_ESS_MH || method == APM_METHOD_ESS_RDSS;
+    int prio_lo = 0, prio_hi = 0;      // numerically lower = higher priority
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (getenv("APM_SAMPLER_NO_PRIORITY")) prio_hi = prio_lo = 0;
     bool ok = cudaMalloc(&s->dU, sizeof(double) * B * s->ubs) == cudaSuccess &&
               (!ess || cudaMalloc(&s->dV, sizeof(double) * B * s->ubs) == cudaSuccess) &&
               cudaMalloc(&s->dCS, sizeof(double) * 2 * B) == cudaSuccess &&
@@ -710,9 +713,11 @@ extern "C" int apm_sampler_create(apm_ctx* ctx, int method, int n_chains, int n_
               cudaMalloc(&s->dIdx, sizeof(int) * IDX_SETS * 4 * B) == cudaSuccess &&
               cudaMallocHost(&s->hIdx, sizeof(int) * IDX_SETS * 4 * B) == cudaSuccess &&
               cudaMallocHost(&s->hCS, sizeof(double) * 2 * B) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&s->s_main, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&s->s_full[0], cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&s->s_full[1], cudaStreamNonBlocking) == cudaSuccess &&
+              // the FULL calls bound the run, the CACHED calls only have to be back before the next FULL call starts: blocks of
+              // the FULL streams are scheduled first whenever both have work pending
+              cudaStreamCreateWithPriority(&s->s_main, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&s->s_full[0], cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&s->s_full[1], cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_full_ready[0], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&s->ev_full_ready[1], cudaEventDisableTiming) == cudaSuccess &&
               cudaMemcpy(s->dSeeds, seeds, sizeof(unsigned long long) * B, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -731,6 +736,16 @@ extern "C" int apm_sampler_create(apm_ctx* ctx, int method, int n_chains, int n_
         if (rc != APM_OK) {
             apm_sampler_destroy(s);
             return rc;
+        }
+    }
+    // the engines' auxiliary streams (chol K, M-space form of a mixed Newton round) belong to the FULL calls: same priority
+    for (apm_ctx* e : {s->eng, s->eng2}) {
+        if (!e || prio_hi == prio_lo) continue;
+        cudaStream_t hi = nullptr;
+        if (cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, prio_hi) == cudaSuccess) {
+            cudaStreamSynchronize(e->aux_stream);
+            cudaStreamDestroy(e->aux_stream);
+            e->aux_stream = hi;
         }
     }
     for (int w = 0; w < s->n_jobs; w++) s->worker[w] = std::thread(s_worker, s, w);

@@ -146,7 +146,7 @@ int main(int argc, char** argv) {
             p.nb = nb; p.logdet_parts = dld1; p.logdet_stride = nb; p.logdet_idx = nullptr;
             p.inv_out = (scaled || syrk) ? dinv1 : nullptr; p.inv_bs = (long long)nb * 4096;
             p.status = dstatus; p.fail_code = 5; p.active = variant == 2 ? dactive : nullptr; p.nchains = B;
-            p.counter = dcounter + 4; p.progress = dprogress; p.list = dskip; p.diagpack = ddp; p.vt_out = nullptr; p.vt_bs = 0; p.fwd_t = nullptr; p.fwd_y = nullptr; p.fwd_bs = 0; p.yprog = nullptr;
+            p.counter = dcounter + 4; p.progress = dprogress; p.list = dskip; p.diagpack = ddp; p.vt_out = nullptr; p.vt_bs = 0; p.fwd_t = nullptr; p.fwd_y = nullptr; p.fwd_bs = 0; p.yprog = nullptr; p.lt_b = nullptr;
             p.spin_ns = 64;
             const int total_tasks = B * nb * (nb + 1) / 2;
             int grid = std::min(occ_new * sms, total_tasks);

@@ -11,7 +11,7 @@ iters = int(os.environ.get('ITERS', 60))
 X, y, th = synth.make_dataset(n, D, seed=0)
 for B in [int(b) for b in os.environ.get('B', '256').split(',')]:
     eng = _capi.Engine(X, y, kernel='ard', max_chains=B, n_slots=2 * B, max_nimp=N)
-    cfgs = [(float(f), int(j), int(m2)) for f in os.environ.get('FRACS', '0.5').split(',') for j in os.environ.get('JOBS', '2').split(',')
+    cfgs = [(float(f), int(j), int(m2)) for f in os.environ.get('FRACS', '0.5').split(',') for j in os.environ.get('JOBS', '1').split(',')
             for m2 in (os.environ.get('MIN2', '0').split(',') if int(j) > 1 else ['0'])]
     for frac, jobs, min2 in cfgs:
         os.environ['APM_SAMPLER_BATCH_FRAC'] = str(frac)
