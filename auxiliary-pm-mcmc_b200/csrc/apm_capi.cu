@@ -80,6 +80,7 @@ struct apm_ctx {
     // SYRK + Cholesky of M' (and the chol(B) of that iteration).  APM_NO_HYBRID_NEWTON=1 disables it.
     bool hybrid_newton = true;
     bool fused_fwd = true;              // forward substitution of the Newton solves inside k_chol_flow's diagonal tasks (APM_NO_FUSED_FWD=1: k_trsv2 does both halves)
+    int trsv_cluster_max = 160;         // backward solve by a cluster of 4 CTAs per chain for batches of at most this many chains (APM_TRSV_CLUSTER_MAX; 0: never)
     bool fused_vt = true;               // k_chol_flow<true> also stores V = anti-transpose of L' (APM_NO_FUSED_VT=1: separate k_antitranspose)
     double pred_factor = 0.15;   // measured optimum 0.1-0.2 (profiles/): a missed prediction costs a latency-bound covariance phase
     int *dMaskM = nullptr, *dMaskB = nullptr, *dDoneM = nullptr;
@@ -206,6 +207,7 @@ static int set_kernel_attrs() {
     CU_TRY(cudaFuncSetAttribute(k_build_dK, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU_TRY(cudaFuncSetAttribute(k_trsv2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU_TRY(cudaFuncSetAttribute(k_trsv2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU_TRY(cudaFuncSetAttribute(k_trsv_back_c4, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CU_TRY(cudaFuncSetAttribute(k_is_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     g_attr_done = 1;
     return APM_OK;
@@ -345,6 +347,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->hybrid_newton = getenv("APM_NO_HYBRID_NEWTON") == nullptr;
     c->fused_vt = getenv("APM_NO_FUSED_VT") == nullptr;
     c->fused_fwd = getenv("APM_NO_FUSED_FWD") == nullptr;
+    if (getenv("APM_TRSV_CLUSTER_MAX")) c->trsv_cluster_max = atoi(getenv("APM_TRSV_CLUSTER_MAX"));
     if (getenv("APM_NEWTON_R0") && atoi(getenv("APM_NEWTON_R0")) > 0) c->newton_r0 = atoi(getenv("APM_NEWTON_R0"));
     if (getenv("APM_FNEW_THR")) c->fnew_thr = atof(getenv("APM_FNEW_THR"));
     if (getenv("APM_PRED_FACTOR") && atof(getenv("APM_PRED_FACTOR")) > 0) c->pred_factor = atof(getenv("APM_PRED_FACTOR"));
@@ -726,7 +729,8 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
                                                           hybrid ? c->dDoneM : nullptr, c->dNActive, B);
     APM_TRY(check_launch(c, "k_newton_init"));
     if (hybrid) nv.done_m = c->dDoneM;
-    const size_t trsv_smem = (size_t)(c->np + 64 + 8 * 64) * sizeof(double);
+    const size_t trsv_c4_smem = (size_t)(c->np + 8 * 64 + 64 + 2 * 4 * 64) * sizeof(double);
+    const size_t trsv_smem = (size_t)(c->np + 64 + 32 * 64) * sizeof(double);
     if (trsv_smem > 160 * 1024) {
         set_err("run_newton: n too large for the single-CTA triangular solve");
         return APM_ERR_INVALID;
@@ -770,7 +774,10 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
                              nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB, nullptr, c->fused_fwd));
             // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
             prof_begin(c, KID_TRSV);
-            if (c->fused_fwd)
+            if (c->fused_fwd && B <= c->trsv_cluster_max)     // a batch of about one chain per SM or less: latency-bound, 4 CTAs per chain
+                k_trsv_back_c4<<<4 * B, 256, trsv_c4_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                                        (long long)c->nb * TB * TB, nvB, B);
+            else if (c->fused_fwd)
                 k_trsv2<true><<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
                                                                 (long long)c->nb * TB * TB, nvB);
             else
@@ -805,7 +812,10 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
                              nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, dSlots, c->fused_fwd));
             // s' = M'^-1 t'
             prof_begin(c, KID_TRSV);
-            if (c->fused_fwd)
+            if (c->fused_fwd && B <= c->trsv_cluster_max)     // a batch of about one chain per SM or less: latency-bound, 4 CTAs per chain
+                k_trsv_back_c4<<<4 * B, 256, trsv_c4_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
+                                                                        (long long)c->nb * TB * TB, nvM, B);
+            else if (c->fused_fwd)
                 k_trsv2<true><<<B, 256, trsv_smem, c->stream>>>(c->dLB, (long long)c->mat, c->np, c->nb, c->dInvB,
                                                                 (long long)c->nb * TB * TB, nvM);
             else

@@ -158,21 +158,37 @@ __global__ void k_chol_flow_init(int* counter, int* progress, int* list, const i
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nchains * nb) progress[e] = 0;
     if (yprog && e < nchains) yprog[e] = 0;
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-        int count = 0;
-        for (int b0 = 0; b0 < nchains; b0 += 32) {
-            const int b = b0 + threadIdx.x;
-            const bool on = b < nchains && status[b] == 0 && (!active || active[b]);
-            const unsigned m = __ballot_sync(0xffffffffu, on);
-            if (on) list[count + __popc(m & ((1u << threadIdx.x) - 1u))] = b;
-            count += __popc(m);
-        }
+    if (blockIdx.x != 0) return;
+    // ordered compaction by block 0 (256 threads = 8 warps): every pass handles 256 chains with one round of independent
+    // loads (a single warp walking the chains paid one dependent global load per 32 chains)
+    __shared__ int wcount[8];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nchains; b0 += 256) {
+        const int b = b0 + threadIdx.x;
+        const bool on = b < nchains && status[b] == 0 && (!active || active[b]);
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) wcount[warp] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; w++) off += wcount[w];
+        if (on) list[off + __popc(m & ((1u << lane) - 1u))] = b;
+        __syncthreads();
         if (threadIdx.x == 0) {
-            counter[0] = 0;
-            counter[1] = count;
-            if (work && count) atomicAdd(work, (unsigned long long)count);   // chain-Choleskys executed (work accounting)
-            if (work2 && count) atomicAdd(work2, (unsigned long long)count); // ... and M' builds, when the source is the fused SYRK
+            int t = 0;
+            for (int w = 0; w < 8; w++) t += wcount[w];
+            base += t;
         }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int count = base;
+        counter[0] = 0;
+        counter[1] = count;
+        if (work && count) atomicAdd(work, (unsigned long long)count);   // chain-Choleskys executed (work accounting)
+        if (work2 && count) atomicAdd(work2, (unsigned long long)count); // ... and M' builds, when the source is the fused SYRK
     }
 }
 

@@ -2,6 +2,7 @@
 // single right-hand-side triangular solves, the importance-sampling epilogue, layout helpers.
 #pragma once
 #include <math_constants.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace apm {
@@ -408,7 +409,7 @@ __global__ void k_symv_reduce(const double* __restrict__ direct, const double* _
 // One CTA (256 threads) per chain walks the 64-row blocks of L twice.  The 64x64 diagonal-block solves use the
 // explicit (L_kk^{-1})^T blocks written by k_chol_step (B = I + W^1/2 K W^1/2 has eigenvalues >= 1, so its
 // diagonal blocks are well conditioned), which turns every step into coalesced, fully parallel mat-vecs.
-// dynamic smem: w[np] + rhs[64] + part[4][64]
+// dynamic smem: w[np] + rhs[64] + part[32][64] (k_trsv2<false> uses 8 of the 32)
 // skip_forward: w = L^-1 t is already in nv.s (forward substitution fused into the factorisation, chol_flow.cuh): only the
 // backward half runs (L is read once instead of twice).
 template <bool SKIP_FWD>
@@ -474,7 +475,10 @@ __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, lon
             const double* col = Lb + kb * 64 + cg * 2;
             if (SKIP_FWD) {
                 // backward-only variant: a pure latency chain of 12 column-block reads -- the 8 rows a thread reads of every
-                // 64-row block are issued together (the trip count is a multiple of 8 by construction)
+                // 64-row block are issued together (the trip count is a multiple of 8 by construction).  Summation order
+                // shared with k_trsv_back_c4 (so that the two give the same bits): rows 16 j .. 16 j + 15 of every block go
+                // into sub-sum j (what CTA j of the cluster adds up), the 8 row slots are added per j, then (v0 + v1) + (v2 + v3).
+                double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
                 for (int ib = kb + 1; ib < nb; ib++) {
                     double2 m[8];
 #pragma unroll
@@ -482,9 +486,14 @@ __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, lon
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         const double sr = w[ib * 64 + q * 8 + rg];
-                        a0 = fma(m[q].x, sr, a0);
-                        a1 = fma(m[q].y, sr, a1);
+                        s0[q >> 1] = fma(m[q].x, sr, s0[q >> 1]);
+                        s1[q >> 1] = fma(m[q].y, sr, s1[q >> 1]);
                     }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    part[(j * 8 + rg) * 64 + cg * 2] = s0[j];
+                    part[(j * 8 + rg) * 64 + cg * 2 + 1] = s1[j];
                 }
             } else {
 #pragma unroll 4
@@ -495,14 +504,28 @@ __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, lon
                     a1 = fma(m.y, sr, a1);
                 }
             }
-            part[rg * 64 + cg * 2] = a0;
-            part[rg * 64 + cg * 2 + 1] = a1;
+            if (!SKIP_FWD) {
+                part[rg * 64 + cg * 2] = a0;
+                part[rg * 64 + cg * 2 + 1] = a1;
+            }
         }
         __syncthreads();
         if (tid < 64) {
-            double v = 0.0;
+            double v;
+            if (SKIP_FWD) {
+                double vj[4];
 #pragma unroll
-            for (int q = 0; q < 8; q++) v += part[q * 64 + tid];
+                for (int j = 0; j < 4; j++) {
+                    vj[j] = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) vj[j] += part[(j * 8 + q) * 64 + tid];
+                }
+                v = (vj[0] + vj[1]) + (vj[2] + vj[3]);
+            } else {
+                v = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) v += part[q * 64 + tid];
+            }
             rhs[tid] = w[kb * 64 + tid] - v;
         }
         __syncthreads();
@@ -529,6 +552,109 @@ __global__ void __launch_bounds__(256) k_trsv2(const double* __restrict__ L, lon
         nv.s[o + i] = s;
         nv.a[o + i] = nv.bvec[o + i] - nv.Ws[o + i] * s;
     }
+}
+
+// Backward half of the solve (as k_trsv2<true>) by a CLUSTER of 4 CTAs per chain, for batches of about one chain per SM or
+// less (the sampler's partial FULL calls, small batches): one CTA per chain then pays the latency of 12 dependent steps with a
+// single CTA's loads in flight (141 chains: 0.71 ms per FULL estimate, the cluster: 0.45 ms; 18 chains: 141 vs 74 us per launch).
+// A full batch is bandwidth bound and better off with one CTA per chain (154 against 172 us per launch): the host picks by the
+// batch size (apm_ctx::trsv_cluster_max; launching both as a pair that decides on the device by the number of active chains
+// costs more in empty cluster launches than the straggler rounds gain).  few_max: chains beyond it are not expected.  CTA r of
+// the cluster reads rows 16 r .. 16 r + 15 of every 64-row block of the column block (2 of the 8 row groups), so that all
+// of a step's loads of a thread are independent; the four 64-entry partial sums are exchanged through distributed shared
+// memory (every CTA writes its vector into all four, one cluster barrier per step, buffers alternate by step parity) and
+// every CTA finishes the step redundantly (same summation order in all four: identical s_k everywhere).
+// grid 4 * chains, 256 threads, dynamic smem: w[np] + part[8][64] + rhs[64] + xch[2][4][64]
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(256) k_trsv_back_c4(const double* __restrict__ L, long long l_bs, int ld, int nb,
+                                                                               const double* __restrict__ LinvT, long long inv_bs,
+                                                                               NewtonVecs nv, int few_max) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) double smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int b = blockIdx.x >> 2;
+    const int cr = (int)cluster.block_rank();
+    if (b >= few_max || !nv.active[b] || nv.status[b] != 0) return;      // the same decision in the four CTAs of a cluster
+    const int np = nb * 64;
+    double* w = smem;             // [np]
+    double* part = w + np;        // [8][64]
+    double* rhs = part + 512;     // [64]
+    double* xch = rhs + 64;       // [2][4][64]
+    double* xch_remote[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) xch_remote[q] = cluster.map_shared_rank(xch, q);
+    const double* Lb = L + (long long)b * l_bs;
+    const double* Ib = LinvT + (long long)b * inv_bs;
+    const long long o = (long long)b * nv.vs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < np; i += 256) w[i] = nv.s[o + i];
+    cluster.sync();               // all four CTAs are running (their shared memory may be written) and w is in place
+    const int cgp = tid & 31, rg = tid >> 5;              // column pair, row slot 0..7
+    const int rrow = 16 * cr + rg;                         // this thread's two rows inside every 64-row block: rrow, rrow + 8
+    int par = 0;
+    for (int kb = nb - 1; kb >= 0; kb--, par ^= 1) {
+        {
+            double a0 = 0.0, a1 = 0.0;
+            const double* col = Lb + kb * 64 + cgp * 2;
+            int ib = kb + 1;
+            for (; ib + 3 < nb; ib += 4) {                 // 8 independent loads in flight
+                double2 m[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) m[q] = *reinterpret_cast<const double2*>(col + (size_t)((ib + (q >> 1)) * 64 + rrow + 8 * (q & 1)) * ld);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const double sr = w[(ib + (q >> 1)) * 64 + rrow + 8 * (q & 1)];
+                    a0 = fma(m[q].x, sr, a0);
+                    a1 = fma(m[q].y, sr, a1);
+                }
+            }
+            for (; ib < nb; ib++) {
+                const double2 m0 = *reinterpret_cast<const double2*>(col + (size_t)(ib * 64 + rrow) * ld);
+                const double2 m1 = *reinterpret_cast<const double2*>(col + (size_t)(ib * 64 + rrow + 8) * ld);
+                const double s0 = w[ib * 64 + rrow], s1 = w[ib * 64 + rrow + 8];
+                a0 = fma(m0.x, s0, a0); a1 = fma(m0.y, s0, a1);
+                a0 = fma(m1.x, s1, a0); a1 = fma(m1.y, s1, a1);
+            }
+            part[rg * 64 + cgp * 2] = a0;
+            part[rg * 64 + cgp * 2 + 1] = a1;
+        }
+        __syncthreads();
+        if (tid < 64) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) v += part[q * 64 + tid];
+#pragma unroll
+            for (int q = 0; q < 4; q++) xch_remote[q][(par * 4 + cr) * 64 + tid] = v;
+        }
+        cluster.sync();
+        if (tid < 64) {
+            const double* x = xch + par * 256;
+            rhs[tid] = w[kb * 64 + tid] - ((x[tid] + x[64 + tid]) + (x[128 + tid] + x[192 + tid]));
+        }
+        __syncthreads();
+        {
+            const double* blk = Ib + (size_t)kb * 4096 + (size_t)(warp * 8) * 64;
+            const double r0 = rhs[lane * 2], r1 = rhs[lane * 2 + 1];
+            double acc[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const double2 m = *reinterpret_cast<const double2*>(blk + rr * 64 + lane * 2);
+                acc[rr] = fma(m.x, r0, m.y * r1);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const double v = warp_sum(acc[rr]);
+                if (lane == 0) w[kb * 64 + warp * 8 + rr] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // every CTA holds the whole solution: each writes a quarter
+    for (int i = cr * 256 + tid; i < np; i += 1024) {
+        const double sv = w[i];
+        nv.s[o + i] = sv;
+        nv.a[o + i] = nv.bvec[o + i] - nv.Ws[o + i] * sv;
+    }
+    cluster.sync();               // no CTA exits while another may still write its shared memory (none does after the last step; cheap)
 }
 
 // start of a Newton mode search: every chain active and (hybrid) in the B-space form; n_active = {B, 0, 0}

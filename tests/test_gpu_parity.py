@@ -312,8 +312,10 @@ def test_fused_forward_substitution_and_fused_transpose_match_the_separate_kerne
     u2 = rs.normal(size=(B, n, N))
     kw = dict(kernel='ard', max_chains=B, n_slots=B, max_nimp=N)
     out = {}
+    # + the backward solve by one CTA per chain / by a cluster of 4 CTAs per chain (the default picks by the batch size)
     for name, env in (('default', {}), ('no_fwd', {'APM_NO_FUSED_FWD': '1'}), ('no_vt', {'APM_NO_FUSED_VT': '1'}),
-                      ('neither', {'APM_NO_FUSED_FWD': '1', 'APM_NO_FUSED_VT': '1'})):
+                      ('neither', {'APM_NO_FUSED_FWD': '1', 'APM_NO_FUSED_VT': '1'}),
+                      ('one_cta', {'APM_TRSV_CLUSTER_MAX': '0'}), ('cluster', {'APM_TRSV_CLUSTER_MAX': '1000000'})):
         eng = _engine_with_env(env, X, y, **kw)
         val, ops, st = eng.estimate_full(thetas, u, np.arange(B))
         cval, _ = eng.estimate_cached(np.arange(B), u2)
@@ -321,7 +323,7 @@ def test_fused_forward_substitution_and_fused_transpose_match_the_separate_kerne
         eng.close()
     val, ops, st, cval, (Kc, Cc, f, ld) = out['default']
     assert np.all(st == 0) and len(set(ops.tolist())) > 1
-    for name in ('no_fwd', 'no_vt', 'neither'):
+    for name in ('no_fwd', 'no_vt', 'neither', 'one_cta', 'cluster'):
         v2, o2, s2, c2, (K2, C2, f2, ld2) = out[name]
         assert np.array_equal(o2, ops) and np.all(s2 == 0), name
         assert np.max(np.abs(v2 - val) / np.abs(val)) < 1e-12, name
@@ -330,6 +332,9 @@ def test_fused_forward_substitution_and_fused_transpose_match_the_separate_kerne
     # the transposed store changes no arithmetic at all
     assert np.array_equal(out['no_vt'][0], val) and np.array_equal(out['no_vt'][3], cval)
     assert np.array_equal(out['neither'][0], out['no_fwd'][0])
+    # the two backward-solve kernels share one summation order: the same bits whichever the batch size selects
+    assert np.array_equal(out['cluster'][0], val) and np.array_equal(out['one_cta'][0], val)
+    assert np.array_equal(out['one_cta'][3], cval) and np.array_equal(out['one_cta'][4][2], f)
 
 
 def test_device_resident_u_and_slot_roundtrip():
