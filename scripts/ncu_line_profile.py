@@ -1,8 +1,10 @@
 """Per-source-line stall samples of one kernel: joins the SASS addresses of an .ncu-rep source page with the line table of
-the binary (nvdisasm -g).  Usage: ncu_line_profile.py <rep> <binary-or-so> <kernel-substring> [top]"""
+the binary (nvdisasm -g).  Usage: ncu_line_profile.py <rep> <binary-or-so> <kernel-substring> [top] [launch]
+(launch: index of the launch inside a report that holds several, default 0)"""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 rep, binary, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+launch = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(binary)], cwd=tmp, capture_output=True)
 dis = ''
@@ -26,9 +28,11 @@ for ln in dis.splitlines():
         off2line[int(m.group(1), 16)] = cur
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
+his = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+hi = his[launch]
+end = his[launch + 1] - 1 if launch + 1 < len(his) else len(rows)
 hdr = rows[hi]; idx = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
+data = [r for r in rows[hi + 1:end] if len(r) >= len(hdr) and r[0] != 'Address']
 num = lambda x: int(x) if x.isdigit() else 0
 base = min(int(r[idx['Address']], 16) for r in data)
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
