@@ -580,8 +580,9 @@ def run_gpu_arm(args):
         }
         hbm_bytes = {  # algorithmic bytes of the bandwidth-bound families over the roofline pass
             'k_build_K': chains_done * 8. * n2,
-            # triangular mat-vecs of the M-space Newton rounds (L_K^T b and L_K mu~) + mu~ = L_K^T a of the covariance phase
-            'k_matvec': syrk_units * 2. * tri,
+            # triangular mat-vec of the M-space Newton rounds: f' = L_K mu~ (k_l_matvec_rev); the other one, t' = P L_K^T b, is
+            # accumulated inside k_chol_flow<true, true> unless the fused forward substitution is switched off
+            'k_matvec': syrk_units * tri * (1. if fused_fwd else 2.),
             # s = L^-T L^-1 t: the forward substitution runs inside k_chol_flow's diagonal tasks, k_trsv2 reads the factor once
             # (backward substitution) plus the nb explicit 64 x 64 inverse diagonal blocks
             'k_trsv2': iters_prof * (tri + (n + 63) // 64 * 64. * 64. * 8.) * (1. if fused_fwd else 2.),
