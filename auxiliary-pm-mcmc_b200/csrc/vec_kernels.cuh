@@ -47,13 +47,27 @@ __global__ void __launch_bounds__(256) k_build_K(KBuildParams p) {
     double* Ts = XjT + 64 * D;            // [64][65] mirror staging
     double* prm = Ts + 64 * VSP;          // [2D+1]
     const int tid = threadIdx.x;
-    for (int e = tid; e < 64 * D; e += 256) {
-        const int r = e / D, k = e % D;
-        Xi[e] = p.X[(size_t)(ti * 64 + r) * D + k];
-        XjT[k * 64 + r] = p.X[(size_t)(tj * 64 + r) * D + k];
+    // The 64 rows of X a tile needs are contiguous in the row-major, row-padded X: two bulk copies (cp.async.bulk,
+    // SASS UBLKCP.S.G) onto an mbarrier bring them in -- X_i where it is used, X_j through the (still unused) mirror staging
+    // area, from where it is transposed so that the feature loop reads it conflict-free.
+    __shared__ __align__(8) unsigned long long xbar;
+    const uint32_t xbar_u = smem_u32(&xbar);
+    const uint32_t xbytes = (uint32_t)(64 * D * sizeof(double));
+    if (tid == 0) {
+        mbar_init(xbar_u, 1);
+        fence_mbar_init();
+        mbar_expect_tx(xbar_u, 2 * xbytes);
+        bulk_load_1d(smem_u32(Xi), p.X + (size_t)ti * 64 * D, xbytes, xbar_u);
+        bulk_load_1d(smem_u32(Ts), p.X + (size_t)tj * 64 * D, xbytes, xbar_u);
     }
     const double* kp = p.kp + (size_t)b * p.kp_stride;
     for (int e = tid; e < 2 * D + 1; e += 256) prm[e] = (p.ard || e < 3) ? kp[e] : 0.0;
+    __syncthreads();                       // the barrier is initialised (and prm written) before anybody waits on it
+    mbar_wait(xbar_u, 0);
+    for (int e = tid; e < 64 * D; e += 256) {
+        const int r = e / D, k = e % D;
+        XjT[k * 64 + r] = Ts[e];
+    }
     __syncthreads();
     const double sigma = prm[0];
     const int tx = tid & 31, ty = tid >> 5;
