@@ -337,6 +337,32 @@ def test_fused_forward_substitution_and_fused_transpose_match_the_separate_kerne
     assert np.array_equal(out['one_cta'][3], cval) and np.array_equal(out['one_cta'][4][2], f)
 
 
+def test_results_do_not_depend_on_the_task_schedule():
+    """Race check without a sanitizer: the persistent factorisation hands tasks to whichever CTA is free, so a different
+    grid (APM_FLOW_GRID) or a repeated run changes which CTA runs which task, which stage buffers and which right-hand-side
+    slot it uses, and how the fused forward substitution / cluster solve interleave with the factorisation -- but never a
+    bit of the result."""
+    cases = ((330, 5, 9, 40), (768, 8, 16, 24))
+    for n, D, N, B in cases:
+        X, y, th = synth.make_dataset(n, D, seed=6)
+        rs = np.random.RandomState(12)
+        thetas = th[None] + 0.6 * rs.normal(size=(B, D + 1))
+        u = rs.normal(size=(B, n, N))
+        u2 = rs.normal(size=(B, n, N))
+        kw = dict(kernel='ard', max_chains=B, n_slots=B, max_nimp=N)
+        ref = None
+        for env in ({}, {'APM_FLOW_GRID': '37'}, {'APM_FLOW_GRID': '148'}, {'APM_FLOW_GRID': '296'}, {'APM_TRSV_CLUSTER_MAX': '0'}):
+            eng = _engine_with_env(env, X, y, **kw)
+            for rep in range(3):
+                val, ops, st = eng.estimate_full(thetas, u, np.arange(B))
+                cval, _ = eng.estimate_cached(np.arange(B), u2)
+                assert np.all(st == 0)
+                if ref is None:
+                    ref = (val, ops, cval)
+                assert np.array_equal(val, ref[0]) and np.array_equal(ops, ref[1]) and np.array_equal(cval, ref[2]), (n, env, rep)
+            eng.close()
+
+
 def test_device_resident_u_and_slot_roundtrip():
     import torch
     X, y, th = synth.make_dataset(150, 4, seed=9)
