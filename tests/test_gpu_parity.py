@@ -337,6 +337,35 @@ def test_fused_forward_substitution_and_fused_transpose_match_the_separate_kerne
     assert np.array_equal(out['one_cta'][3], cval) and np.array_equal(out['one_cta'][4][2], f)
 
 
+def test_reference_form_switches_agree_with_the_default_path():
+    """The switches that restore the reference's own forms -- two symmetric mat-vecs per Newton step (APM_FNEW_THR=0), explicit
+    C = K - Z Z^T with its own Cholesky (APM_EXPLICIT_COV, lpa.py:111-112 + est.py:209), no auxiliary stream (APM_NO_OVERLAP) --
+    still run on top of the fused factorisation kernels and agree with the default path to rounding."""
+    n, D, N, B = 330, 5, 9, 12
+    X, y, th = synth.make_dataset(n, D, seed=14)
+    rs = np.random.RandomState(3)
+    thetas = th[None] + 0.5 * rs.normal(size=(B, D + 1))
+    u = rs.normal(size=(B, n, N))
+    u2 = rs.normal(size=(B, n, N))
+    kw = dict(kernel='ard', max_chains=B, n_slots=B, max_nimp=N)
+    ref = None
+    for env in ({}, {'APM_FNEW_THR': '0'}, {'APM_EXPLICIT_COV': '1'}, {'APM_NO_OVERLAP': '1'},
+                {'APM_EXPLICIT_COV': '1', 'APM_FNEW_THR': '0', 'APM_NO_FUSED_FWD': '1'}):
+        eng = _engine_with_env(env, X, y, **kw)
+        val, ops, st = eng.estimate_full(thetas, u, np.arange(B))
+        cval, _ = eng.estimate_cached(np.arange(B), u2)
+        Kc, Cc, f, ld = eng.slot_export(2)
+        eng.close()
+        assert np.all(st == 0)
+        if ref is None:
+            ref = (val, ops, cval, Cc, f)
+            continue
+        assert np.array_equal(ops, ref[1]), env
+        assert np.max(np.abs(val - ref[0]) / np.abs(ref[0])) < 1e-10, env
+        assert np.max(np.abs(cval - ref[2]) / np.abs(ref[2])) < 1e-10, env
+        assert np.max(np.abs(Cc - ref[3])) < 1e-9 * np.max(np.abs(ref[3])) and np.max(np.abs(f - ref[4])) < 1e-9, env
+
+
 def test_results_do_not_depend_on_the_task_schedule():
     """Race check without a sanitizer: the persistent factorisation hands tasks to whichever CTA is free, so a different
     grid (APM_FLOW_GRID) or a repeated run changes which CTA runs which task, which stage buffers and which right-hand-side
