@@ -79,6 +79,7 @@ struct apm_ctx {
     // Cholesky factor is exactly what the factored covariance needs, so the converged chain skips the separate
     // SYRK + Cholesky of M' (and the chol(B) of that iteration).  APM_NO_HYBRID_NEWTON=1 disables it.
     bool hybrid_newton = true;
+    int flow_spin_ns = 64;              // back-off of the producer lanes' dependency polls in k_chol_flow (APM_FLOW_SPIN_NS)
     bool fused_fwd = true;              // forward substitution of the Newton solves inside k_chol_flow's diagonal tasks (APM_NO_FUSED_FWD=1: k_trsv2 does both halves)
     int trsv_cluster_max = 160;         // backward solve by a cluster of 4 CTAs per chain for batches of at most this many chains (APM_TRSV_CLUSTER_MAX; 0: never)
     bool fused_vt = true;               // k_chol_flow<true> also stores V = anti-transpose of L' (APM_NO_FUSED_VT=1: separate k_antitranspose)
@@ -347,6 +348,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
     c->hybrid_newton = getenv("APM_NO_HYBRID_NEWTON") == nullptr;
     c->fused_vt = getenv("APM_NO_FUSED_VT") == nullptr;
     c->fused_fwd = getenv("APM_NO_FUSED_FWD") == nullptr;
+    if (getenv("APM_FLOW_SPIN_NS")) c->flow_spin_ns = atoi(getenv("APM_FLOW_SPIN_NS"));
     if (getenv("APM_TRSV_CLUSTER_MAX")) c->trsv_cluster_max = atoi(getenv("APM_TRSV_CLUSTER_MAX"));
     if (getenv("APM_NEWTON_R0") && atoi(getenv("APM_NEWTON_R0")) > 0) c->newton_r0 = atoi(getenv("APM_NEWTON_R0"));
     if (getenv("APM_FNEW_THR")) c->fnew_thr = atof(getenv("APM_FNEW_THR"));
@@ -645,7 +647,7 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     q.status = c->dStatus; q.fail_code = fail_code; q.active = active; q.nchains = B;
     q.counter = c->dFlowCounter + 2 * set; q.progress = c->dFlow2Progress[set]; q.list = c->dFlow2Skip[set];
     q.diagpack = c->dDiagPack[set];
-    q.spin_ns = 64;
+    q.spin_ns = c->flow_spin_ns;
     q.lk_idx = syrk_slots; q.w = c->dVec[V_W]; q.w_bs = c->np;
     // the M' factorisations also leave V = anti-transpose of L' in the slot's L_C buffer (what the importance-sampling tail reads)
     q.vt_out = (syrk_slots && c->fused_vt) ? c->dSlotLC : nullptr; q.vt_bs = (long long)c->mat;
