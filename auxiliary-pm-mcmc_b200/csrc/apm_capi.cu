@@ -79,6 +79,8 @@ struct apm_ctx {
     // Cholesky factor is exactly what the factored covariance needs, so the converged chain skips the separate
     // SYRK + Cholesky of M' (and the chol(B) of that iteration).  APM_NO_HYBRID_NEWTON=1 disables it.
     bool hybrid_newton = true;
+    int flow_grid_small = 0;            // persistent grid of the 2-CTAs-per-SM instantiations of k_chol_flow
+    int flow_small_max = 200;           // batches of at most this many chains use them (APM_FLOW_SMALL_MAX; 0: never)
     int flow_spin_ns = 64;              // back-off of the producer lanes' dependency polls in k_chol_flow (APM_FLOW_SPIN_NS)
     bool fused_fwd = true;              // forward substitution of the Newton solves inside k_chol_flow's diagonal tasks (APM_NO_FUSED_FWD=1: k_trsv2 does both halves)
     int trsv_cluster_max = 160;         // backward solve by a cluster of 4 CTAs per chain for batches of at most this many chains (APM_TRSV_CLUSTER_MAX; 0: never)
@@ -196,10 +198,14 @@ static int check_launch(apm_ctx* c, const char* what) {
 static int g_attr_done = 0;
 static int set_kernel_attrs() {
     if (g_attr_done) return APM_OK;
-    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
-    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
+    CU_TRY(cudaFuncSetAttribute(k_chol_flow<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_syrk_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     CU_TRY(cudaFuncSetAttribute(k_trsm_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
@@ -339,9 +345,11 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
         }
         int occ = 0, sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_flow<true, true>, CF_THREADS, CF_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chol_flow<true, true, 3>, CF_THREADS, CF_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;
         c->flow2_grid = occ * sms;
-        if (getenv("APM_FLOW_GRID") && atoi(getenv("APM_FLOW_GRID")) > 0) c->flow2_grid = atoi(getenv("APM_FLOW_GRID"));
+        c->flow_grid_small = (occ < 2 ? occ : 2) * sms;
+        if (getenv("APM_FLOW_GRID") && atoi(getenv("APM_FLOW_GRID")) > 0) c->flow2_grid = c->flow_grid_small = atoi(getenv("APM_FLOW_GRID"));
+        if (getenv("APM_FLOW_SMALL_MAX")) c->flow_small_max = atoi(getenv("APM_FLOW_SMALL_MAX"));
     }
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
@@ -658,15 +666,25 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     k_chol_flow_init<<<(B * c->nb + 255) / 256, 256, 0, st>>>(q.counter, q.progress, q.list, c->dStatus, active, B, c->nb, c->dWork,
                                                              syrk_slots ? c->dWork + 1 : nullptr, fwd ? q.yprog : nullptr);
     APM_TRY(check_launch(c, "k_chol_flow_init"));
-    const int grid = c->flow2_grid < total_tasks ? c->flow2_grid : total_tasks;
+    // batches whose launches are bound by the chains' critical paths run on the instantiations compiled for 2 CTAs per SM
+    // (see k_chol_flow); the choice depends on the batch size only and changes no arithmetic
+    const bool small = B <= c->flow_small_max;
+    const int cap = small ? c->flow_grid_small : c->flow2_grid;
+    const int grid = cap < total_tasks ? cap : total_tasks;
     prof_begin(c, KID_CHOL);
+#define APM_LAUNCH_FLOW(SY, FW)                                                                                      \
+    do {                                                                                                              \
+        if (small) k_chol_flow<SY, FW, 2><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);     \
+        else k_chol_flow<SY, FW, 3><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);           \
+    } while (0)
     if (syrk_slots) {
-        if (fwd) k_chol_flow<true, true><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
-        else k_chol_flow<true, false><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
+        if (fwd) APM_LAUNCH_FLOW(true, true);
+        else APM_LAUNCH_FLOW(true, false);
     } else {
-        if (fwd) k_chol_flow<false, true><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
-        else k_chol_flow<false, false><<<grid, CF_THREADS, CF_SMEM_BYTES, st>>>(*tm, *tms, c->tmSlotLK16, q);
+        if (fwd) APM_LAUNCH_FLOW(false, true);
+        else APM_LAUNCH_FLOW(false, false);
     }
+#undef APM_LAUNCH_FLOW
     return check_launch(c, "k_chol_flow");
 }
 

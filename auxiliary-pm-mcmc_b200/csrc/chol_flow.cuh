@@ -44,7 +44,9 @@ constexpr int CF_STAGES = APM_CF_STAGES;
 constexpr int DP_LBLOCKS = 36;                         // lower 8x8 blocks (q >= p) of a 64x64 triangle, block (q,p) at q(q+1)/2 + p
 constexpr int DP_DOUBLES = (DP_LBLOCKS + 8) * 64;      // + inverses of the 8 diagonal 8x8 blocks
 constexpr int DP_BYTES = DP_DOUBLES * 8;               // 22528
-constexpr int CF_CTRL_BYTES = 2560;                  // barriers / task slots / W or y of a stage (first KB) + two right-hand-side blocks
+// control block: barriers / task slots (512 B), W_r or y and b_r slices of the stages (128 B per stage each), two right-hand-side blocks
+constexpr int CF_WST_OFF = 512, CF_BST_OFF = CF_WST_OFF + CF_STAGES * 128, CF_RHS_OFF = CF_BST_OFF + CF_STAGES * 128;
+constexpr int CF_CTRL_BYTES = CF_RHS_OFF + 2 * 64 * 8;
 constexpr int CF_SMEM_BYTES = 1024 + CF_STAGES * 2 * CF_CHUNK_BYTES + DP_BYTES + CF_CTRL_BYTES;   // 1024: manual alignment slack
 
 __device__ __forceinline__ int dp_block(int q, int p) { return (q * (q + 1) / 2 + p) * 64; }
@@ -498,9 +500,13 @@ __device__ __forceinline__ void cf_store_antitransposed(const CfAcc& acc, double
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------
 // SYRK: the source is the fused M' = P (I + L_K^T W L_K) P (two instantiations keep the plain path free of its registers)
-// FWD: fused forward substitution (p.fwd_*); separate instantiations keep the plain factorisation free of its registers
-template <bool SYRK, bool FWD = false>
-__global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tms, const __grid_constant__ CUtensorMap tml,
+// FWD: fused forward substitution (p.fwd_*); separate instantiations keep the plain factorisation free of its registers.
+// MINCTAS: resident CTAs per SM the kernel is compiled for.  3 (128 registers, a few spills) keeps the tensor pipe busiest when
+// every CTA slot has independent tasks (>= ~200 chains); 2 (168 registers, no spills, grid 2 x SMs) runs every task faster and
+// wins when the launch is bound by the chains' critical paths (measured, 64 / 141 / 256 / 512 chains: k_chol 3.30 / 5.78 / 9.68 /
+// 18.69 ms per FULL estimate against 3.61 / 5.94 / 9.49 / 17.81).  Same arithmetic per task: the host picks by the batch size.
+template <bool SYRK, bool FWD = false, int MINCTAS = APM_CF_MIN_CTAS>
+__global__ void __launch_bounds__(CF_THREADS, MINCTAS) k_chol_flow(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tms, const __grid_constant__ CUtensorMap tml,
                                                                            CholFlowParams p) {
     extern __shared__ unsigned char cf_smem_raw[];
     const uint32_t raw = smem_u32(cf_smem_raw);
@@ -516,13 +522,12 @@ __global__ void __launch_bounds__(CF_THREADS, APM_CF_MIN_CTAS) k_chol_flow(const
     const uint32_t bar_dp_full = bar_tq_empty + 16, bar_dp_empty = bar_dp_full + 8;
     volatile CfTask* tq = reinterpret_cast<volatile CfTask*>(ctrl + 16 * CF_STAGES + 48);       // 2 descriptors
     double* red = reinterpret_cast<double*>(ctrl + 16 * CF_STAGES + 48 + 2 * sizeof(CfTask));   // 4 partial log-dets
-    double* wst = reinterpret_cast<double*>(ctrl + 512);                                         // W_r of a TN stage: [stage][16]
-    const uint32_t wst_u = ctrl_u + 512;
-    double* bst = reinterpret_cast<double*>(ctrl + 1024);                                        // b_r of a TN stage: [stage][16]
-    const uint32_t bst_u = ctrl_u + 1024;
-    double* fw_rhs = reinterpret_cast<double*>(ctrl + 1536);                                     // [2][64]: right-hand side block of a diag task (by task parity)
-    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= 512 && 512 + CF_STAGES * 128 <= 1024 && 1024 + CF_STAGES * 128 <= 1536 &&
-                  1536 + 2 * 64 * 8 <= CF_CTRL_BYTES, "control block too small");
+    double* wst = reinterpret_cast<double*>(ctrl + CF_WST_OFF);                                         // W_r of a TN stage: [stage][16]
+    const uint32_t wst_u = ctrl_u + CF_WST_OFF;
+    double* bst = reinterpret_cast<double*>(ctrl + CF_BST_OFF);                                        // b_r of a TN stage: [stage][16]
+    const uint32_t bst_u = ctrl_u + CF_BST_OFF;
+    double* fw_rhs = reinterpret_cast<double*>(ctrl + CF_RHS_OFF);                                     // [2][64]: right-hand side block of a diag task (by task parity)
+    static_assert(16 * CF_STAGES + 48 + 2 * sizeof(CfTask) + 4 * 8 <= CF_WST_OFF, "control block too small");
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {

@@ -156,8 +156,8 @@ int main(int argc, char** argv) {
                 if (r == 1) CK(cudaEventRecord(e0));
                 CK(cudaMemsetAsync(dstatus, 0, B * 4));
                 k_chol_flow_init<<<(B * nb + 255) / 256, 256>>>(p.counter, p.progress, p.list, dstatus, p.active, B, nb, nullptr, nullptr);
-                if (syrk) k_chol_flow<true><<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, tmK, tmLK16, p);
-                else k_chol_flow<false><<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, inplace ? tm1 : tmK, tmLK16, p);
+                if (syrk) k_chol_flow<true, false, 3><<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, tmK, tmLK16, p);
+                else k_chol_flow<false, false, 3><<<grid, CF_THREADS, CF_SMEM_BYTES>>>(tm1, inplace ? tm1 : tmK, tmLK16, p);
                 if (inplace && r >= 1) break;
             }
             CK(cudaEventRecord(e1));

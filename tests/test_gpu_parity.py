@@ -380,7 +380,9 @@ def test_results_do_not_depend_on_the_task_schedule():
         u2 = rs.normal(size=(B, n, N))
         kw = dict(kernel='ard', max_chains=B, n_slots=B, max_nimp=N)
         ref = None
-        for env in ({}, {'APM_FLOW_GRID': '37'}, {'APM_FLOW_GRID': '148'}, {'APM_FLOW_GRID': '296'}, {'APM_TRSV_CLUSTER_MAX': '0'}):
+        # ... and the instantiations compiled for 3 / 2 resident CTAs per SM (picked by the batch size: APM_FLOW_SMALL_MAX)
+        for env in ({}, {'APM_FLOW_GRID': '37'}, {'APM_FLOW_GRID': '148'}, {'APM_FLOW_GRID': '296'}, {'APM_TRSV_CLUSTER_MAX': '0'},
+                    {'APM_FLOW_SMALL_MAX': '0'}, {'APM_FLOW_SMALL_MAX': '100000'}):
             eng = _engine_with_env(env, X, y, **kw)
             for rep in range(3):
                 val, ops, st = eng.estimate_full(thetas, u, np.arange(B))
