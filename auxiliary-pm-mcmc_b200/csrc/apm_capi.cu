@@ -81,6 +81,7 @@ struct apm_ctx {
     bool hybrid_newton = true;
     int flow_grid_small = 0;            // persistent grid of the 2-CTAs-per-SM instantiations of k_chol_flow
     int flow_small_max = 200;           // batches of at most this many chains use them (APM_FLOW_SMALL_MAX; 0: never)
+    int newton_late_round = 4;          // Newton rounds from this index on (0-based) are expected to hold only stragglers (APM_NEWTON_LATE_ROUND)
     int flow_spin_ns = 64;              // back-off of the producer lanes' dependency polls in k_chol_flow (APM_FLOW_SPIN_NS)
     bool fused_fwd = true;              // forward substitution of the Newton solves inside k_chol_flow's diagonal tasks (APM_NO_FUSED_FWD=1: k_trsv2 does both halves)
     int trsv_cluster_max = 160;         // backward solve by a cluster of 4 CTAs per chain for batches of at most this many chains (APM_TRSV_CLUSTER_MAX; 0: never)
@@ -350,6 +351,7 @@ static int create_impl(const double* X, const double* y, int n, int D, int kerne
         c->flow_grid_small = (occ < 2 ? occ : 2) * sms;
         if (getenv("APM_FLOW_GRID") && atoi(getenv("APM_FLOW_GRID")) > 0) c->flow2_grid = c->flow_grid_small = atoi(getenv("APM_FLOW_GRID"));
         if (getenv("APM_FLOW_SMALL_MAX")) c->flow_small_max = atoi(getenv("APM_FLOW_SMALL_MAX"));
+        if (getenv("APM_NEWTON_LATE_ROUND")) c->newton_late_round = atoi(getenv("APM_NEWTON_LATE_ROUND"));
     }
     c->overlap_chol_k = getenv("APM_NO_OVERLAP") == nullptr;
     c->factored_cov = getenv("APM_EXPLICIT_COV") == nullptr;
@@ -615,7 +617,7 @@ static int build_K(apm_ctx* c, int B, int kind, double eps) {
 static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, const int* src_idx, double* dst,
                     long long dst_bs, const int* dst_idx, const double* scale, int add_identity, double* logdet_parts,
                     const int* logdet_idx, int fail_code, const int* active, double* inv_out = nullptr,
-                    const int* syrk_slots = nullptr, bool fwd = false) {
+                    const int* syrk_slots = nullptr, bool fwd = false, bool few_expected = false) {
     // fwd: the factorisation also solves L y = t for the right-hand side in dVec[V_T] (y -> dVec[V_S]): the forward half of
     // the Newton step's triangular solves, fused into the diagonal tasks
     // syrk_slots != null: the source is M' = P (I + L_K^T W L_K) P, accumulated on the fly from chol(K) in those slots and
@@ -668,7 +670,8 @@ static int run_chol(apm_ctx* c, int B, const double* src, long long src_bs, cons
     APM_TRY(check_launch(c, "k_chol_flow_init"));
     // batches whose launches are bound by the chains' critical paths run on the instantiations compiled for 2 CTAs per SM
     // (see k_chol_flow); the choice depends on the batch size only and changes no arithmetic
-    const bool small = B <= c->flow_small_max;
+    // (few_expected: a late Newton round, where only stragglers are left on typical data -- a full batch would lose 1-4 %)
+    const bool small = B <= c->flow_small_max || (few_expected && c->flow_small_max > 0);
     const int cap = small ? c->flow_grid_small : c->flow2_grid;
     const int grid = cap < total_tasks ? cap : total_tasks;
     prof_begin(c, KID_CHOL);
@@ -791,7 +794,7 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
             if (!matfree) APM_TRY(run_symv(c, B, nv.bvec, nv.Ws, nv.t, maskB));
             // L = chol(I + Ws K Ws)                                    (lpa.py:91-92)
             APM_TRY(run_chol(c, B, c->dK, (long long)c->mat, nullptr, c->dLB, (long long)c->mat, nullptr, nv.Ws, 1, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB, nullptr, c->fused_fwd));
+                             nullptr, APM_CHAIN_CHOL_B, maskB, c->dInvB, nullptr, c->fused_fwd, it >= c->newton_late_round));
             // s = L^-T L^-1 t ; a = b - Ws s                           (lpa.py:94)
             prof_begin(c, KID_TRSV);
             if (c->fused_fwd && B <= c->trsv_cluster_max)     // a batch of about one chain per SM or less: latency-bound, 4 CTAs per chain
@@ -829,7 +832,7 @@ static int run_newton(apm_ctx* c, int B, const int* dSlots = nullptr, bool lk_pe
             }
             // L' = chol(M'), M' = P (I + L_K^T W L_K) P built inside the factorisation from L_K and W (never stored)
             APM_TRY(run_chol(c, B, nullptr, 0, nullptr, c->dLB, (long long)c->mat, nullptr, nullptr, 0, c->dLdB,
-                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, dSlots, c->fused_fwd));
+                             nullptr, APM_CHAIN_CHOL_C, maskM, c->dInvB, dSlots, c->fused_fwd, it >= c->newton_late_round));
             // s' = M'^-1 t'
             prof_begin(c, KID_TRSV);
             if (c->fused_fwd && B <= c->trsv_cluster_max)     // a batch of about one chain per SM or less: latency-bound, 4 CTAs per chain

@@ -97,7 +97,7 @@ for r in data:
     if ms > 1.0:
         traffic.setdefault(name, []).append((ms, rd, wr))
 stall = [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio')]
-big = [r for r in data if '<0, 1>' in r[ix['Kernel Name']] and float(r[ix['gpu__time_duration.sum']].replace(',', '')) > 1.0]
+big = [r for r in data if '<0, 1' in r[ix['Kernel Name']] and float(r[ix['gpu__time_duration.sum']].replace(',', '')) > 1.0]
 if big and stall:
     r = big[0]
     o2 += ['', '## Warp stall reasons of a full-batch Newton-round launch (`<0, 1>`), warps per issue-active cycle', '', '| reason | ratio |', '|---|---:|']
@@ -112,7 +112,7 @@ for name, v in traffic.items():
     rec[name] = {'ms': ms, 'dram_read': rd, 'dram_write': wr}
 tf = os.path.join(P, 'ncu_traffic.json')
 allrec = json.load(open(tf)) if os.path.isfile(tf) else {}
-key = [k for k in rec if '<0, 1>' in k]
+key = [k for k in rec if '<0, 1' in k]
 if key:
     x = rec[key[0]]
     allrec['k_chol:n=768:chains=256'] = {
