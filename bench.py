@@ -695,7 +695,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='skip the BASELINE configurations 2-5 (and the CPU sampler legs of the reference arm)')
     ap.add_argument('--quick-configs', action='store_true', help='shorter sampler runs / fewer sweep points in the configurations')
-    ap.add_argument('--apm-iters', type=int, default=100, help='iterations of the batched ESS+RDSS sampler leg (chains drain at the end of a run: short runs understate the steady state)')
+    ap.add_argument('--apm-iters', type=int, default=200, help='iterations of the batched ESS+RDSS sampler leg (chains drain at the end of a run: short runs understate the steady state)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
